@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""Benchmark of the batched-HMM hot path (BASELINE.json metric: state-transitions/s = B*T*N^2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+
+Default workload = BASELINE.json configs[1] ("c2"): GaussianHMM, 8 states, forward-backward
+log-likelihood of 16,384 synthetic sequences of T=2,048 per GPU (weak scaling: every rank owns its
+own 16,384 sequences; the path shards by sequence with no data-path collective).  One "step" =
+one pass of the hot path over the batch.  Prints ONE JSON line (rank 0).
+
+  value     device-resident throughput: inputs already in HBM, CUDA events around K steps
+  e2e       the same metric through the public API (GaussianHMM.log_likelihood_batch) with pinned
+            HOST buffers: H2D of the observations + kernels + D2H of the log-likelihoods per step
+  roofline  dominant kernel against the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle (NumPy port of the reference algorithm) timed on the host cores on a
+            bounded sample -- a reported baseline only
+`--impl reference` times that CPU implementation alone with all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, N, M, B per GPU, T)
+    "c2": ("GaussianHMM N=8 D=1 forward-backward log-likelihood, B=16384 T=2048 per GPU", 8, 0, 16384, 2048),
+    "c3": ("DiscreteHMM N=64 M=256 Viterbi, B=65536 T=4096", 64, 256, 65536, 4096),
+    "c4": ("DiscreteHMM N=128 M=1024 Baum-Welch iteration, B=131072 T=512 per GPU", 128, 1024, 131072, 512),
+    "c5": ("GaussianHMM N=1024 D=1 forward-backward, B=4096 T=1024", 1024, 0, 4096, 1024),
+}
+CFG_INDEX = {"c2": 2, "c3": 3, "c4": 4, "c5": 5}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------- synthetic data
+def make_gaussian(N, B, T, seed):
+    import kerehmm_b200 as K
+    np.random.seed(seed)
+    model = K.GaussianHMM(N, 1, random_transitions=True, random_emissions=True)
+    mean = np.array([d.mean for d in model.emissionDistributions])
+    rng = np.random.default_rng(1000 + seed)
+    obs = np.empty((B, T), dtype=np.float32)
+    step = max(1, (1 << 24) // T)
+    for b0 in range(0, B, step):
+        nb = min(step, B - b0)
+        obs[b0:b0 + nb] = mean[rng.integers(0, N, size=(nb, T))] + rng.standard_normal((nb, T), dtype=np.float32)
+    return model, obs
+
+
+def make_discrete(N, M, B, T, seed):
+    import kerehmm_b200 as K
+    np.random.seed(seed)
+    model = K.DiscreteHMM(N, M, random_transitions=True, random_emissions=True)
+    rng = np.random.default_rng(1000 + seed)
+    dt = np.uint8 if M <= 256 else np.uint16
+    obs = rng.integers(0, M, size=(B, T), dtype=dt)
+    return model, obs
+
+
+# ------------------------------------------------------------------------------ CPU legs
+def _cpu_chunk(args):
+    kind, params, obs = args
+    from oracle import hmm_oracle as O
+    t0 = time.perf_counter()
+    if kind == "c2" or kind == "c5":
+        pi, A, mean, sd = params
+        E = O.emissions_gaussian_1d(mean, sd, obs.astype(np.float64))
+        O.fwdbwd_loglik_batch(pi, A, E)
+    elif kind == "c3":
+        pi, A, Bm = params
+        with np.errstate(divide="ignore"):
+            O.viterbi(pi, A, Bm, obs.astype(np.int64))
+    elif kind == "c4":
+        pi, A, Bm = params
+        O.mstep_discrete(O.batch_stats_discrete(pi, A, Bm, obs.astype(np.int64)))
+    return time.perf_counter() - t0
+
+
+CPU_SAMPLE = {"c2": (8192, 2048), "c3": (16, 512), "c4": (16, 128), "c5": (8, 16)}
+
+
+def cpu_params(kind, model):
+    pi, A = model.initialProbabilities.copy(), model.transitionMatrix.copy()
+    if isinstance(model, _HostModel):
+        return (pi, A, model._mean, model._sd) if kind in ("c2", "c5") else (pi, A, model._B)
+    if kind in ("c2", "c5"):
+        return (pi, A, np.array([d.mean for d in model.emissionDistributions], dtype=np.float64),
+                np.array([d.variance for d in model.emissionDistributions], dtype=np.float64))
+    return (pi, A, model.emission_matrix())
+
+
+def cpu_leg(kind, model, obs, cores):
+    """Oracle port on a bounded sample split over `cores` worker processes -> (transitions/s, sample text)."""
+    import multiprocessing as mp
+    N = model.nStates
+    sb, st = CPU_SAMPLE[kind]
+    sb, st = min(sb, obs.shape[0]), min(st, obs.shape[1])
+    sample = np.ascontiguousarray(obs[:sb, :st])
+    params = cpu_params(kind, model)
+    cores = max(1, min(cores, sb))
+    chunks = [(kind, params, c) for c in np.array_split(sample, cores) if len(c)]
+    t0 = time.perf_counter()
+    if len(chunks) == 1:
+        _cpu_chunk(chunks[0])
+    else:
+        with mp.get_context("fork").Pool(len(chunks)) as pool:
+            pool.map(_cpu_chunk, chunks)
+    dt = time.perf_counter() - t0
+    return sb * st * N * N / dt, "oracle port (NumPy fp64), B=%d T=%d at the workload's N, %d processes" % (
+        sb, st, len(chunks)), len(chunks), dt
+
+
+# ------------------------------------------------------------------------ clock sampling
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []          # the upper half = samples under load
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import kerehmm_b200 as K
+    from kerehmm_b200 import _lib, engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    engine.require_cuda()
+    kind = args.workload
+    desc, N, M, B, T = WORKLOADS[kind]
+    if args.batch:
+        B = args.batch
+    seed = CFG_INDEX[kind]
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    hbm_peak, peak_src = peaks()
+
+    launches_per_step = 0
+    extra = {}
+    if kind in ("c2",):
+        model, obs_h = make_gaussian(N, B, T, seed)
+        if rank:      # different sequences per rank, same model
+            obs_h = make_gaussian(N, B, T, seed + 100 * rank)[1]
+        p = model._params()
+        dm = engine.DeviceModel(p, torch.float32)
+        host_sets = [torch.from_numpy(obs_h).pin_memory(), torch.from_numpy(obs_h[::-1].copy()).pin_memory()]
+        dev_sets = [h.to(dev) for h in host_sets]
+        ll = torch.empty((B,), dtype=torch.float64, device=dev)
+        llb = torch.empty((B,), dtype=torch.float64, device=dev)
+
+        def step(i):
+            o = dev_sets[i & 1]
+            _lib.call("khmm_fwdbwd_loglik_gauss_f32", B, T, N, engine.ptr(dm.pi), engine.ptr(dm.A),
+                      engine.ptr(dm.mean), engine.ptr(dm.sd), engine.ptr(o), _lib.F32, None, engine.ptr(ll),
+                      engine.ptr(llb), stream.cuda_stream)
+
+        def e2e_step(i):
+            out = model.log_likelihood_batch(host_sets[i & 1])
+            return out[0]
+
+        launches_per_step = 1
+        algo_bytes = B * T * 4 + 2 * B * 8          # observations once + two float64 results per sequence
+        h2d, d2h = B * T * 4, 2 * B * 8
+        dominant = "fwdbwd_small_kernel<8, gauss>"
+        l2_note = "two alternating 134 MB observation sets (268 MB > 126 MB L2)"
+        dtype = "f32"
+    elif kind == "c3":
+        model, obs_h = make_discrete(N, M, B, T, seed)
+        host_sets = [torch.from_numpy(obs_h).pin_memory()]
+        ob = engine.prepare_obs(host_sets[0].to(dev), symbols=True)
+        p = model._params()
+
+        def step(i):
+            engine.viterbi(p, ob, torch.uint8)
+
+        def e2e_step(i):
+            return model.viterbi_batch(host_sets[0], path_dtype="uint8")[1]
+
+        launches_per_step = 2
+        algo_bytes = B * T * (1 + N + 1 + 1)         # obs + N backpointer bytes written + 1 read + path byte
+        h2d, d2h = B * T, B * T + B * 8
+        dominant = "viterbi_generic_kernel<uint8>"
+        l2_note = "backpointer workspace 17 GB per step (>> L2)"
+        dtype = "f64"
+    elif kind == "c4":
+        model, obs_h = make_discrete(N, M, B, T, seed + 100 * rank)
+        model = make_discrete(N, M, 1, 1, seed)[0]
+        host_sets = [torch.from_numpy(obs_h.view(np.int16)).pin_memory()]
+        ob = engine.prepare_obs(host_sets[0].to(dev), symbols=True, u16_bits=True)
+
+        def step(i):
+            from kerehmm_b200 import dist as kdist
+            p_ = model._params()
+            counts = engine.estep_discrete(p_, ob, torch.float32)
+            kdist.all_reduce_counts(counts.buf)
+            model._assign(*engine.mstep_discrete(p_, counts))
+
+        def e2e_step(i):
+            o = engine.prepare_obs(host_sets[0], symbols=True, u16_bits=True)
+            p_ = model._params()
+            counts = engine.estep_discrete(p_, o, torch.float32)
+            from kerehmm_b200 import dist as kdist
+            kdist.all_reduce_counts(counts.buf)
+            model._assign(*engine.mstep_discrete(p_, counts))
+            return counts.buf[-3:].cpu()
+
+        launches_per_step = 4
+        algo_bytes = B * T * 2
+        h2d, d2h = B * T * 2, 24
+        dominant = "xi_accumulate_kernel / backward_generic_kernel<estep>"
+        l2_note = "alpha/V stashes of tens of GB per step (>> L2)"
+        dtype = "f32"
+    elif kind == "c5":
+        Bg = B // world if args.strong else B
+        model, obs_h = make_gaussian(N, Bg, T, seed)
+        host_sets = [torch.from_numpy(obs_h).pin_memory()]
+        ob = engine.prepare_obs(host_sets[0].to(dev), symbols=False)
+        p = model._params()
+        B = Bg
+
+        def step(i):
+            a, c, _ = engine.forward(p, ob, torch.float32)
+            engine.backward(p, ob, torch.float32, c, alpha=a, want_beta=False, want_gamma=True,
+                            gamma_kind=_lib.GAMMA_POSTERIOR)
+
+        def e2e_step(i):
+            return model.posterior_batch(host_sets[0])[1]
+
+        launches_per_step = 2
+        algo_bytes = B * T * 4 + B * T * N * 4
+        h2d, d2h = B * T * 4, B * T * N * 4 + B * 8
+        dominant = "forward_generic_kernel / backward_generic_kernel"
+        l2_note = "alpha/gamma 2 x 17 GB per step (>> L2)"
+        dtype = "f32"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    ms_per_step = ms / args.steps
+    transitions = float(B) * T * N * N * world
+    value = transitions / (ms_per_step * 1e-3)
+
+    # ---- end-to-end timing through the public API with host buffers
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        r = e2e_step(i)
+        _ = r if isinstance(r, np.ndarray) else r
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = transitions / float(t_e.item())
+
+    out = None
+    if rank == 0:
+        achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+        out = {
+            "metric": "state-transitions/sec (B*T*N^2)", "value": value, "unit": "transitions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong" if (kind == "c5" and args.strong) else "weak",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic (seeded; reference-compatible random model init)",
+            "config": {"workload": desc, "name": kind, "N": N, "M": M, "B_per_gpu": B, "T": T,
+                       "sharding": "sequences sharded across ranks, no data-path collective" if kind != "c4"
+                       else "sequences sharded across ranks, one count all-reduce per iteration",
+                       "l2": l2_note},
+            "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(t_e.item()) * 1e3, "api": "kerehmm_b200 public class API, pinned host buffers"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "kernel": dominant, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes},
+            "clocks": clocks,
+        }
+        if kind in ("c2", "c5"):
+            flops = transitions / world * 4.0          # 2 (forward) + 2 (backward) flop per transition
+            out["roofline"]["fp32_simt"] = {"achieved_tflops": flops / (ms_per_step * 1e-3) / 1e12,
+                                            "nominal_peak_tflops": 74.4,
+                                            "note": "matrix-vector FMAs only; the recursion is FP32-issue bound, "
+                                                    "not HBM bound (DESIGN.md)"}
+        if world == 1 and not args.no_cpu:
+            cv, sample, cores, dt = cpu_leg(kind, model, obs_h if kind != "c4" else obs_h, args.cpu_cores)
+            out["cpu_baseline"] = {"value": cv, "unit": "transitions/s", "cores": cores, "kind": "port",
+                                   "sample": sample, "seconds": dt}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return out
+
+
+def run_reference(args):
+    """The reference's algorithm on the host cores (oracle port; the reference itself is Python-2
+    source that cannot be shipped or imported on the box -- DESIGN.md)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind = args.workload
+    desc, N, M, B, T = WORKLOADS[kind]
+    seed = CFG_INDEX[kind]
+    sb, st = CPU_SAMPLE[kind]
+    if kind in ("c2", "c5"):
+        model, obs = make_gaussian_host(N, sb, st, seed)
+    else:
+        model, obs = make_discrete_host(N, M, sb, st, seed)
+    cores = args.cpu_cores
+    for _ in range(args.warmup):
+        cpu_leg(kind, model, obs, cores)
+    vals, secs = [], []
+    for _ in range(args.steps):
+        v, sample, used, dt = cpu_leg(kind, model, obs, cores)
+        vals.append(v); secs.append(dt)
+    value = float(np.mean(vals))
+    out = {"impl": "reference", "metric": "state-transitions/sec (B*T*N^2)", "value": value, "unit": "transitions/s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic (seeded; same generator as the GPU arm)",
+           "config": {"workload": desc, "name": kind, "N": N, "M": M, "B_per_gpu": B, "T": T},
+           "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": used, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+class _HostModel:
+    """Parameter holder for the CPU arm: built from the oracle's generators (same RNG draw order as
+    the package constructors, tests/test_oracle_golden.py), so no product code is on this path."""
+
+    def __init__(self, pi, A, mean=None, sd=None, Bm=None):
+        self.initialProbabilities, self.transitionMatrix, self.nStates = pi, A, A.shape[0]
+        self._mean, self._sd, self._B = mean, sd, Bm
+
+
+def make_gaussian_host(N, B, T, seed):
+    from oracle import hmm_oracle as O
+    np.random.seed(seed)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    rng = np.random.default_rng(1000 + seed)
+    obs = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T), dtype=np.float32)).astype(np.float32)
+    return _HostModel(pi, A, mean=mean, sd=sd), obs
+
+
+def make_discrete_host(N, M, B, T, seed):
+    from oracle import hmm_oracle as O
+    np.random.seed(seed)
+    pi, A, Bm = O.random_discrete_model(N, M)
+    rng = np.random.default_rng(1000 + seed)
+    obs = rng.integers(0, M, size=(B, T), dtype=np.uint8 if M <= 256 else np.uint16)
+    return _HostModel(pi, A, Bm=Bm), obs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override sequences per GPU (debug)")
+    ap.add_argument("--strong", action="store_true", help="c5: split the fixed batch across ranks")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-cores", type=int, default=os.cpu_count() or 1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

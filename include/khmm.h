@@ -1,0 +1,231 @@
+/*
+ * khmm.h -- C ABI of libkhmm.so, the B200 (sm_100a) engine behind kerehmm_b200.
+ *
+ * The reference (keryil/kereHMM) is pure Python and has NO plugin / FFI interface
+ * (SURVEY.md 8(b)); its boundary is the method surface of AbstractHMM / DiscreteHMM /
+ * GaussianHMM.  Each entry point below names the reference method whose inner loops it
+ * replaces (paths relative to the reference checkout).  The Python classes in
+ * kerehmm_b200/ bind these through ctypes (kerehmm_b200/_lib.py); INTEGRATION.md shows
+ * the stub a kereHMM maintainer would add to call them from the reference classes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer on `device`
+ *     unless its name ends in `_host`; the caller owns all buffers (no allocation inside);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream;
+ *   - return value: 0 = KHMM_OK, otherwise an error code; khmm_last_error() returns a
+ *     thread-local message;
+ *   - batch layout: observations obs[B][T] (row per sequence), optional lengths[B]
+ *     (int32, NULL = every sequence has T steps, 1 <= lengths[b] <= T);
+ *     alpha/beta/gamma/V are [B][T][N], scale is [B][T], per-sequence results are [B];
+ *   - transition matrix A[N][N] is row-major "from i to j" exactly as
+ *     AbstractHMM.transitionMatrix; AT is its transpose; the discrete emission table is
+ *     SYMBOL-MAJOR Bsm[M][N] (Bsm[k][j] = emissionDistributions[j].probabilities[k]) so
+ *     that the N emission values of one observation are contiguous;
+ *   - 1 <= N <= 1024.
+ */
+#ifndef KHMM_H
+#define KHMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KHMM_OK 0
+#define KHMM_ERR_INVALID 1     /* bad argument */
+#define KHMM_ERR_CUDA 2        /* CUDA runtime error (message has the cudaError string) */
+#define KHMM_ERR_UNSUPPORTED 3 /* shape outside what the kernels cover */
+
+/* dtype codes (observations, paths) */
+#define KHMM_U8 0
+#define KHMM_U16 1
+#define KHMM_I32 2
+#define KHMM_I64 3
+#define KHMM_F32 4
+#define KHMM_F64 5
+
+/* gamma flavours for khmm_backward_* */
+#define KHMM_GAMMA_REFERENCE 0 /* alpha*beta*c_t, AbstractHMM.gamma (abstract_hmm.py:291-297) */
+#define KHMM_GAMMA_POSTERIOR 1 /* alpha*beta: the true state posterior */
+
+typedef void *khmm_stream_t;
+
+const char *khmm_last_error(void);
+int khmm_version(void);
+/* Fills SM count / compute capability / memory of `device`; fails if there is no CUDA device. */
+int khmm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+
+/* out[c][r] = in[r][c] for a rows x cols matrix (used for AT and for state-major <-> symbol-major). */
+int khmm_transpose_f32(int rows, int cols, const float *in, float *out, khmm_stream_t stream);
+int khmm_transpose_f64(int rows, int cols, const double *in, double *out, khmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Viterbi -- AbstractHMM.viterbi_path (kerehmm/abstract_hmm.py:203-239), discrete emissions.
+ * float64 max-plus DP in the reference's association order, first-index argmax ties, psi
+ * backpointers kept in HBM (1 byte per entry when N <= 256, else 2), then a backtrace.
+ * logpi[N], logA[N][N], logBsm[M][N] are the HOST-computed np.log tables (device copies):
+ * log is never evaluated on the device so results are bit-identical to the reference.
+ * backptr: workspace of khmm_viterbi_workspace_bytes(B,T,N) bytes.
+ * path: [B][T] of path_dtype (U8/U16/I32/I64); logp: [B] float64 = max_j delta[len-1][j].
+ */
+size_t khmm_viterbi_workspace_bytes(int64_t B, int64_t T, int N);
+int khmm_viterbi_discrete_f64(int64_t B, int64_t T, int N, int M,
+                              const double *logpi, const double *logA, const double *logBsm,
+                              const void *obs, int obs_dtype, const int32_t *lengths,
+                              void *backptr, size_t backptr_bytes,
+                              void *path, int path_dtype, double *logp,
+                              khmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Scaled forward -- AbstractHMM.forward (abstract_hmm.py:250-285) with the emission
+ * evaluation (abstract_hmm.py:353-367 -> distribution.py:35-36 / :151-155) fused in.
+ * alpha (may be NULL), scale (may be NULL; c_t is the SUM, not its reciprocal), loglik
+ * (may be NULL; [B] float64 = sum_t log c_t, the true log P(O)).
+ * Gaussian: D = 1, pdf = exp(-((x-mean)/sd)^2/2)/(sd*sqrt(2*pi)); `sd` is the reference's
+ * `variance` attribute, which it passes to scipy as the scale.
+ */
+int khmm_forward_discrete_f32(int64_t B, int64_t T, int N, int M,
+                              const float *pi, const float *A, const float *Bsm,
+                              const void *obs, int obs_dtype, const int32_t *lengths,
+                              float *alpha, float *scale, double *loglik, khmm_stream_t stream);
+int khmm_forward_discrete_f64(int64_t B, int64_t T, int N, int M,
+                              const double *pi, const double *A, const double *Bsm,
+                              const void *obs, int obs_dtype, const int32_t *lengths,
+                              double *alpha, double *scale, double *loglik, khmm_stream_t stream);
+int khmm_forward_gauss_f32(int64_t B, int64_t T, int N,
+                           const float *pi, const float *A, const float *mean, const float *sd,
+                           const void *obs, int obs_dtype, const int32_t *lengths,
+                           float *alpha, float *scale, double *loglik, khmm_stream_t stream);
+int khmm_forward_gauss_f64(int64_t B, int64_t T, int N,
+                           const double *pi, const double *A, const double *mean, const double *sd,
+                           const void *obs, int obs_dtype, const int32_t *lengths,
+                           double *alpha, double *scale, double *loglik, khmm_stream_t stream);
+/* Emissions given as a dense matrix E[B][T][N] (multivariate Gaussians, user emissions). */
+int khmm_forward_dense_f32(int64_t B, int64_t T, int N, const float *pi, const float *A, const float *E,
+                           const int32_t *lengths, float *alpha, float *scale, double *loglik,
+                           khmm_stream_t stream);
+int khmm_forward_dense_f64(int64_t B, int64_t T, int N, const double *pi, const double *A, const double *E,
+                           const int32_t *lengths, double *alpha, double *scale, double *loglik,
+                           khmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Scaled backward -- AbstractHMM.backward (abstract_hmm.py:327-351), ghmm convention:
+ * beta[len-1] = 1, beta[t][i] = sum_j A[i][j] b_j(o_{t+1}) beta[t+1][j] / c_{t+1}.
+ * Takes AT (transpose of A) so the per-state reads coalesce.  scale: forward's c [B][T].
+ * beta (may be NULL).  If alpha != NULL and gamma != NULL the kernel also writes
+ * gamma = alpha*beta*c (KHMM_GAMMA_REFERENCE, abstract_hmm.py:291-297) or alpha*beta
+ * (KHMM_GAMMA_POSTERIOR) in the same pass.
+ */
+int khmm_backward_discrete_f32(int64_t B, int64_t T, int N, int M, const float *AT, const float *Bsm,
+                               const void *obs, int obs_dtype, const int32_t *lengths, const float *scale,
+                               const float *alpha, float *beta, float *gamma, int gamma_kind,
+                               khmm_stream_t stream);
+int khmm_backward_discrete_f64(int64_t B, int64_t T, int N, int M, const double *AT, const double *Bsm,
+                               const void *obs, int obs_dtype, const int32_t *lengths, const double *scale,
+                               const double *alpha, double *beta, double *gamma, int gamma_kind,
+                               khmm_stream_t stream);
+int khmm_backward_gauss_f32(int64_t B, int64_t T, int N, const float *AT, const float *mean, const float *sd,
+                            const void *obs, int obs_dtype, const int32_t *lengths, const float *scale,
+                            const float *alpha, float *beta, float *gamma, int gamma_kind,
+                            khmm_stream_t stream);
+int khmm_backward_gauss_f64(int64_t B, int64_t T, int N, const double *AT, const double *mean, const double *sd,
+                            const void *obs, int obs_dtype, const int32_t *lengths, const double *scale,
+                            const double *alpha, double *beta, double *gamma, int gamma_kind,
+                            khmm_stream_t stream);
+int khmm_backward_dense_f32(int64_t B, int64_t T, int N, const float *AT, const float *E,
+                            const int32_t *lengths, const float *scale,
+                            const float *alpha, float *beta, float *gamma, int gamma_kind,
+                            khmm_stream_t stream);
+int khmm_backward_dense_f64(int64_t B, int64_t T, int N, const double *AT, const double *E,
+                            const int32_t *lengths, const double *scale,
+                            const double *alpha, double *beta, double *gamma, int gamma_kind,
+                            khmm_stream_t stream);
+
+/* AbstractHMM.gamma (abstract_hmm.py:291-297) on caller-supplied arrays: out = alpha*beta*scale[...,None]
+ * (KHMM_GAMMA_REFERENCE) or alpha*beta (KHMM_GAMMA_POSTERIOR); rows = B*T. */
+int khmm_gamma_f32(int64_t rows, int N, const float *alpha, const float *beta, const float *scale, float *out,
+                   int gamma_kind, khmm_stream_t stream);
+int khmm_gamma_f64(int64_t rows, int N, const double *alpha, const double *beta, const double *scale, double *out,
+                   int gamma_kind, khmm_stream_t stream);
+/* AbstractHMM.zi (abstract_hmm.py:299-325) materialised for ONE sequence (API compatibility; the
+ * training path never materialises it): zi[t][i][j] = alpha[t][i]*A[i][j]*E[t+1][j]*beta[t+1][j],
+ * t < T-1, with E the dense emission matrix [T][N] and the reference's left-to-right product order. */
+int khmm_zi_f64(int64_t T, int N, const double *A, const double *E, const double *alpha, const double *beta,
+                double *zi, khmm_stream_t stream);
+/* Dense emission matrix E[b][t][j] = b_j(o_{b,t}) (AbstractHMM.emission_probability(None, o),
+ * abstract_hmm.py:362-366) for discrete tables and 1-D Gaussians. */
+int khmm_emissions_discrete_f64(int64_t B, int64_t T, int N, int M, const double *Bsm, const void *obs,
+                                int obs_dtype, double *E, khmm_stream_t stream);
+int khmm_emissions_gauss_f64(int64_t B, int64_t T, int N, const double *mean, const double *sd, const void *obs,
+                             int obs_dtype, double *E, khmm_stream_t stream);
+/* Full-covariance Gaussians (distribution.py:153): means[N][D], Linv[N][D][D] = inverse of the lower
+ * Cholesky factor of each covariance (row-major, lower triangular), lognorm[N] =
+ * -0.5*(D*log(2*pi) + log det cov); obs[B][T][D] (f32/f64).  E = exp(lognorm - 0.5*|Linv (x-mean)|^2). */
+int khmm_emissions_gauss_full_f64(int64_t B, int64_t T, int N, int D, const double *means, const double *Linv,
+                                  const double *lognorm, const void *obs, int obs_dtype, double *E,
+                                  khmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused forward-backward log-likelihood (no alpha/beta in HBM) for small state spaces
+ * (N <= KHMM_SMALL_N_MAX): one thread per sequence, A and the alpha/beta rows in registers,
+ * emission evaluation fused.  loglik[B] = sum_t log c_t (forward); loglik_bwd[B] (may be
+ * NULL: forward only) = the same likelihood recovered from the backward recursion, which runs
+ * concurrently with its own scaling s_t: log(sum_i pi_i b_i(o_0) beta_0(i)) = sum_t log s_t +
+ * log(pi . w_0)  -- equal to loglik up to rounding.
+ */
+#define KHMM_SMALL_N_MAX 16
+int khmm_fwdbwd_loglik_gauss_f32(int64_t B, int64_t T, int N,
+                                 const float *pi, const float *A, const float *mean, const float *sd,
+                                 const void *obs, int obs_dtype, const int32_t *lengths,
+                                 double *loglik, double *loglik_bwd, khmm_stream_t stream);
+int khmm_fwdbwd_loglik_discrete_f32(int64_t B, int64_t T, int N, int M,
+                                    const float *pi, const float *A, const float *Bsm,
+                                    const void *obs, int obs_dtype, const int32_t *lengths,
+                                    double *loglik, double *loglik_bwd, khmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Baum-Welch E-step -- the statistics DiscreteHMM.do_pass forms (discrete_hmm.py:117-159)
+ * from forward, backward, AbstractHMM.zi (abstract_hmm.py:299-325) and gamma (:291-297),
+ * with the reference's weighting (gamma carries c_t, zi carries c_{t+1}, gamma[0] is
+ * overwritten by smooth1d(gamma[0])), summed over the sequences
+ * of the batch (Q8).  Call order for one batch chunk:
+ *   khmm_forward_discrete_*   -> alpha, scale (stash)
+ *   khmm_estep_discrete_*     -> adds into counts[], writes V[b][t][j] = b_j(o_t) beta_t(j)
+ *   khmm_xi_accumulate_*      -> adds sum_{b,t<len-1} alpha[b][t][i] * V[b][t+1][j] into counts.xi
+ * counts is ONE float64 buffer of khmm_counts_len(N,M) doubles (zeroed by the caller before
+ * the first chunk; this is the buffer that is all-reduced across GPUs):
+ *   [ pi: N | xi_raw: N*N | gam: N | emis_num (symbol-major [M][N]): M*N | emis_den: N |
+ *     loglik_sum: 1 | nseq: 1 | flags: 1 ]
+ * xi_raw is sum alpha (x) V WITHOUT the elementwise A factor (the M-step applies it).
+ * flags != 0 means some sequence hit the reference's ZeroDivisionError case
+ * (every gamma[0] entry < 1e-10, util.py:57-58).
+ */
+size_t khmm_counts_len(int N, int M);
+int khmm_estep_discrete_f32(int64_t B, int64_t T, int N, int M, const float *AT, const float *Bsm,
+                            const void *obs, int obs_dtype, const int32_t *lengths,
+                            const float *alpha, const float *scale, float *V, double *counts,
+                            khmm_stream_t stream);
+int khmm_estep_discrete_f64(int64_t B, int64_t T, int N, int M, const double *AT, const double *Bsm,
+                            const void *obs, int obs_dtype, const int32_t *lengths,
+                            const double *alpha, const double *scale, double *V, double *counts,
+                            khmm_stream_t stream);
+int khmm_xi_accumulate_f32(int64_t B, int64_t T, int N, const int32_t *lengths,
+                           const float *alpha, const float *V, double *xi_raw, khmm_stream_t stream);
+int khmm_xi_accumulate_f64(int64_t B, int64_t T, int N, const int32_t *lengths,
+                           const double *alpha, const double *V, double *xi_raw, khmm_stream_t stream);
+
+/* M-step on the device -- discrete_hmm.py:132-161 + util.smooth_probabilities (util.py:39-63),
+ * float64, operation for operation.  Reads counts (after the all-reduce), A (old, [N][N]);
+ * writes pi_new[N], A_new[N][N], B_new state-major [N][M].  status[0] (device int32) gets a
+ * bit mask: 1 = ZeroDivisionError case, 2 = the 2-D smoothing ValueError case (2 <= k < n
+ * small entries in a row, util.py:51-53), 4 = a sanity_check (isclose(sum,1)) failure. */
+int khmm_mstep_discrete_f64(int N, int M, const double *counts, const double *A,
+                            double *pi_new, double *A_new, double *B_new, int32_t *status,
+                            khmm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KHMM_H */

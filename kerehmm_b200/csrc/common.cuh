@@ -1,0 +1,111 @@
+// Shared device/host helpers for libkhmm (sm_100a).  See include/khmm.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/khmm.h"
+
+namespace khmm {
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define KHMM_CUDA_CHECK(expr)                                    \
+    do {                                                         \
+        cudaError_t _e = (expr);                                 \
+        if (_e != cudaSuccess) return khmm::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define KHMM_LAUNCH_CHECK(name)                                       \
+    do {                                                              \
+        cudaError_t _e = cudaGetLastError();                          \
+        if (_e != cudaSuccess) return khmm::cuda_fail(_e, name);      \
+    } while (0)
+
+#define KHMM_REQUIRE(cond, ...)              \
+    do {                                     \
+        if (!(cond)) {                       \
+            khmm::set_error(__VA_ARGS__);    \
+            return KHMM_ERR_INVALID;         \
+        }                                    \
+    } while (0)
+
+int sm_count();  // cached SM count of the current device (148 on B200)
+
+// ---------------------------------------------------------------- observation loads
+__device__ __forceinline__ int load_symbol(const void *p, int dtype, int64_t idx) {
+    switch (dtype) {
+        case KHMM_U8: return (int)((const uint8_t *)p)[idx];
+        case KHMM_U16: return (int)((const uint16_t *)p)[idx];
+        case KHMM_I32: return ((const int32_t *)p)[idx];
+        default: return (int)((const int64_t *)p)[idx];
+    }
+}
+template <typename R>
+__device__ __forceinline__ R load_real(const void *p, int dtype, int64_t idx) {
+    return dtype == KHMM_F32 ? (R)((const float *)p)[idx] : (R)((const double *)p)[idx];
+}
+
+// ---------------------------------------------------------------- emission functors
+// eval(b, t, j) = b_j(o_{b,t}); `prep(j)` caches per-state constants when a thread owns state j.
+template <typename R>
+struct DiscreteEmis {
+    const R *Bsm;  // [M][N]
+    const void *obs;
+    int obs_dtype;
+    int N, M;
+    int64_t T;
+    struct Obs { int sym; };
+    __device__ __forceinline__ Obs load(int64_t b, int64_t t) const {
+        int s = load_symbol(obs, obs_dtype, b * T + t);
+        // out-of-alphabet symbols index nothing valid in the reference either (IndexError);
+        // clamp so a bad pad value cannot fault the kernel.
+        s = s < 0 ? 0 : (s >= M ? M - 1 : s);
+        return Obs{s};
+    }
+    __device__ __forceinline__ R eval(const Obs &o, int j) const { return __ldg(Bsm + (int64_t)o.sym * N + j); }
+};
+
+template <typename R>
+struct GaussEmis {
+    const R *mean, *sd;
+    const void *obs;
+    int obs_dtype;
+    int N;
+    int64_t T;
+    struct Obs { R x; };
+    __device__ __forceinline__ Obs load(int64_t b, int64_t t) const {
+        return Obs{load_real<R>(obs, obs_dtype, b * T + t)};
+    }
+    // scipy.stats.norm(loc, scale).pdf(x) = exp(-z^2/2)/sqrt(2*pi)/scale, z=(x-loc)/scale
+    __device__ __forceinline__ R eval(const Obs &o, int j) const {
+        R s = __ldg(sd + j);
+        R z = (o.x - __ldg(mean + j)) / s;
+        if (sizeof(R) == 8)
+            return (R)(exp(-0.5 * (double)z * (double)z) * 0.3989422804014327 / (double)s);
+        return (R)(expf(-0.5f * (float)z * (float)z) * 0.3989422804014327f / (float)s);
+    }
+};
+
+template <typename R>
+struct DenseEmis {
+    const R *E;  // [B][T][N]
+    int N;
+    int64_t T;
+    struct Obs { const R *row; };
+    __device__ __forceinline__ Obs load(int64_t b, int64_t t) const { return Obs{E + (b * T + t) * N}; }
+    __device__ __forceinline__ R eval(const Obs &o, int j) const { return __ldg(o.row + j); }
+};
+
+// ------------------------------------------------------------------- warp reductions
+template <typename R>
+__device__ __forceinline__ R warp_sum(R v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace khmm

@@ -1,0 +1,133 @@
+"""DiscreteHMM -- kerehmm/discrete_hmm.py:11-227 on the B200 engine."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine
+from .abstract_hmm import AbstractHMM
+from .distribution import DiscreteDistribution
+from .util import DELTA_P
+
+
+class DiscreteHMM(AbstractHMM):
+    """HMM with one categorical emission table per state.
+
+    `DiscreteHMM(number_of_states, alphabet_size, state_labels=None, random_emissions=False,
+    verbose=False, random_transitions=False)` -- same constructor, attributes and RNG draw order
+    as the reference (discrete_hmm.py:16-22)."""
+
+    def __init__(self, number_of_states, alphabet_size, state_labels=None, random_emissions=False, *args, **kwargs):
+        super(DiscreteHMM, self).__init__(number_of_states, state_labels, *args, **kwargs)
+        self.alphabetSize = alphabet_size
+        self.emissionDistributions = np.array(
+            [DiscreteDistribution(n=alphabet_size, randomize=random_emissions) for _ in range(self.nStates)])
+        self.sanity_check()
+
+    def sanity_check(self):
+        """Takes no arguments, like the reference's override (discrete_hmm.py:24-27)."""
+        super(DiscreteHMM, self).sanity_check()
+        for dist in self.emissionDistributions:
+            assert np.isclose(dist.probabilities.sum(), 1.)
+
+    # -------------------------------------------------------------------------- packing
+    def emission_matrix(self):
+        """State-major (N, M) table assembled from the per-state distribution objects."""
+        return np.stack([np.asarray(d.probabilities, dtype=np.float64) for d in self.emissionDistributions])
+
+    def _params(self):
+        return engine.ModelParams(kind="discrete", pi=np.asarray(self.initialProbabilities, dtype=np.float64),
+                                  A=np.asarray(self.transitionMatrix, dtype=np.float64), B=self.emission_matrix())
+
+    def _symbols(self):
+        return True
+
+    def _assign(self, pi, A, Bm):
+        """Install re-estimated parameters the way do_pass does (discrete_hmm.py:168-173):
+        new arrays for pi/A, new distribution objects, a sanity_check after each."""
+        self.initialProbabilities = pi
+        self.sanity_check()
+        dists = []
+        for i in range(self.nStates):
+            d = DiscreteDistribution(n=self.alphabetSize)
+            d.probabilities = Bm[i].copy()
+            dists.append(d)
+        self.emissionDistributions = np.array(dists)
+        self.sanity_check()
+        self.transitionMatrix = A
+        self.sanity_check()
+
+    # ------------------------------------------------------------------ state alignment
+    def compute_emission_mapping_score(self, to_hmm, mapping):
+        score = 0.
+        for fro, to in zip(self.emissionDistributions[mapping], to_hmm.emissionDistributions):
+            assert isinstance(fro, DiscreteDistribution)
+            score += fro.b_distance(to)
+        return score
+
+    def initialize_parameters(self, observations):
+        pass
+
+    # ---------------------------------------------------------------------- Baum-Welch
+    def do_pass(self, observations, verbose=False):
+        """One Baum-Welch pass on ONE sequence with the reference's exact (non-textbook) weighting
+        (discrete_hmm.py:95-191): float64 kernels for forward, the
+        backward/E-step statistics, the xi contraction and the M-step.  Mutates
+        `initialProbabilities`, `transitionMatrix`, `emissionDistributions`."""
+        if verbose:
+            print("do_pass() called\n  observation: {}\n  initial: {}\n  transition: {}\n  emission: {}".format(
+                observations, self.initialProbabilities, self.transitionMatrix, self.emission_matrix()))
+        if np.asarray(observations).ndim != 1:
+            raise ValueError("do_pass takes one sequence; use do_pass_batch for a batch")
+        t = engine.require_cuda()
+        p = self._params()
+        ob = self._prep(observations, single=True)
+        counts = engine.estep_discrete(p, ob, t.float64)
+        self._assign(*engine.mstep_discrete(p, counts))
+        if verbose:
+            print("do_pass() returning\n  initial: {}\n  transition: {}\n  emission: {}".format(
+                self.initialProbabilities, self.transitionMatrix, self.emission_matrix()))
+
+    def estep_batch(self, observations, lengths=None, dtype="float32", chunk=None, counts=None):
+        """Reference-weighted sufficient statistics summed over a batch as an
+        `engine.Counts` on the device -- the buffer that is all-reduced across GPUs."""
+        ob = self._prep(observations, lengths)
+        return engine.estep_discrete(self._params(), ob, self._real(dtype), counts=counts, chunk=chunk)
+
+    def do_pass_batch(self, observations, lengths=None, dtype="float32", chunk=None, group=None):
+        """One Baum-Welch pass over a batch of sequences (this rank's shard when torch.distributed
+        is initialised: the packed counts are all-reduced before the M-step, which every rank then
+        performs identically).  Returns the summed log-likelihood of the batch under the OLD
+        parameters."""
+        from . import dist
+        p = self._params()
+        counts = self.estep_batch(observations, lengths, dtype, chunk)
+        dist.all_reduce_counts(counts.buf, group=group)
+        loglik = float(counts.buf[counts.sl["tail"]][0].item())
+        self._assign(*engine.mstep_discrete(p, counts))
+        return loglik
+
+    def train_batch(self, observations, lengths=None, iterations=10, dtype="float32", chunk=None, group=None,
+                    tol=None):
+        """`iterations` batched Baum-Welch passes; returns the list of per-pass log-likelihoods.
+        Stops early when `tol` is given and the log-likelihood gain drops below it."""
+        history = []
+        for _ in range(iterations):
+            history.append(self.do_pass_batch(observations, lengths, dtype, chunk, group))
+            if tol is not None and len(history) > 1 and history[-1] - history[-2] <= tol:
+                break
+        return history
+
+    def setup_left_to_right(self, set_emissions=False):
+        """discrete_hmm.py:196-227: A[s,s] = A[s,s+1] = 0.5 - (N-2)*DELTA_P (cyclic), rest DELTA_P."""
+        n = self.nStates
+        self.transitionMatrix[:] = DELTA_P
+        for state in range(n):
+            self.transitionMatrix[state, state] = - DELTA_P * (n - 2) + .5
+            self.transitionMatrix[state, (state + 1) % n] = - DELTA_P * (n - 2) + .5
+        self.initialProbabilities = np.array([1 - DELTA_P * (n - 1)] + [DELTA_P] * (n - 1))
+        if set_emissions:
+            for state in range(n):
+                distribution = self.emissionDistributions[state]
+                probs = np.full_like(distribution.probabilities, DELTA_P)
+                probs[state] = 1 - (n - 1) * DELTA_P
+                distribution.probabilities = probs

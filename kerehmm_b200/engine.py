@@ -1,0 +1,400 @@
+"""Device-side glue between the Python HMM classes and libkhmm (include/khmm.h).
+
+PyTorch is used here only for device memory, streams and host<->device copies; every
+computation on the hot path is a libkhmm kernel.  There is no CPU fallback: without a CUDA
+device or without the built library these functions raise.
+
+Input rule for the batched API: observations given as a NumPy array / CPU tensor ("host
+buffers") are copied to the device inside the call and results come back as NumPy arrays;
+observations given as a CUDA tensor are used in place and results stay on the device as torch
+tensors.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise RuntimeError("kerehmm_b200 needs a CUDA device (built for B200 / sm_100a); "
+                           "there is no CPU fallback.")
+    _lib.lib()
+    return t
+
+
+def device():
+    t = require_cuda()
+    return t.device("cuda", t.cuda.current_device())
+
+
+def stream_ptr():
+    return torch().cuda.current_stream().cuda_stream
+
+
+def ptr(x):
+    return None if x is None else x.data_ptr()
+
+
+# ------------------------------------------------------------------------- model packing
+@dataclass
+class ModelParams:
+    """Host float64 parameters of one HMM, in the reference's conventions."""
+    kind: str                       # "discrete" | "gauss" | "gauss_full"
+    pi: np.ndarray                  # (N,)
+    A: np.ndarray                   # (N, N)
+    B: Optional[np.ndarray] = None  # discrete: (N, M) state-major, as the reference stores it
+    mean: Optional[np.ndarray] = None   # gauss: (N,) ; gauss_full: (N, D)
+    sd: Optional[np.ndarray] = None     # gauss: (N,) -- the reference's `variance` attribute
+    cov: Optional[np.ndarray] = None    # gauss_full: (N, D, D)
+
+    @property
+    def N(self):
+        return int(self.A.shape[0])
+
+    @property
+    def M(self):
+        return int(self.B.shape[1])
+
+
+def _dev(a, dtype):
+    t = torch()
+    return t.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device(), non_blocking=False)
+
+
+class DeviceModel:
+    """Device copies of the parameters in one real type (re-made on every call: the reference's
+    parameters are plain mutable arrays, SURVEY.md 8(b) ownership)."""
+
+    def __init__(self, p: ModelParams, real):
+        t = torch()
+        self.p, self.real = p, real
+        self.suffix = "f32" if real == t.float32 else "f64"
+        self.pi = _dev(p.pi, real)
+        self.A = _dev(p.A, real)
+        self.AT = _dev(p.A.T, real)
+        if p.kind == "discrete":
+            self.Bsm = _dev(p.B.T, real)          # symbol-major [M][N]
+        elif p.kind == "gauss":
+            self.mean = _dev(p.mean, real)
+            self.sd = _dev(p.sd, real)
+
+
+_INT_CODES = {"uint8": _lib.U8, "int16": _lib.U16, "uint16": _lib.U16, "int32": _lib.I32, "int64": _lib.I64}
+
+
+@dataclass
+class Obs:
+    tensor: object      # torch tensor on the device
+    code: int           # libkhmm dtype code
+    B: int
+    T: int
+    on_host: bool       # the caller passed host memory -> results go back to the host
+    lengths: object = None
+    h2d_bytes: int = 0
+
+
+def _as_tensor(x):
+    t = torch()
+    if isinstance(x, t.Tensor):
+        return x
+    a = np.asarray(x)
+    if a.dtype == np.uint16:            # torch has no first-class uint16: ship the bits as int16
+        a = a.view(np.int16)
+    if a.dtype == np.int8:
+        a = a.astype(np.int16)
+    if a.dtype.kind == "u" and a.dtype.itemsize > 2:
+        a = a.astype(np.int64)
+    if a.dtype == np.bool_ or a.dtype.kind not in "iuf":
+        raise TypeError("observations must be numeric, got %s" % a.dtype)
+    return t.from_numpy(np.ascontiguousarray(a))
+
+
+def prepare_obs(obs, symbols: bool, lengths=None, feature_dims: int = 0, u16_bits: bool = False) -> Obs:
+    """Move a batch of observations to the device.  symbols=True: integer symbols (B, T);
+    else real observations (B, T) or (B, T, D)."""
+    t = require_cuda()
+    was_u16 = (not isinstance(obs, t.Tensor)) and np.asarray(obs).dtype == np.uint16
+    x = _as_tensor(obs)
+    on_host = not x.is_cuda
+    want_nd = 3 if feature_dims else 2
+    if x.dim() != want_nd:
+        raise ValueError("expected observations with %d dims (batch, time%s), got shape %s"
+                         % (want_nd, ", features" if feature_dims else "", tuple(x.shape)))
+    if symbols:
+        if x.dtype.is_floating_point:
+            # the reference indexes tables with the observation, which fails for floats (Q10)
+            raise IndexError("only integers are valid symbols for a discrete emission table")
+        name = str(x.dtype).replace("torch.", "")
+        if name not in _INT_CODES:
+            x = x.to(t.int64)
+            name = "int64"
+        code = _INT_CODES[name]
+        if name == "int16" and not (was_u16 or u16_bits):
+            x = x.to(t.int32)
+            code = _lib.I32
+    else:
+        if not x.dtype.is_floating_point:
+            x = x.to(t.float32)
+        if x.dtype not in (t.float32, t.float64):
+            x = x.to(t.float32)
+        code = _lib.F32 if x.dtype == t.float32 else _lib.F64
+    h2d = 0
+    if on_host:
+        h2d = x.numel() * x.element_size()
+        x = x.to(device(), non_blocking=True)
+    x = x.contiguous()
+    B, T = int(x.shape[0]), int(x.shape[1])
+    if T < 1:
+        raise ValueError("sequences must have at least one observation")
+    L = None
+    if lengths is not None:
+        la = np.asarray(lengths.cpu() if isinstance(lengths, t.Tensor) else lengths).astype(np.int64)
+        if la.shape != (B,):
+            raise ValueError("lengths must have shape (B,)")
+        if B and (la.min() < 1 or la.max() > T):
+            raise ValueError("lengths must lie in [1, T]")
+        L = t.as_tensor(la.astype(np.int32)).to(device())
+    return Obs(tensor=x, code=code, B=B, T=T, on_host=on_host, lengths=L, h2d_bytes=h2d)
+
+
+def finish(ob: Obs, *tensors):
+    """Return results on the side the observations came from."""
+    if ob.on_host:
+        out = tuple(None if x is None else x.cpu().numpy() for x in tensors)
+    else:
+        out = tensors
+    return out if len(out) != 1 else out[0]
+
+
+# ------------------------------------------------------------------------------ kernels
+def _emission_args(dm: DeviceModel):
+    k = dm.p.kind
+    if k == "discrete":
+        return "discrete", (dm.p.M,), (ptr(dm.Bsm),)
+    if k == "gauss":
+        return "gauss", (), (ptr(dm.mean), ptr(dm.sd))
+    raise ValueError(k)
+
+
+def dense_emissions(p: ModelParams, ob: Obs):
+    """E[B][T][N] float64 on the device (abstract_hmm.py:362-366 batched)."""
+    t = require_cuda()
+    N = p.N
+    E = t.empty((ob.B, ob.T, N), dtype=t.float64, device=device())
+    if p.kind == "discrete":
+        Bsm = _dev(p.B.T, t.float64)
+        _lib.call("khmm_emissions_discrete_f64", ob.B, ob.T, N, p.M, ptr(Bsm), ptr(ob.tensor), ob.code, ptr(E),
+                  stream_ptr())
+    elif p.kind == "gauss":
+        mean, sd = _dev(p.mean, t.float64), _dev(p.sd, t.float64)
+        _lib.call("khmm_emissions_gauss_f64", ob.B, ob.T, N, ptr(mean), ptr(sd), ptr(ob.tensor), ob.code, ptr(E),
+                  stream_ptr())
+    else:
+        D = p.mean.shape[1]
+        Ls = np.linalg.cholesky(p.cov)
+        Linv = np.stack([np.linalg.inv(L) for L in Ls])
+        lognorm = -0.5 * (D * np.log(2.0 * np.pi) + 2.0 * np.log(np.diagonal(Ls, axis1=1, axis2=2)).sum(axis=1))
+        dm_, dl, dn = _dev(p.mean, t.float64), _dev(Linv, t.float64), _dev(lognorm, t.float64)
+        _lib.call("khmm_emissions_gauss_full_f64", ob.B, ob.T, N, D, ptr(dm_), ptr(dl), ptr(dn), ptr(ob.tensor),
+                  ob.code, ptr(E), stream_ptr())
+    return E
+
+
+def forward(p: ModelParams, ob: Obs, real, want_alpha=True, want_scale=True, want_loglik=True):
+    """Scaled forward on the device -> (alpha|None, scale|None, loglik|None) device tensors."""
+    t = require_cuda()
+    dm = DeviceModel(p, real)
+    N, dev = p.N, device()
+    alpha = t.empty((ob.B, ob.T, N), dtype=real, device=dev) if want_alpha else None
+    scale = t.empty((ob.B, ob.T), dtype=real, device=dev) if want_scale else None
+    loglik = t.empty((ob.B,), dtype=t.float64, device=dev) if want_loglik else None
+    if p.kind == "gauss_full":
+        E = dense_emissions(p, ob).to(real)
+        _lib.call("khmm_forward_dense_" + dm.suffix, ob.B, ob.T, N, ptr(dm.pi), ptr(dm.A), ptr(E), ptr(ob.lengths),
+                  ptr(alpha), ptr(scale), ptr(loglik), stream_ptr())
+        return alpha, scale, loglik
+    name, ints, ptrs = _emission_args(dm)
+    _lib.call("khmm_forward_%s_%s" % (name, dm.suffix), ob.B, ob.T, N, *ints, ptr(dm.pi), ptr(dm.A), *ptrs,
+              ptr(ob.tensor), ob.code, ptr(ob.lengths), ptr(alpha), ptr(scale), ptr(loglik), stream_ptr())
+    return alpha, scale, loglik
+
+
+def backward(p: ModelParams, ob: Obs, real, scale, alpha=None, want_beta=True, want_gamma=False,
+             gamma_kind=_lib.GAMMA_REFERENCE):
+    """Scaled backward (+ optional fused gamma) -> (beta|None, gamma|None)."""
+    t = require_cuda()
+    dm = DeviceModel(p, real)
+    N, dev = p.N, device()
+    beta = t.empty((ob.B, ob.T, N), dtype=real, device=dev) if want_beta else None
+    gamma = t.empty((ob.B, ob.T, N), dtype=real, device=dev) if want_gamma else None
+    if p.kind == "gauss_full":
+        E = dense_emissions(p, ob).to(real)
+        _lib.call("khmm_backward_dense_" + dm.suffix, ob.B, ob.T, N, ptr(dm.AT), ptr(E), ptr(ob.lengths), ptr(scale),
+                  ptr(alpha), ptr(beta), ptr(gamma), gamma_kind, stream_ptr())
+        return beta, gamma
+    name, ints, ptrs = _emission_args(dm)
+    _lib.call("khmm_backward_%s_%s" % (name, dm.suffix), ob.B, ob.T, N, *ints, ptr(dm.AT), *ptrs, ptr(ob.tensor),
+              ob.code, ptr(ob.lengths), ptr(scale), ptr(alpha), ptr(beta), ptr(gamma), gamma_kind, stream_ptr())
+    return beta, gamma
+
+
+def fwdbwd_loglik_small(p: ModelParams, ob: Obs, both=True):
+    """Fused forward(+backward) log-likelihood for N <= 16, fp32 -> (loglik, loglik_bwd|None)."""
+    t = require_cuda()
+    if p.N > _lib.SMALL_N_MAX:
+        raise ValueError("fused log-likelihood kernel covers N <= %d" % _lib.SMALL_N_MAX)
+    dm = DeviceModel(p, t.float32)
+    dev = device()
+    ll = t.empty((ob.B,), dtype=t.float64, device=dev)
+    llb = t.empty((ob.B,), dtype=t.float64, device=dev) if both else None
+    if p.kind == "gauss":
+        _lib.call("khmm_fwdbwd_loglik_gauss_f32", ob.B, ob.T, p.N, ptr(dm.pi), ptr(dm.A), ptr(dm.mean), ptr(dm.sd),
+                  ptr(ob.tensor), ob.code, ptr(ob.lengths), ptr(ll), ptr(llb), stream_ptr())
+    elif p.kind == "discrete":
+        _lib.call("khmm_fwdbwd_loglik_discrete_f32", ob.B, ob.T, p.N, p.M, ptr(dm.pi), ptr(dm.A), ptr(dm.Bsm),
+                  ptr(ob.tensor), ob.code, ptr(ob.lengths), ptr(ll), ptr(llb), stream_ptr())
+    else:
+        raise ValueError("fused log-likelihood kernel needs discrete or 1-D Gaussian emissions")
+    return ll, llb
+
+
+_PATH_CODES = {"uint8": _lib.U8, "int16": _lib.U16, "int32": _lib.I32, "int64": _lib.I64}
+
+
+def viterbi(p: ModelParams, ob: Obs, path_dtype=None):
+    """Bit-exact float64 Viterbi -> (path[B][T], logp[B]) device tensors.  The log tables are
+    taken on the HOST with np.log, exactly what abstract_hmm.py:218,227,229 evaluates."""
+    t = require_cuda()
+    if p.kind != "discrete":
+        raise IndexError("viterbi_path needs integer observations (discrete emissions); "
+                         "the reference fails on float observations too (abstract_hmm.py:234-237)")
+    N, M, dev = p.N, p.M, device()
+    with np.errstate(divide="ignore"):
+        logpi, logA, logBsm = np.log(p.pi), np.log(p.A), np.log(p.B.T)
+    d_logpi, d_logA, d_logBsm = _dev(logpi, t.float64), _dev(logA, t.float64), _dev(logBsm, t.float64)
+    path_dtype = path_dtype or t.int64
+    pname = str(path_dtype).replace("torch.", "")
+    path = t.zeros((ob.B, ob.T), dtype=path_dtype, device=dev)
+    logp = t.empty((ob.B,), dtype=t.float64, device=dev)
+    ws_bytes = _lib.lib().khmm_viterbi_workspace_bytes(ob.B, ob.T, N)
+    ws = t.empty((ws_bytes,), dtype=t.uint8, device=dev)
+    _lib.call("khmm_viterbi_discrete_f64", ob.B, ob.T, N, M, ptr(d_logpi), ptr(d_logA), ptr(d_logBsm),
+              ptr(ob.tensor), ob.code, ptr(ob.lengths), ptr(ws), ws_bytes, ptr(path), _PATH_CODES[pname],
+              ptr(logp), stream_ptr())
+    return path, logp
+
+
+def gamma(alpha, beta, scale, kind=_lib.GAMMA_REFERENCE):
+    t = require_cuda()
+    out = t.empty_like(alpha)
+    suffix = "f32" if alpha.dtype == t.float32 else "f64"
+    N = alpha.shape[-1]
+    _lib.call("khmm_gamma_" + suffix, alpha.numel() // N, N, ptr(alpha), ptr(beta), ptr(scale), ptr(out), kind,
+              stream_ptr())
+    return out
+
+
+def zi_single(A, E, alpha, beta):
+    """Materialised zi for one sequence (float64 device tensors) -> (T-1, N, N)."""
+    t = require_cuda()
+    T, N = alpha.shape
+    out = t.empty((max(T - 1, 0), N, N), dtype=t.float64, device=device())
+    _lib.call("khmm_zi_f64", T, N, ptr(A), ptr(E), ptr(alpha), ptr(beta), ptr(out), stream_ptr())
+    return out
+
+
+# --------------------------------------------------------------------------- Baum-Welch
+class Counts:
+    """View helpers over the packed float64 count buffer (layout in include/khmm.h)."""
+
+    def __init__(self, N, M, buf=None):
+        t = require_cuda()
+        self.N, self.M = N, M
+        n = _lib.lib().khmm_counts_len(N, M)
+        self.buf = buf if buf is not None else t.zeros((n,), dtype=t.float64, device=device())
+        o = 0
+        self.sl = {}
+        for name, size in (("pi", N), ("xi", N * N), ("gam", N), ("emis_num", M * N), ("emis_den", N), ("tail", 3)):
+            self.sl[name] = slice(o, o + size)
+            o += size
+
+    def host(self):
+        h = self.buf.cpu().numpy()
+        N, M = self.N, self.M
+        return dict(pi=h[self.sl["pi"]], xi_raw=h[self.sl["xi"]].reshape(N, N), gam=h[self.sl["gam"]],
+                    emis_num=h[self.sl["emis_num"]].reshape(M, N).T, emis_den=h[self.sl["emis_den"]],
+                    loglik=h[self.sl["tail"]][0], nseq=h[self.sl["tail"]][1], flags=h[self.sl["tail"]][2])
+
+
+def estep_chunk_size(B, T, N, esize, reserve=0.75):
+    """How many sequences fit at once: alpha + V stashes [B][T][N] and scale [B][T]."""
+    t = torch()
+    free, _ = t.cuda.mem_get_info()
+    per_seq = T * N * esize * 2 + T * esize + 64
+    return int(max(1, min(B, (free * reserve) // per_seq)))
+
+
+def estep_discrete(p: ModelParams, ob: Obs, real, counts: Counts = None, chunk=None):
+    """Accumulate the reference-weighted Baum-Welch statistics of a batch into `counts`."""
+    t = require_cuda()
+    if p.kind != "discrete":
+        raise NotImplementedError("Baum-Welch is defined for discrete emissions "
+                                  "(GaussianHMM.do_pass is broken in the reference, SURVEY.md Q9)")
+    dm = DeviceModel(p, real)
+    N, M, dev = p.N, p.M, device()
+    counts = counts or Counts(N, M)
+    esize = 4 if real == t.float32 else 8
+    chunk = chunk or estep_chunk_size(ob.B, ob.T, N, esize)
+    xi_ptr = counts.buf[counts.sl["xi"]].data_ptr()
+    sfx = dm.suffix
+    alpha = t.empty((min(chunk, ob.B), ob.T, N), dtype=real, device=dev)
+    V = t.empty_like(alpha)
+    scale = t.empty((min(chunk, ob.B), ob.T), dtype=real, device=dev)
+    for b0 in range(0, ob.B, chunk):
+        nb = min(chunk, ob.B - b0)
+        obs_c = ob.tensor[b0:b0 + nb]
+        len_c = None if ob.lengths is None else ob.lengths[b0:b0 + nb]
+        _lib.call("khmm_forward_discrete_" + sfx, nb, ob.T, N, M, ptr(dm.pi), ptr(dm.A), ptr(dm.Bsm), ptr(obs_c),
+                  ob.code, ptr(len_c), ptr(alpha), ptr(scale), None, stream_ptr())
+        _lib.call("khmm_estep_discrete_" + sfx, nb, ob.T, N, M, ptr(dm.AT), ptr(dm.Bsm), ptr(obs_c), ob.code,
+                  ptr(len_c), ptr(alpha), ptr(scale), ptr(V), ptr(counts.buf), stream_ptr())
+        _lib.call("khmm_xi_accumulate_" + sfx, nb, ob.T, N, ptr(len_c), ptr(alpha), ptr(V), xi_ptr, stream_ptr())
+    return counts
+
+
+def mstep_discrete(p: ModelParams, counts: Counts):
+    """Device M-step -> (pi, A, B) float64 NumPy; raises what the reference would raise."""
+    t = require_cuda()
+    N, M, dev = p.N, p.M, device()
+    A_old = _dev(p.A, t.float64)
+    pi_new = t.empty((N,), dtype=t.float64, device=dev)
+    A_new = t.empty((N, N), dtype=t.float64, device=dev)
+    B_new = t.empty((N, M), dtype=t.float64, device=dev)
+    status = t.zeros((1,), dtype=t.int32, device=dev)
+    _lib.call("khmm_mstep_discrete_f64", N, M, ptr(counts.buf), ptr(A_old), ptr(pi_new), ptr(A_new), ptr(B_new),
+              ptr(status), stream_ptr())
+    st = int(status.item())
+    if st & 1:
+        raise ZeroDivisionError("float division by zero")          # util.py:57-58 with k == n
+    if st & 2:
+        raise ValueError("operands could not be broadcast together "
+                         "(smooth_probabilities 2-D path with 2 <= k < n small entries, util.py:51-53)")
+    if st & 4:
+        raise AssertionError("sanity_check failed: a re-estimated distribution does not sum to 1")
+    return pi_new.cpu().numpy(), A_new.cpu().numpy(), B_new.cpu().numpy()

@@ -1,0 +1,400 @@
+"""GPU parity: the CUDA path (through the Python classes -> ctypes -> libkhmm C ABI) against the
+CPU oracle and the reference's golden vectors.  Integer results (Viterbi paths) must be bit-exact,
+as must the float64 Viterbi log-probability; float64 recursions agree to ~1e-12, float32 ones to
+the 1e-5 relative bound BASELINE.json states."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from conftest import gcase
+from oracle import hmm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+F32_RTOL = 1e-5          # north_star: fp32 log-likelihoods / parameters within 1e-5 relative
+
+
+@pytest.fixture(scope="module")
+def K():
+    import kerehmm_b200
+    from kerehmm_b200 import engine
+    engine.require_cuda()
+    return kerehmm_b200
+
+
+def discrete_model(K, pi, A, Bm):
+    h = K.DiscreteHMM(A.shape[0], Bm.shape[1])
+    h.initialProbabilities = pi.copy()
+    h.transitionMatrix = A.copy()
+    for i, d in enumerate(h.emissionDistributions):
+        d.probabilities = Bm[i].copy()
+    return h
+
+
+def gaussian_model(K, pi, A, mean, sd):
+    h = K.GaussianHMM(A.shape[0], 1)
+    h.initialProbabilities = pi.copy()
+    h.transitionMatrix = A.copy()
+    h.emissionDistributions = [K.GaussianDistribution(1, mean=float(m), variance=float(s)) for m, s in zip(mean, sd)]
+    return h
+
+
+def random_discrete(K, N, M, seed):
+    np.random.seed(seed)
+    pi, A, Bm = O.random_discrete_model(N, M)
+    return discrete_model(K, pi, A, Bm), (pi, A, Bm)
+
+
+# ------------------------------------------------------------------ golden, single sequence
+@pytest.mark.parametrize("name", ["D1", "D2", "D3", "D4"])
+def test_single_sequence_api_matches_reference_golden(K, golden, name):
+    g = gcase(golden, name)
+    h = discrete_model(K, g["pi"], g["A"], g["B"])
+    obs = [int(o) for o in g["obs"]]
+    alpha, scale = h.forward(obs)
+    assert alpha.dtype == np.float64 and alpha.shape == g["alpha"].shape
+    np.testing.assert_allclose(alpha, g["alpha"], rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(scale, g["scale"], rtol=1e-11)
+    beta = h.backward(obs, scale_coefficients=scale)
+    np.testing.assert_allclose(beta, g["beta"], rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(h.gamma(alpha, beta, scale), g["gamma"], rtol=1e-11, atol=1e-300)
+    assert np.isclose(h.forward_probability(obs), g["forward_probability"], rtol=1e-12)
+    assert np.isclose(h.log_likelihood(obs), np.log(g["scale"]).sum(), rtol=1e-12)
+    path, logp = h.viterbi_path(g["obs"])
+    assert path.dtype == g["obs"].dtype                       # np.empty_like(observations), :234
+    assert np.array_equal(path, g["path"])
+    assert logp == g["logp"]                                  # bit-exact float64
+    if "zi" in g:
+        z = h.zi(obs, alpha=alpha, beta=beta)
+        np.testing.assert_allclose(z, g["zi"], rtol=1e-11, atol=1e-300)
+    with pytest.raises(TypeError):                            # inverted guards, SURVEY Q7
+        h.zi(obs)
+
+
+@pytest.mark.parametrize("name", ["D1", "D2", "D3"])
+def test_do_pass_and_train_match_reference_golden(K, golden, name):
+    g = gcase(golden, name)
+    h = discrete_model(K, g["pi"], g["A"], g["B"])
+    obs = [int(o) for o in g["obs"]]
+    h.do_pass(obs)
+    np.testing.assert_allclose(h.initialProbabilities, g["pass_pi"], rtol=1e-9, atol=1e-20)
+    np.testing.assert_allclose(h.transitionMatrix, g["pass_A"], rtol=1e-9, atol=1e-20)
+    np.testing.assert_allclose(h.emission_matrix(), g["pass_B"], rtol=1e-9, atol=1e-20)
+    if "train3_A" in g:
+        h = discrete_model(K, g["pi"], g["A"], g["B"])
+        with contextlib.redirect_stdout(io.StringIO()) as out:
+            h.train(obs, iterations=3, auto_stop=False)
+        assert out.getvalue().count("ITERATION #") == 4       # iterations + 1 passes, SURVEY Q6
+        np.testing.assert_allclose(h.transitionMatrix, g["train3_A"], rtol=1e-8, atol=1e-18)
+        np.testing.assert_allclose(h.emission_matrix(), g["train3_B"], rtol=1e-8, atol=1e-18)
+        np.testing.assert_allclose(h.initialProbabilities, g["train3_pi"], rtol=1e-8, atol=1e-18)
+        h = discrete_model(K, g["pi"], g["A"], g["B"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            h.train(obs, iterations=50, auto_stop=True)
+        np.testing.assert_allclose(h.transitionMatrix, g["trainauto_A"], rtol=1e-7, atol=1e-16)
+
+
+@pytest.mark.parametrize("name", ["TIES", "KAT_l2r", "KAT_l2r_emis", "KAT_l2r_trans"])
+def test_viterbi_known_answers(K, golden, name):
+    g = gcase(golden, name)
+    h = discrete_model(K, g["pi"], g["A"], g["B"])
+    path, logp = h.viterbi_path(g["obs"])
+    assert np.array_equal(path, g["path"]) and logp == g["logp"]
+
+
+def test_reference_known_answer_tests(K, golden):
+    """kerehmm/test/discrete_hmm_test.py:48-98 run against the CUDA engine."""
+    n = 3
+    hmm = K.DiscreteHMM(n, n)
+    pt, pe = 1. / n, 1. / n
+    forward, coefs = hmm.forward([0, 0, 0])
+    assert np.array_equal(forward, hmm.forward([1, 1, 1])[0])
+    line = np.array([pt * pe] * n)
+    assert np.allclose(forward[0] * coefs[0], line, rtol=1e-15)
+    line[:] = (line * pt).sum() * pe
+    assert np.allclose(forward[1] * np.prod(coefs[:2]), line, rtol=1e-15)
+    line[:] = (line * pt).sum() * pe
+    assert np.allclose(forward[2] * np.prod(coefs[:3]), line, rtol=1e-15)
+    g = gcase(golden, "KAT_uniform")
+    np.testing.assert_allclose(forward, g["alpha"], rtol=1e-15)
+    path, _ = hmm.viterbi_path(g["vit_obs"])
+    assert not path.any()                                      # uniform model: first-index ties -> zeros
+    hmm = K.DiscreteHMM(n, n)
+    hmm.setup_strict_left_to_right(set_emissions=True)
+    path, _ = hmm.viterbi_path(np.array(range(n)))
+    assert np.array_equal(path, np.array(range(n)))
+    hmm = K.DiscreteHMM(n, n)
+    hmm.setup_strict_left_to_right()
+    path, _ = hmm.viterbi_path(np.random.randint(0, n - 1, n))
+    assert np.array_equal(path, np.array(range(n)))
+
+
+@pytest.mark.parametrize("name", ["G1", "G2", "G3"])
+def test_gaussian_single_sequence_golden(K, golden, name):
+    g = gcase(golden, name)
+    h = gaussian_model(K, g["pi"], g["A"], g["mean"], g["sd"])
+    obs = list(g["obs"])
+    alpha, scale = h.forward(obs)
+    np.testing.assert_allclose(alpha, g["alpha"], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(scale, g["scale"], rtol=1e-9, atol=1e-300)
+    beta = h.backward(obs, scale_coefficients=scale)
+    np.testing.assert_allclose(beta, g["beta"], rtol=1e-9, atol=1e-300)
+    if "emis" in g:
+        np.testing.assert_allclose(h.emission_probability(None, obs[3]), g["emis"][3], rtol=1e-13)
+    with pytest.raises(TypeError):                            # GaussianHMM.do_pass is broken upstream (Q9)
+        h.do_pass(obs)
+    with pytest.raises(IndexError):                           # Viterbi on float observations (Q10)
+        h.viterbi_path(np.array(obs))
+
+
+def test_multivariate_gaussian_golden(K, golden):
+    g = gcase(golden, "GM")
+    h = K.GaussianHMM(3, 2)
+    h.initialProbabilities, h.transitionMatrix = g["pi"].copy(), g["A"].copy()
+    h.emissionDistributions = [K.GaussianDistribution(2, mean=g["means"][i], variance=g["covs"][i]) for i in range(3)]
+    alpha, scale = h.forward(g["obs"])
+    np.testing.assert_allclose(alpha, g["alpha"], rtol=1e-9)
+    np.testing.assert_allclose(scale, g["scale"], rtol=1e-9)
+    np.testing.assert_allclose(h.backward(g["obs"], scale), g["beta"], rtol=1e-9)
+
+
+# ------------------------------------------------------------------------ batched Viterbi
+@pytest.mark.parametrize("N,M,B,T,dtype", [(3, 4, 70, 100, np.int64), (64, 256, 40, 64, np.uint8),
+                                           (128, 1024, 9, 40, np.uint16), (300, 16, 5, 30, np.int32),
+                                           (17, 5, 33, 1, np.uint8)])
+def test_viterbi_batch_bit_exact(K, N, M, B, T, dtype):
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=N + M)
+    obs = np.random.default_rng(N).integers(0, M, size=(B, T)).astype(dtype)
+    path, logp = h.viterbi_batch(obs)
+    with np.errstate(divide="ignore"):
+        rp, rl = O.viterbi(pi, A, Bm, obs.astype(np.int64))
+    assert np.array_equal(path, rp)
+    assert np.array_equal(logp, rl)                            # bit-exact float64
+
+
+def test_viterbi_batch_ragged_and_cuda_tensor_input(K):
+    import torch
+    N, M, B, T = 20, 11, 37, 50
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=5)
+    rng = np.random.default_rng(6)
+    obs = rng.integers(0, M, size=(B, T)).astype(np.uint8)
+    lengths = rng.integers(1, T + 1, size=B)
+    path, logp = h.viterbi_batch(torch.from_numpy(obs).cuda(), lengths=lengths, path_dtype=torch.int32)
+    assert path.is_cuda and logp.is_cuda                       # CUDA in -> CUDA out
+    path, logp = path.cpu().numpy(), logp.cpu().numpy()
+    for b in range(B):
+        L = lengths[b]
+        rp, rl = O.viterbi(pi, A, Bm, obs[b, :L].astype(np.int64))
+        assert np.array_equal(path[b, :L], rp) and logp[b] == rl
+        assert not path[b, L:].any()
+
+
+def test_viterbi_with_zero_probabilities(K):
+    """log(0) = -inf entries; -inf columns resolve to index 0."""
+    N, M = 5, 4
+    A = np.zeros((N, N))
+    for i in range(N):
+        A[i, (i + 1) % N] = 0.75
+        A[i, i] = 0.25
+    Bm = np.full((N, M), 0.25)
+    Bm[2] = [1, 0, 0, 0]
+    pi = np.array([1., 0, 0, 0, 0])
+    h = discrete_model(K, pi, A, Bm)
+    obs = np.random.default_rng(3).integers(0, M, size=(16, 25))
+    path, logp = h.viterbi_batch(obs)
+    with np.errstate(divide="ignore"):
+        rp, rl = O.viterbi(pi, A, Bm, obs)
+    assert np.array_equal(path, rp) and np.array_equal(logp, rl)
+
+
+# ----------------------------------------------------------------- batched forward/backward
+@pytest.mark.parametrize("N,M,B,T", [(3, 4, 65, 120), (8, 16, 33, 90), (40, 64, 10, 50), (128, 1024, 6, 40),
+                                     (260, 32, 3, 20)])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_forward_backward_batch_discrete(K, N, M, B, T, dtype):
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=N)
+    rng = np.random.default_rng(N + 1)
+    obs = rng.integers(0, M, size=(B, T))
+    lengths = rng.integers(max(1, T // 2), T + 1, size=B)
+    alpha, scale, ll = h.forward_batch(obs, lengths=lengths, dtype=dtype)
+    beta = h.backward_batch(obs, scale, lengths=lengths, dtype=dtype)
+    gam, ll2 = h.posterior_batch(obs, lengths=lengths, dtype=dtype)
+    rtol = 2e-5 if dtype == "float32" else 1e-10
+    for b in range(B):
+        L = lengths[b]
+        E = O.emissions_discrete(Bm, obs[b, :L])
+        ra, rc = O.forward(pi, A, E)
+        rb = O.backward(A, E, rc)
+        np.testing.assert_allclose(alpha[b, :L], ra, rtol=rtol, atol=1e-30)
+        np.testing.assert_allclose(scale[b, :L], rc, rtol=rtol)
+        np.testing.assert_allclose(beta[b, :L], rb, rtol=rtol * 5, atol=1e-30)
+        np.testing.assert_allclose(gam[b, :L], ra * rb, rtol=rtol * 5, atol=1e-30)
+        assert np.isclose(ll[b], np.log(rc).sum(), rtol=F32_RTOL if dtype == "float32" else 1e-12)
+        assert ll2[b] == ll[b]
+
+
+@pytest.mark.parametrize("N,B,T", [(8, 300, 257), (3, 64, 100), (12, 40, 64), (16, 33, 50), (1, 5, 10)])
+def test_fused_loglik_small_gaussian(K, N, B, T):
+    np.random.seed(100 + N)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    sd = sd * np.random.uniform(0.5, 2.0, size=N)
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(N)
+    obs = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T))).astype(np.float32)
+    lengths = rng.integers(1, T + 1, size=B)
+    ll, llb = h.log_likelihood_batch(obs, lengths=lengths)
+    _, _, ll_generic = h.forward_batch(obs, lengths=lengths, return_alpha=False)
+    for b in range(B):
+        E = O.emissions_gaussian_1d(mean, sd, obs[b, :lengths[b]].astype(np.float64))
+        ref = np.log(O.forward(pi, A, E)[1]).sum()
+        assert np.isclose(ll[b], ref, rtol=F32_RTOL, atol=1e-4), (b, ll[b], ref)
+        assert np.isclose(llb[b], ref, rtol=F32_RTOL, atol=1e-4), (b, llb[b], ref)
+        assert np.isclose(ll_generic[b], ref, rtol=F32_RTOL, atol=1e-4)
+
+
+def test_fused_loglik_small_discrete(K):
+    N, M, B, T = 3, 4, 50, 1000
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=1)
+    obs = np.random.default_rng(2).integers(0, M, size=(B, T)).astype(np.uint8)
+    ll, llb = h.log_likelihood_batch(obs)
+    ref = O.loglik(O.forward(pi, A, O.emissions_discrete(Bm, obs))[1])
+    np.testing.assert_allclose(ll, ref, rtol=F32_RTOL)
+    np.testing.assert_allclose(llb, ref, rtol=F32_RTOL)
+
+
+def test_gaussian_forward_backward_batch_generic(K):
+    N, B, T = 8, 25, 80
+    np.random.seed(3)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(4)
+    obs = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T)))
+    for dtype, rtol in (("float64", 1e-9), ("float32", 1e-4)):
+        alpha, scale, ll = h.forward_batch(obs.astype(np.float32 if dtype == "float32" else np.float64), dtype=dtype)
+        o = obs.astype(np.float32).astype(np.float64) if dtype == "float32" else obs
+        E = O.emissions_gaussian_1d(mean, sd, o)
+        ra, rc = O.forward(pi, A, E)
+        np.testing.assert_allclose(scale, rc, rtol=rtol, atol=1e-300)
+        np.testing.assert_allclose(alpha, ra, rtol=rtol, atol=1e-12)
+        np.testing.assert_allclose(ll, np.log(rc).sum(axis=1), rtol=F32_RTOL)
+
+
+# ----------------------------------------------------------------------------- Baum-Welch
+@pytest.mark.parametrize("N,M,B,T", [(3, 4, 12, 60), (16, 32, 9, 40), (128, 64, 5, 24), (130, 9, 3, 12)])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_do_pass_batch_matches_oracle(K, N, M, B, T, dtype):
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=10 + N)
+    rng = np.random.default_rng(11)
+    obs = rng.integers(0, M, size=(B, T))
+    lengths = rng.integers(max(2, T // 2), T + 1, size=B)
+    stats = None
+    for b in range(B):
+        s = O.sequence_stats_discrete(pi, A, Bm, obs[b, :lengths[b]])
+        stats = s if stats is None else {k: stats[k] + s[k] for k in s}
+    rpi, rA, rB = O.mstep_discrete(stats)
+    # E-step statistics first (chunked so that the chunk loop is exercised)
+    c = h.estep_batch(obs, lengths=lengths, dtype=dtype, chunk=4).host()
+    rtol = 2e-5 if dtype == "float32" else 1e-10
+    np.testing.assert_allclose(c["pi"], stats["pi"], rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(c["xi_raw"] * A, stats["xi"], rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(c["gam"], stats["gam"], rtol=rtol)
+    np.testing.assert_allclose(c["emis_num"], stats["emis_num"], rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(c["emis_den"], stats["emis_den"], rtol=rtol)
+    assert np.isclose(c["loglik"], stats["loglik"], rtol=F32_RTOL) and c["nseq"] == B and c["flags"] == 0
+    ll = h.do_pass_batch(obs, lengths=lengths, dtype=dtype)
+    assert np.isclose(ll, stats["loglik"], rtol=F32_RTOL)
+    np.testing.assert_allclose(h.initialProbabilities, rpi, rtol=rtol, atol=1e-14)
+    np.testing.assert_allclose(h.transitionMatrix, rA, rtol=rtol, atol=1e-14)
+    np.testing.assert_allclose(h.emission_matrix(), rB, rtol=rtol, atol=1e-14)
+
+
+def test_train_batch_increases_likelihood(K):
+    N, M, B, T = 6, 8, 200, 64
+    teacher, _ = random_discrete(K, N, M, seed=41)
+    np.random.seed(42)
+    obs = np.array([teacher.simulate(T).emissions for _ in range(B)])
+    h, _ = random_discrete(K, N, M, seed=43)
+    hist = h.train_batch(obs, iterations=6)
+    assert len(hist) == 6
+    # the reference's weighting is not textbook EM, but on well-conditioned data it still climbs
+    assert hist[-1] > hist[0]
+    h.sanity_check()
+
+
+# ------------------------------------------------------------------------- errors / edges
+def test_error_behaviour(K):
+    h, _ = random_discrete(K, 4, 5, seed=0)
+    with pytest.raises(IndexError):
+        h.forward_batch(np.zeros((2, 3), dtype=np.float32))    # float symbols
+    with pytest.raises(ValueError):
+        h.forward_batch(np.zeros((2, 3), dtype=np.int64), lengths=[1, 4])
+    with pytest.raises(ValueError):
+        h.forward_batch(np.zeros((3,), dtype=np.int64))
+    big = K.DiscreteHMM(1025, 2)
+    from kerehmm_b200._lib import KhmmError
+    with pytest.raises(KhmmError):
+        big.forward_batch(np.zeros((1, 4), dtype=np.int64))
+    # empty batch is fine
+    a, s, ll = h.forward_batch(np.zeros((0, 7), dtype=np.int64))
+    assert a.shape == (0, 7, 4) and ll.shape == (0,)
+    p, lp = h.viterbi_batch(np.zeros((0, 7), dtype=np.int64))
+    assert p.shape == (0, 7)
+    # T == 1 do_pass: 0/0 in the transition update -> the reference's sanity assertion (Q13)
+    with pytest.raises((AssertionError, ZeroDivisionError, ValueError)):
+        h.do_pass([1])
+
+
+def test_parameters_are_reread_on_every_call(K):
+    """Callers mutate the attributes between calls (discrete_hmm_test.py:52-55)."""
+    h = K.DiscreteHMM(3, 3)
+    a1, _ = h.forward([0, 1, 2])
+    h.transitionMatrix[:] = np.array([[.8, .1, .1], [.1, .8, .1], [.1, .1, .8]])
+    h.emissionDistributions[0].probabilities[:] = [.9, .05, .05]
+    a2, c2 = h.forward([0, 1, 2])
+    assert not np.allclose(a1, a2)
+    Bm = h.emission_matrix()
+    ra, rc = O.forward(h.initialProbabilities, h.transitionMatrix, O.emissions_discrete(Bm, np.array([0, 1, 2])))
+    np.testing.assert_allclose(a2, ra, rtol=1e-12)
+
+
+# ---------------------------------------------- full-size properties (BASELINE.json shapes)
+def test_viterbi_config3_shape_properties(K):
+    """N=64, M=256, T=4096 at a reduced batch: the returned log-probability must equal, bit for
+    bit, the score of the returned path recomputed in the DP's own order; and the oracle agrees on
+    a sub-sample."""
+    N, M, B, T = 64, 256, 512, 4096
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=3)
+    obs = np.random.default_rng(1003).integers(0, M, size=(B, T)).astype(np.uint8)
+    path, logp = h.viterbi_batch(obs, path_dtype="uint8")
+    assert path.dtype == np.uint8
+    with np.errstate(divide="ignore"):
+        lpi, lA, lB = np.log(pi), np.log(A), np.log(Bm)
+    p = path.astype(np.int64)
+    o = obs.astype(np.int64)
+    score = lpi[p[:, 0]] + lB[p[:, 0], o[:, 0]]
+    for t in range(1, T):
+        score = (score + lA[p[:, t - 1], p[:, t]]) + lB[p[:, t], o[:, t]]
+    assert np.array_equal(score, logp)
+    rp, rl = O.viterbi(pi, A, Bm, o[:8])
+    assert np.array_equal(p[:8], rp) and np.array_equal(logp[:8], rl)
+
+
+def test_fwdbwd_config2_shape_properties(K):
+    """N=8 Gaussian, T=2048 at a reduced batch: forward and backward likelihoods agree, and the
+    oracle agrees on a sub-sample."""
+    N, B, T = 8, 2048, 2048
+    np.random.seed(2)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(1002)
+    obs = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T))).astype(np.float32)
+    ll, llb = h.log_likelihood_batch(obs)
+    np.testing.assert_allclose(ll, llb, rtol=2e-6)
+    E = O.emissions_gaussian_1d(mean, sd, obs[:16].astype(np.float64))
+    ref = O.loglik(O.forward(pi, A, E)[1])
+    np.testing.assert_allclose(ll[:16], ref, rtol=F32_RTOL)
+    gam, ll3 = h.posterior_batch(obs[:64])
+    np.testing.assert_allclose(gam.sum(axis=2), 1.0, rtol=1e-4)
+    np.testing.assert_allclose(ll3, ll[:64], rtol=F32_RTOL)
