@@ -123,8 +123,8 @@ template <typename R>
 static int xi_impl(int64_t B, int64_t T, int N, const int32_t *lengths, const R *alpha, const R *V, double *xi,
                    khmm_stream_t stream) {
     KHMM_REQUIRE(B >= 0 && T >= 1 && N >= 1 && N <= 1024, "xi_accumulate: bad shape");
-    KHMM_REQUIRE(alpha && V && xi, "xi_accumulate: NULL pointer argument");
     if (B == 0 || T < 2) return KHMM_OK;
+    KHMM_REQUIRE(alpha && V && xi, "xi_accumulate: NULL pointer argument");
     int64_t rows = B * T - 1;  // the last row has no successor
     int tiles = (N + XT - 1) / XT;
     int64_t want = ((int64_t)sm_count() * 2 + (int64_t)tiles * tiles - 1) / ((int64_t)tiles * tiles);

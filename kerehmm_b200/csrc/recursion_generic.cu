@@ -360,8 +360,8 @@ static int launch_forward(int64_t B, int64_t T, int N, const R *pi, const R *A, 
                           R *alpha, R *scale, double *loglik, khmm_stream_t stream) {
     int rc = check_common(B, T, N);
     if (rc) return rc;
-    KHMM_REQUIRE(pi && A, "forward: pi/A must not be NULL");
     if (B == 0) return KHMM_OK;
+    KHMM_REQUIRE(pi && A, "forward: pi/A must not be NULL");
     int NT = ((N + 31) / 32) * 32;
     bool as = a_fits_smem<R>(N);
     size_t smem = generic_smem<R>(N, as);
@@ -383,10 +383,10 @@ static int launch_backward(int64_t B, int64_t T, int N, const R *AT, Emis em, co
                            khmm_stream_t stream) {
     int rc = check_common(B, T, N);
     if (rc) return rc;
+    if (B == 0) return KHMM_OK;
     KHMM_REQUIRE(AT && scale, "backward: AT/scale must not be NULL");
     KHMM_REQUIRE(!gamma || alpha, "backward: gamma output needs alpha");
     KHMM_REQUIRE(!ESTEP || (alpha && eo.counts), "estep: needs alpha and counts");
-    if (B == 0) return KHMM_OK;
     int NT = ((N + 31) / 32) * 32;
     bool as = a_fits_smem<R>(N);
     size_t smem = generic_smem<R>(N, as);
@@ -402,13 +402,15 @@ static int launch_backward(int64_t B, int64_t T, int N, const R *AT, Emis em, co
     return KHMM_OK;
 }
 
-static int check_symbols(int obs_dtype, int M, const void *obs, const void *Bsm) {
+static int check_symbols(int64_t B, int obs_dtype, int M, const void *obs, const void *Bsm) {
+    if (B == 0) return KHMM_OK;
     KHMM_REQUIRE(obs && Bsm && M >= 1, "discrete: obs/Bsm NULL or M < 1");
     KHMM_REQUIRE(obs_dtype >= KHMM_U8 && obs_dtype <= KHMM_I64, "discrete: obs dtype code %d is not an integer type",
                  obs_dtype);
     return KHMM_OK;
 }
-static int check_reals(int obs_dtype, const void *obs, const void *mean, const void *sd) {
+static int check_reals(int64_t B, int obs_dtype, const void *obs, const void *mean, const void *sd) {
+    if (B == 0) return KHMM_OK;
     KHMM_REQUIRE(obs && mean && sd, "gauss: obs/mean/sd must not be NULL");
     KHMM_REQUIRE(obs_dtype == KHMM_F32 || obs_dtype == KHMM_F64, "gauss: obs dtype code %d is not f32/f64", obs_dtype);
     return KHMM_OK;
@@ -421,7 +423,7 @@ using namespace khmm;
 #define FWD_DISCRETE(R, name)                                                                                         \
     int name(int64_t B, int64_t T, int N, int M, const R *pi, const R *A, const R *Bsm, const void *obs,              \
              int obs_dtype, const int32_t *lengths, R *alpha, R *scale, double *loglik, khmm_stream_t stream) {       \
-        int rc = check_symbols(obs_dtype, M, obs, Bsm);                                                               \
+        int rc = check_symbols(B, obs_dtype, M, obs, Bsm);                                                               \
         if (rc) return rc;                                                                                            \
         DiscreteEmis<R> em{Bsm, obs, obs_dtype, N, M, T};                                                             \
         return launch_forward<R>(B, T, N, pi, A, em, lengths, alpha, scale, loglik, stream);                          \
@@ -429,7 +431,7 @@ using namespace khmm;
 #define FWD_GAUSS(R, name)                                                                                            \
     int name(int64_t B, int64_t T, int N, const R *pi, const R *A, const R *mean, const R *sd, const void *obs,       \
              int obs_dtype, const int32_t *lengths, R *alpha, R *scale, double *loglik, khmm_stream_t stream) {       \
-        int rc = check_reals(obs_dtype, obs, mean, sd);                                                               \
+        int rc = check_reals(B, obs_dtype, obs, mean, sd);                                                               \
         if (rc) return rc;                                                                                            \
         GaussEmis<R> em{mean, sd, obs, obs_dtype, N, T};                                                              \
         return launch_forward<R>(B, T, N, pi, A, em, lengths, alpha, scale, loglik, stream);                          \
@@ -437,7 +439,7 @@ using namespace khmm;
 #define FWD_DENSE(R, name)                                                                                            \
     int name(int64_t B, int64_t T, int N, const R *pi, const R *A, const R *E, const int32_t *lengths, R *alpha,      \
              R *scale, double *loglik, khmm_stream_t stream) {                                                        \
-        KHMM_REQUIRE(E, "dense: E must not be NULL");                                                                 \
+        KHMM_REQUIRE(E || B == 0, "dense: E must not be NULL");                                                                 \
         DenseEmis<R> em{E, N, T};                                                                                     \
         return launch_forward<R>(B, T, N, pi, A, em, lengths, alpha, scale, loglik, stream);                          \
     }
@@ -445,7 +447,7 @@ using namespace khmm;
     int name(int64_t B, int64_t T, int N, int M, const R *AT, const R *Bsm, const void *obs, int obs_dtype,           \
              const int32_t *lengths, const R *scale, const R *alpha, R *beta, R *gamma, int gamma_kind,               \
              khmm_stream_t stream) {                                                                                  \
-        int rc = check_symbols(obs_dtype, M, obs, Bsm);                                                               \
+        int rc = check_symbols(B, obs_dtype, M, obs, Bsm);                                                               \
         if (rc) return rc;                                                                                            \
         DiscreteEmis<R> em{Bsm, obs, obs_dtype, N, M, T};                                                             \
         return launch_backward<R, DiscreteEmis<R>, false>(B, T, N, AT, em, lengths, scale, alpha, beta, gamma,        \
@@ -455,7 +457,7 @@ using namespace khmm;
     int name(int64_t B, int64_t T, int N, const R *AT, const R *mean, const R *sd, const void *obs, int obs_dtype,    \
              const int32_t *lengths, const R *scale, const R *alpha, R *beta, R *gamma, int gamma_kind,               \
              khmm_stream_t stream) {                                                                                  \
-        int rc = check_reals(obs_dtype, obs, mean, sd);                                                               \
+        int rc = check_reals(B, obs_dtype, obs, mean, sd);                                                               \
         if (rc) return rc;                                                                                            \
         GaussEmis<R> em{mean, sd, obs, obs_dtype, N, T};                                                              \
         return launch_backward<R, GaussEmis<R>, false>(B, T, N, AT, em, lengths, scale, alpha, beta, gamma,           \
@@ -464,7 +466,7 @@ using namespace khmm;
 #define BWD_DENSE(R, name)                                                                                            \
     int name(int64_t B, int64_t T, int N, const R *AT, const R *E, const int32_t *lengths, const R *scale,            \
              const R *alpha, R *beta, R *gamma, int gamma_kind, khmm_stream_t stream) {                               \
-        KHMM_REQUIRE(E, "dense: E must not be NULL");                                                                 \
+        KHMM_REQUIRE(E || B == 0, "dense: E must not be NULL");                                                                 \
         DenseEmis<R> em{E, N, T};                                                                                     \
         return launch_backward<R, DenseEmis<R>, false>(B, T, N, AT, em, lengths, scale, alpha, beta, gamma,           \
                                                        gamma_kind, nullptr, EstepOut{nullptr, 0}, stream);            \
@@ -472,7 +474,7 @@ using namespace khmm;
 #define ESTEP_DISCRETE(R, name)                                                                                       \
     int name(int64_t B, int64_t T, int N, int M, const R *AT, const R *Bsm, const void *obs, int obs_dtype,           \
              const int32_t *lengths, const R *alpha, const R *scale, R *V, double *counts, khmm_stream_t stream) {    \
-        int rc = check_symbols(obs_dtype, M, obs, Bsm);                                                               \
+        int rc = check_symbols(B, obs_dtype, M, obs, Bsm);                                                               \
         if (rc) return rc;                                                                                            \
         DiscreteEmis<R> em{Bsm, obs, obs_dtype, N, M, T};                                                             \
         return launch_backward<R, DiscreteEmis<R>, true>(B, T, N, AT, em, lengths, scale, alpha, nullptr, nullptr,    \

@@ -12,142 +12,240 @@
 // (w_t = b_t . beta_t up to scaling).  Both are "row vector times matrix, times emission,
 // normalise" -- with A^T and reversed time for the backward pass -- so one code path serves both.
 //
-// Scaling uses the hardware reciprocal r_t ~ 1/c_t and accumulates log P from r_t itself
-// (exponent in an integer, mantissa product in a double), which makes the result independent of
-// the reciprocal's rounding and costs no transcendental per step.
+// Blackwell specifics: all FP32 work is issued as packed FFMA2/FMUL2/FADD2 (fma.rn.f32x2, two
+// states per instruction) -- the kernel is bound by FP32 issue, not by HBM; the
+// matrix-vector product pairs the INPUT states (even/odd partial sums, one scalar add per output)
+// so no broadcast moves are needed; exp2 and the reciprocal are single MUFU instructions
+// (ex2.approx / rcp.approx); observations are prefetched one 8-step block ahead so their latency
+// never sits on the recursion's dependency chain.
+//
+// Scaling uses r_t ~ 1/c_t from the hardware reciprocal and accumulates log P from r_t itself
+// (exponent in an integer, mantissa product in fp32, renormalised every block), so the result
+// does not depend on the reciprocal's rounding and costs no transcendental per step.
 #include "common.cuh"
 
 namespace khmm {
 
-template <int NP>
-struct SmallConsts {  // per-thread (identical across threads) model constants, in registers
-    float mx[NP][NP];  // mx[y][x]: out[x] = sum_y in[y]*mx[y][x]  (A forward, A^T backward)
-    float e0[NP], e1[NP], e2[NP];  // gaussian: mean, k=-0.5*log2(e)/sd^2, log2(1/(sd*sqrt(2pi)))
-};
-
-struct LogAccum {  // log2 of a product of positive floats, exact to double rounding
-    int esum = 0, n = 0;
-    double mprod = 1.0, l2 = 0.0;
-    bool bad = false;
-    __device__ __forceinline__ void mul(float r) {
-        unsigned bits = __float_as_uint(r);
-        int e = (bits >> 23) & 0xff;
-        bad |= (e == 0) | (e == 255) | ((bits >> 31) != 0);
-        esum += e;
-        n++;
-        mprod *= (double)__uint_as_float((bits & 0x7fffffu) | 0x3f800000u);
-        if ((n & 255) == 0) { l2 += log2(mprod); mprod = 1.0; }
-    }
-    __device__ __forceinline__ double log2_total() const {
-        if (bad) return __longlong_as_double(0x7ff8000000000000ll);
-        return (double)(esum - 127 * n) + l2 + log2(mprod);
-    }
-};
-
-template <int NP, bool GAUSS>
-__device__ __forceinline__ void emis_small(const SmallConsts<NP> &mc, float x, int sym, const float *__restrict__ Bsm,
-                                           int N, float (&bv)[NP]) {
-    if (GAUSS) {
-#pragma unroll
-        for (int j = 0; j < NP; j++) {
-            float d = x - mc.e0[j];
-            bv[j] = exp2f(fmaf(d * d, mc.e1[j], mc.e2[j]));
-        }
-    } else {
-        const float *row = Bsm + (int64_t)sym * N;
-#pragma unroll
-        for (int j = 0; j < NP; j++) bv[j] = j < N ? __ldg(row + j) : 0.f;
-    }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-template <int NP, bool GAUSS>
-__global__ void __launch_bounds__(128)
+struct LogAccum {  // log2 of a product of positive normal floats
+    int esum = 0;      // sum of biased exponents
+    int n = 0;         // number of factors
+    float mant = 1.f;  // product of mantissas since the last fold, in [1, 2^8]
+    __device__ __forceinline__ void mul(float r) {
+        unsigned bits = __float_as_uint(r);
+        esum += (int)(bits >> 23);
+        n++;
+        mant *= __uint_as_float((bits & 0x7fffffu) | 0x3f800000u);
+    }
+    __device__ __forceinline__ void fold() {  // call at least every 100 factors
+        unsigned bits = __float_as_uint(mant);
+        esum += (int)(bits >> 23) - 127;
+        mant = __uint_as_float((bits & 0x7fffffu) | 0x3f800000u);
+    }
+    __device__ __forceinline__ double log2_total() const {
+        return (double)(esum - 127 * n) + (double)log2f(mant);
+    }
+};
+
+template <int NP, bool GAUSS, bool MX_SMEM>
+struct SmallStep {
+    static constexpr int H = NP / 2;
+    // mx2[y2][x] = (M[2*y2][x], M[2*y2+1][x]) with M = A (forward) or A^T (backward)
+    float2 mx2[MX_SMEM ? 1 : H][MX_SMEM ? 1 : NP];
+    const float2 *mxs;     // shared-memory copy when MX_SMEM
+    float2 nm[H], kk[H], lc[H];  // gaussian: -mean, -0.5*log2(e)/sd^2, -log2(sd*sqrt(2pi)) per state pair
+    const float *Bsm;
+    int N;
+
+    __device__ __forceinline__ float2 mat(int y2, int x) const { return MX_SMEM ? mxs[y2 * NP + x] : mx2[y2][x]; }
+
+    // emission values of the NP states for one observation
+    __device__ __forceinline__ void emis(float x, int sym, float2 (&bv)[H]) const {
+        if (GAUSS) {
+            const float2 xx = make_float2(x, x);
+#pragma unroll
+            for (int k = 0; k < H; k++) {
+                float2 d = __fadd2_rn(xx, nm[k]);
+                float2 a = __ffma2_rn(__fmul2_rn(d, d), kk[k], lc[k]);
+                bv[k] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+            }
+        } else {
+            const float *row = Bsm + (int64_t)sym * N;
+#pragma unroll
+            for (int k = 0; k < H; k++)
+                bv[k] = make_float2(2 * k < N ? __ldg(row + 2 * k) : 0.f, 2 * k + 1 < N ? __ldg(row + 2 * k + 1) : 0.f);
+        }
+    }
+
+    // u <- normalise((u M) . b), log accumulated from the reciprocal
+    __device__ __forceinline__ void step(float2 (&u)[H], const float2 (&bv)[H], LogAccum &acc) const {
+        float2 val[H];
+#pragma unroll
+        for (int k = 0; k < H; k++) {
+            float2 c0 = __fmul2_rn(u[0], mat(0, 2 * k));
+            float2 c1 = __fmul2_rn(u[0], mat(0, 2 * k + 1));
+#pragma unroll
+            for (int y2 = 1; y2 < H; y2++) {
+                c0 = __ffma2_rn(u[y2], mat(y2, 2 * k), c0);
+                c1 = __ffma2_rn(u[y2], mat(y2, 2 * k + 1), c1);
+            }
+            val[k] = __fmul2_rn(make_float2(c0.x + c0.y, c1.x + c1.y), bv[k]);
+        }
+        normalise(val, u, acc);
+    }
+
+    __device__ __forceinline__ void normalise(const float2 (&val)[H], float2 (&u)[H], LogAccum &acc) const {
+        float2 s2 = val[0];
+        if constexpr (H >= 2) s2 = __fadd2_rn(s2, val[1]);
+        if constexpr (H >= 4) s2 = __fadd2_rn(s2, __fadd2_rn(val[2], val[3]));
+        if constexpr (H >= 8) s2 = __fadd2_rn(s2, __fadd2_rn(__fadd2_rn(val[4], val[5]), __fadd2_rn(val[6], val[7])));
+        const float r = rcp_approx(s2.x + s2.y);
+        acc.mul(r);
+        const float2 rr = make_float2(r, r);
+#pragma unroll
+        for (int k = 0; k < H; k++) u[k] = __fmul2_rn(val[k], rr);
+    }
+};
+
+constexpr int kBlk = 8;  // steps per observation prefetch block
+
+template <int NP, bool GAUSS, bool MX_SMEM>
+__global__ void __launch_bounds__(64)
 fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict__ pi, const float *__restrict__ A,
                     const float *__restrict__ p0, const float *__restrict__ p1, const void *__restrict__ obs,
                     int obs_dtype, const int32_t *__restrict__ lengths, double *__restrict__ loglik,
                     double *__restrict__ loglik_bwd) {
+    constexpr int H = NP / 2;
+    __shared__ float2 mx_sh[MX_SMEM ? 2 * H * NP : 1];  // [dir][y2][x]
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const bool two = loglik_bwd != nullptr;
-    const int dir = two ? (int)(warp & 1) : 0;  // warp-uniform
+    const int dir = two ? (int)(warp & 1) : 0;  // warp-uniform: 0 forward, 1 backward
     const int64_t b = (two ? (warp >> 1) : warp) * 32 + lane;
 
-    SmallConsts<NP> mc;
-#pragma unroll
-    for (int y = 0; y < NP; y++)
-#pragma unroll
-        for (int x = 0; x < NP; x++) {
-            float v = 0.f;
-            if (y < N && x < N) v = dir ? __ldg(A + x * N + y) : __ldg(A + y * N + x);
-            mc.mx[y][x] = v;
+    auto m_elem = [&](int d, int y, int x) -> float {  // M[y][x], zero padded
+        if (y >= N || x >= N) return 0.f;
+        return d ? __ldg(A + x * N + y) : __ldg(A + y * N + x);
+    };
+    SmallStep<NP, GAUSS, MX_SMEM> S;
+    S.N = N;
+    S.Bsm = p0;
+    S.mxs = nullptr;
+    if (MX_SMEM) {
+        for (int k = threadIdx.x; k < 2 * H * NP; k += blockDim.x) {
+            int d = k / (H * NP), y2 = (k / NP) % H, x = k % NP;
+            mx_sh[k] = make_float2(m_elem(d, 2 * y2, x), m_elem(d, 2 * y2 + 1, x));
         }
-    float pv[NP];
+        __syncthreads();
+        S.mxs = mx_sh + dir * H * NP;
+    } else {
 #pragma unroll
-    for (int j = 0; j < NP; j++) {
-        pv[j] = j < N ? __ldg(pi + j) : 0.f;
+        for (int y2 = 0; y2 < H; y2++)
+#pragma unroll
+            for (int x = 0; x < NP; x++) S.mx2[y2][x] = make_float2(m_elem(dir, 2 * y2, x), m_elem(dir, 2 * y2 + 1, x));
+    }
+    float2 pv[H];
+#pragma unroll
+    for (int k = 0; k < H; k++) {
+        pv[k] = make_float2(2 * k < N ? __ldg(pi + 2 * k) : 0.f, 2 * k + 1 < N ? __ldg(pi + 2 * k + 1) : 0.f);
         if (GAUSS) {
-            float m = j < N ? __ldg(p0 + j) : 0.f, sd = j < N ? __ldg(p1 + j) : 1.f;
-            mc.e0[j] = m;
-            mc.e1[j] = j < N ? -0.5f * 1.4426950408889634f / (sd * sd) : 0.f;
-            mc.e2[j] = j < N ? -log2f(sd * 2.5066282746310002f) : -INFINITY;
+            float m[2], kq[2], l[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                int j = 2 * k + q;
+                float sd = j < N ? __ldg(p1 + j) : 1.f;
+                m[q] = j < N ? -__ldg(p0 + j) : 0.f;
+                kq[q] = j < N ? -0.5f * 1.4426950408889634f / (sd * sd) : 0.f;
+                l[q] = j < N ? -log2f(sd * 2.5066282746310002f) : -INFINITY;  // padded states emit 0
+            }
+            S.nm[k] = make_float2(m[0], m[1]);
+            S.kk[k] = make_float2(kq[0], kq[1]);
+            S.lc[k] = make_float2(l[0], l[1]);
         }
     }
     if (b >= B) return;
     const int len = lengths ? lengths[b] : (int)T;
     const int64_t base = b * T;
 
-    float u[NP];
+    // observation of recursion step `s` (time index runs backwards for the backward pass)
+    auto load_x = [&](int s) -> float {
+        int t = dir ? len - 1 - s : s;
+        if (GAUSS) return load_real<float>(obs, obs_dtype, base + t);
+        int sym = load_symbol(obs, obs_dtype, base + t);
+        sym = sym < 0 ? 0 : (sym >= M ? M - 1 : sym);
+        return __int_as_float(sym);
+    };
+
+    float2 u[H], bv[H];
     LogAccum acc;
-    for (int step = 0; step < len; step++) {
-        const int t = dir ? len - 1 - step : step;
-        float x = 0.f;
-        int sym = 0;
-        if (GAUSS) {
-            x = load_real<float>(obs, obs_dtype, base + t);
-        } else {
-            sym = load_symbol(obs, obs_dtype, base + t);
-            sym = sym < 0 ? 0 : (sym >= M ? M - 1 : sym);
+    {   // step 0: start vector (pi forward, ones backward) times the first emission
+        float x0 = load_x(0);
+        S.emis(x0, __float_as_int(x0), bv);
+        float2 val[H];
+#pragma unroll
+        for (int k = 0; k < H; k++) {
+            float2 st = dir ? make_float2(2 * k < N ? 1.f : 0.f, 2 * k + 1 < N ? 1.f : 0.f) : pv[k];
+            val[k] = __fmul2_rn(st, bv[k]);
         }
-        float bv[NP];
-        emis_small<NP, GAUSS>(mc, x, sym, p0, N, bv);
-        float val[NP];
-        if (step == 0) {
+        S.normalise(val, u, acc);
+    }
+    float xs[kBlk], xn[kBlk];
 #pragma unroll
-            for (int j = 0; j < NP; j++) val[j] = (dir ? (j < N ? 1.f : 0.f) : pv[j]) * bv[j];
+    for (int q = 0; q < kBlk; q++) xs[q] = (1 + q < len) ? load_x(1 + q) : 0.f;
+    for (int s0 = 1; s0 < len; s0 += kBlk) {
+#pragma unroll
+        for (int q = 0; q < kBlk; q++) xn[q] = (s0 + kBlk + q < len) ? load_x(s0 + kBlk + q) : 0.f;
+        if (s0 + kBlk <= len) {
+#pragma unroll
+            for (int q = 0; q < kBlk; q++) {
+                S.emis(xs[q], __float_as_int(xs[q]), bv);
+                S.step(u, bv, acc);
+            }
         } else {
 #pragma unroll
-            for (int xx = 0; xx < NP; xx++) {
-                float s = 0.f;
-#pragma unroll
-                for (int y = 0; y < NP; y++) s = fmaf(u[y], mc.mx[y][xx], s);
-                val[xx] = s * bv[xx];
+            for (int q = 0; q < kBlk; q++) {
+                if (s0 + q < len) {
+                    S.emis(xs[q], __float_as_int(xs[q]), bv);
+                    S.step(u, bv, acc);
+                }
             }
         }
-        float s = 0.f;
+        acc.fold();
 #pragma unroll
-        for (int j = 0; j < NP; j++) s += val[j];
-        float r = __frcp_rn(s);
-        acc.mul(r);
-#pragma unroll
-        for (int j = 0; j < NP; j++) u[j] = val[j] * r;
+        for (int q = 0; q < kBlk; q++) xs[q] = xn[q];
     }
     // closing dot product: forward sum(u) (= 1 up to rounding), backward pi . w_0
-    float fin = 0.f;
+    float2 f2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < NP; j++) fin = fmaf(u[j], dir ? pv[j] : (j < N ? 1.f : 0.f), fin);
+    for (int k = 0; k < H; k++) {
+        float2 w = dir ? pv[k] : make_float2(2 * k < N ? 1.f : 0.f, 2 * k + 1 < N ? 1.f : 0.f);
+        f2 = __ffma2_rn(u[k], w, f2);
+    }
+    const float fin = f2.x + f2.y;
     double ll = (-acc.log2_total()) * 0.6931471805599453 + log((double)fin);
+    if (!(fin > 0.f) || !(fin < INFINITY)) ll = __longlong_as_double(0x7ff8000000000000ll);  // underflow -> NaN (Q15)
     (dir ? loglik_bwd : loglik)[b] = ll;
 }
 
-template <int NP, bool GAUSS>
+template <int NP, bool GAUSS, bool MX_SMEM>
 static int launch_small(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *p0,
                         const float *p1, const void *obs, int obs_dtype, const int32_t *lengths, double *loglik,
                         double *loglik_bwd, cudaStream_t st) {
     int64_t warps = (B + 31) / 32 * (loglik_bwd ? 2 : 1);
     int threads = 64;  // one forward + one backward warp per CTA
     int64_t grid = (warps * 32 + threads - 1) / threads;
-    fwdbwd_small_kernel<NP, GAUSS><<<(unsigned)grid, threads, 0, st>>>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype,
-                                                                      lengths, loglik, loglik_bwd);
+    fwdbwd_small_kernel<NP, GAUSS, MX_SMEM><<<(unsigned)grid, threads, 0, st>>>(
+        B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd);
     KHMM_LAUNCH_CHECK("fwdbwd_small_kernel");
     return KHMM_OK;
 }
@@ -161,12 +259,13 @@ static int dispatch_small(int64_t B, int64_t T, int N, int M, const float *pi, c
         set_error("fwdbwd_loglik: N=%d > %d; use forward/backward", N, KHMM_SMALL_N_MAX);
         return KHMM_ERR_UNSUPPORTED;
     }
-    KHMM_REQUIRE(pi && A && p0 && obs && loglik, "fwdbwd_loglik: NULL pointer argument");
     if (B == 0) return KHMM_OK;
+    KHMM_REQUIRE(pi && A && p0 && obs && loglik, "fwdbwd_loglik: NULL pointer argument");
     cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 4) return launch_small<4, GAUSS>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
-    if (N <= 8) return launch_small<8, GAUSS>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
-    return launch_small<16, GAUSS>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
+    if (N <= 2) return launch_small<2, GAUSS, false>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
+    if (N <= 4) return launch_small<4, GAUSS, false>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
+    if (N <= 8) return launch_small<8, GAUSS, false>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
+    return launch_small<16, GAUSS, true>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
 }
 
 }  // namespace khmm

@@ -92,16 +92,18 @@ viterbi_generic_kernel(int64_t B, int64_t T, int N, int M, const double *__restr
             }
             __syncthreads();
             // termination for sequences that end at this step: first-index argmax (abstract_hmm.py:233,235)
-            if (j < S && t == len[j] - 1) {
-                int s = j;
-                double m = next[s];
-                int am = 0;
-                for (int k = 1; k < N; k++) {
-                    double v = next[k * S + s];
-                    if (v > m) { m = v; am = k; }
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                if (j == s && t == len[s] - 1) {
+                    double m = next[s];
+                    int am = 0;
+                    for (int k = 1; k < N; k++) {
+                        double v = next[k * S + s];
+                        if (v > m) { m = v; am = k; }
+                    }
+                    last_state[b0 + s] = am;
+                    logp[b0 + s] = m;
                 }
-                last_state[b0 + s] = am;
-                logp[b0 + s] = m;
             }
             cur ^= 1;
         }
@@ -184,6 +186,7 @@ int khmm_viterbi_discrete_f64(int64_t B, int64_t T, int N, int M, const double *
         set_error("N=%d > 1024 is not supported", N);
         return KHMM_ERR_UNSUPPORTED;
     }
+    if (B == 0) return KHMM_OK;
     KHMM_REQUIRE(logpi && logA && logBsm && obs && path && logp && backptr, "viterbi: NULL pointer argument");
     KHMM_REQUIRE(obs_dtype >= KHMM_U8 && obs_dtype <= KHMM_I64, "viterbi: obs dtype code %d is not an integer type",
                  obs_dtype);
