@@ -194,7 +194,7 @@ def run_ours(args):
     hbm_peak, peak_src = peaks()
 
     launches_per_step = 0
-    extra = {}
+    ncu_traffic = None
     if kind in ("c2",):
         model, obs_h = make_gaussian(N, B, T, seed)
         if rank:      # different sequences per rank, same model
@@ -220,6 +220,9 @@ def run_ours(args):
         algo_bytes = B * T * 4 + 2 * B * 8          # observations once + two float64 results per sequence
         h2d, d2h = B * T * 4, 2 * B * 8
         dominant = "fwdbwd_small_kernel<8, gauss>"
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+        # (profiles/r1_ncu_c2_fwdbwd_small_summary.csv): the two directions share most lines in L2
+        ncu_traffic = 180.484352e6 + 4.261632e6
         l2_note = "two alternating 134 MB observation sets (268 MB > 126 MB L2)"
         dtype = "f32"
     elif kind == "c3":
@@ -348,7 +351,7 @@ def run_ours(args):
                     "ms_per_step": float(t_e.item()) * 1e3, "api": "kerehmm_b200 public class API, pinned host buffers"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "kernel": dominant, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": ncu_traffic, "kernel": dominant, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes},
             "clocks": clocks,
         }

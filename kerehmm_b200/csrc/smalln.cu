@@ -60,14 +60,14 @@ struct LogAccum {  // log2 of a product of positive normal floats
 template <int NP, bool GAUSS, bool MX_SMEM>
 struct SmallStep {
     static constexpr int H = NP / 2;
-    // mx2[y2][x] = (M[2*y2][x], M[2*y2+1][x]) with M = A (forward) or A^T (backward)
-    float2 mx2[MX_SMEM ? 1 : H][MX_SMEM ? 1 : NP];
+    // mx2[y][k] = (M[y][2k], M[y][2k+1]) with M = A (forward) or A^T (backward)
+    float2 mx2[MX_SMEM ? 1 : NP][MX_SMEM ? 1 : H];
     const float2 *mxs;     // shared-memory copy when MX_SMEM
     float2 nm[H], kk[H], lc[H];  // gaussian: -mean, -0.5*log2(e)/sd^2, -log2(sd*sqrt(2pi)) per state pair
     const float *Bsm;
     int N;
 
-    __device__ __forceinline__ float2 mat(int y2, int x) const { return MX_SMEM ? mxs[y2 * NP + x] : mx2[y2][x]; }
+    __device__ __forceinline__ float2 mat(int y, int k) const { return MX_SMEM ? mxs[y * H + k] : mx2[y][k]; }
 
     // emission values of the NP states for one observation
     __device__ __forceinline__ void emis(float x, int sym, float2 (&bv)[H]) const {
@@ -87,51 +87,59 @@ struct SmallStep {
         }
     }
 
-    // u <- normalise((u M) . b), log accumulated from the reciprocal
-    __device__ __forceinline__ void step(float2 (&u)[H], const float2 (&bv)[H], LogAccum &acc) const {
-        float2 val[H];
+    // One recursion step with the scale applied AFTER the matrix-vector product:
+    //     w_t = (w_{t-1} M) . (b_t * r_{t-1}),   r_t = 1 / sum(w_t)
+    // (w_t is the reference's unnormalised alpha_t; same arithmetic as normalising w_{t-1} first, but
+    // the sum -> reciprocal chain of step t-1 now runs in parallel with the matrix-vector product of
+    // step t instead of in front of it).  log P accumulates from the reciprocals themselves.
+    __device__ __forceinline__ void step(float2 (&w)[H], float &r, const float2 (&bv)[H], LogAccum &acc) const {
+        const float2 rr = make_float2(r, r);
+        float2 out[H];
 #pragma unroll
         for (int k = 0; k < H; k++) {
-            float2 c0 = __fmul2_rn(u[0], mat(0, 2 * k));
-            float2 c1 = __fmul2_rn(u[0], mat(0, 2 * k + 1));
+            // even / odd input states in two independent chains, scalar-broadcast operand form
+            float2 c0 = __fmul2_rn(make_float2(w[0].x, w[0].x), mat(0, k));
+            float2 c1 = __fmul2_rn(make_float2(w[0].y, w[0].y), mat(1, k));
 #pragma unroll
             for (int y2 = 1; y2 < H; y2++) {
-                c0 = __ffma2_rn(u[y2], mat(y2, 2 * k), c0);
-                c1 = __ffma2_rn(u[y2], mat(y2, 2 * k + 1), c1);
+                c0 = __ffma2_rn(make_float2(w[y2].x, w[y2].x), mat(2 * y2, k), c0);
+                c1 = __ffma2_rn(make_float2(w[y2].y, w[y2].y), mat(2 * y2 + 1, k), c1);
             }
-            val[k] = __fmul2_rn(make_float2(c0.x + c0.y, c1.x + c1.y), bv[k]);
+            out[k] = __fadd2_rn(c0, c1);
         }
-        normalise(val, u, acc);
+#pragma unroll
+        for (int k = 0; k < H; k++) w[k] = __fmul2_rn(out[k], __fmul2_rn(bv[k], rr));
+        r = recip_sum(w);
+        acc.mul(r);
     }
 
-    __device__ __forceinline__ void normalise(const float2 (&val)[H], float2 (&u)[H], LogAccum &acc) const {
+    __device__ __forceinline__ float recip_sum(const float2 (&val)[H]) const {
         float2 s2 = val[0];
         if constexpr (H >= 2) s2 = __fadd2_rn(s2, val[1]);
         if constexpr (H >= 4) s2 = __fadd2_rn(s2, __fadd2_rn(val[2], val[3]));
         if constexpr (H >= 8) s2 = __fadd2_rn(s2, __fadd2_rn(__fadd2_rn(val[4], val[5]), __fadd2_rn(val[6], val[7])));
-        const float r = rcp_approx(s2.x + s2.y);
-        acc.mul(r);
-        const float2 rr = make_float2(r, r);
-#pragma unroll
-        for (int k = 0; k < H; k++) u[k] = __fmul2_rn(val[k], rr);
+        return rcp_approx(s2.x + s2.y);
     }
 };
 
 constexpr int kBlk = 8;  // steps per observation prefetch block
 
-template <int NP, bool GAUSS, bool MX_SMEM>
+template <int NP, bool GAUSS, bool MX_SMEM, int Q>
 __global__ void __launch_bounds__(64)
 fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict__ pi, const float *__restrict__ A,
                     const float *__restrict__ p0, const float *__restrict__ p1, const void *__restrict__ obs,
                     int obs_dtype, const int32_t *__restrict__ lengths, double *__restrict__ loglik,
                     double *__restrict__ loglik_bwd) {
+    // Q sequences per thread: their recursions are independent, so the compiler interleaves the two
+    // dependency chains and one warp keeps the FMA pipe busy on its own (the model constants are
+    // shared between them).
     constexpr int H = NP / 2;
-    __shared__ float2 mx_sh[MX_SMEM ? 2 * H * NP : 1];  // [dir][y2][x]
+    __shared__ float2 mx_sh[MX_SMEM ? 2 * H * NP : 1];  // [dir][y][k]
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const bool two = loglik_bwd != nullptr;
     const int dir = two ? (int)(warp & 1) : 0;  // warp-uniform: 0 forward, 1 backward
-    const int64_t b = (two ? (warp >> 1) : warp) * 32 + lane;
+    const int64_t bfirst = (two ? (warp >> 1) : warp) * (32 * Q) + lane;   // sequences bfirst + 32*q
 
     auto m_elem = [&](int d, int y, int x) -> float {  // M[y][x], zero padded
         if (y >= N || x >= N) return 0.f;
@@ -143,16 +151,16 @@ fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict_
     S.mxs = nullptr;
     if (MX_SMEM) {
         for (int k = threadIdx.x; k < 2 * H * NP; k += blockDim.x) {
-            int d = k / (H * NP), y2 = (k / NP) % H, x = k % NP;
-            mx_sh[k] = make_float2(m_elem(d, 2 * y2, x), m_elem(d, 2 * y2 + 1, x));
+            int d = k / (H * NP), y = (k / H) % NP, kk2 = k % H;
+            mx_sh[k] = make_float2(m_elem(d, y, 2 * kk2), m_elem(d, y, 2 * kk2 + 1));
         }
         __syncthreads();
         S.mxs = mx_sh + dir * H * NP;
     } else {
 #pragma unroll
-        for (int y2 = 0; y2 < H; y2++)
+        for (int y = 0; y < NP; y++)
 #pragma unroll
-            for (int x = 0; x < NP; x++) S.mx2[y2][x] = make_float2(m_elem(dir, 2 * y2, x), m_elem(dir, 2 * y2 + 1, x));
+            for (int k = 0; k < H; k++) S.mx2[y][k] = make_float2(m_elem(dir, y, 2 * k), m_elem(dir, y, 2 * k + 1));
     }
     float2 pv[H];
 #pragma unroll
@@ -173,79 +181,122 @@ fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict_
             S.lc[k] = make_float2(l[0], l[1]);
         }
     }
-    if (b >= B) return;
-    const int len = lengths ? lengths[b] : (int)T;
-    const int64_t base = b * T;
+    if (bfirst >= B) return;
+    int len[Q];
+    int64_t base[Q];
+    int lmax = 0;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        int64_t b = bfirst + 32 * q;
+        len[q] = b < B ? (lengths ? lengths[b] : (int)T) : 0;
+        base[q] = (b < B ? b : bfirst) * T;
+        lmax = max(lmax, len[q]);
+    }
 
-    // observation of recursion step `s` (time index runs backwards for the backward pass)
-    auto load_x = [&](int s) -> float {
-        int t = dir ? len - 1 - s : s;
-        if (GAUSS) return load_real<float>(obs, obs_dtype, base + t);
-        int sym = load_symbol(obs, obs_dtype, base + t);
+    // observation of recursion step `s` of sequence q (time runs backwards for the backward pass)
+    auto load_x = [&](int q, int s) -> float {
+        int t = dir ? len[q] - 1 - s : s;
+        if (GAUSS) return load_real<float>(obs, obs_dtype, base[q] + t);
+        int sym = load_symbol(obs, obs_dtype, base[q] + t);
         sym = sym < 0 ? 0 : (sym >= M ? M - 1 : sym);
         return __int_as_float(sym);
     };
 
-    float2 u[H], bv[H];
-    LogAccum acc;
-    {   // step 0: start vector (pi forward, ones backward) times the first emission
-        float x0 = load_x(0);
+    float2 u[Q][H];
+    float r[Q];
+    LogAccum acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {   // step 0: start vector (pi forward, ones backward) times the first emission
+        float2 bv[H];
+        float x0 = len[q] > 0 ? load_x(q, 0) : 0.f;
         S.emis(x0, __float_as_int(x0), bv);
-        float2 val[H];
 #pragma unroll
         for (int k = 0; k < H; k++) {
             float2 st = dir ? make_float2(2 * k < N ? 1.f : 0.f, 2 * k + 1 < N ? 1.f : 0.f) : pv[k];
-            val[k] = __fmul2_rn(st, bv[k]);
+            u[q][k] = __fmul2_rn(st, bv[k]);
         }
-        S.normalise(val, u, acc);
+        r[q] = S.recip_sum(u[q]);
+        acc[q].mul(r[q]);
     }
-    float xs[kBlk], xn[kBlk];
+    float xs[Q][kBlk], xn[Q][kBlk];
 #pragma unroll
-    for (int q = 0; q < kBlk; q++) xs[q] = (1 + q < len) ? load_x(1 + q) : 0.f;
-    for (int s0 = 1; s0 < len; s0 += kBlk) {
+    for (int q = 0; q < Q; q++)
 #pragma unroll
-        for (int q = 0; q < kBlk; q++) xn[q] = (s0 + kBlk + q < len) ? load_x(s0 + kBlk + q) : 0.f;
-        if (s0 + kBlk <= len) {
+        for (int i = 0; i < kBlk; i++) xs[q][i] = (1 + i < len[q]) ? load_x(q, 1 + i) : 0.f;
+    for (int s0 = 1; s0 < lmax; s0 += kBlk) {
 #pragma unroll
-            for (int q = 0; q < kBlk; q++) {
-                S.emis(xs[q], __float_as_int(xs[q]), bv);
-                S.step(u, bv, acc);
+        for (int q = 0; q < Q; q++)
+#pragma unroll
+            for (int i = 0; i < kBlk; i++) xn[q][i] = (s0 + kBlk + i < len[q]) ? load_x(q, s0 + kBlk + i) : 0.f;
+        bool full = true;
+#pragma unroll
+        for (int q = 0; q < Q; q++) full = full && (s0 + kBlk <= len[q]);
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < kBlk; i++) {
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    float2 bv[H];
+                    S.emis(xs[q][i], __float_as_int(xs[q][i]), bv);
+                    S.step(u[q], r[q], bv, acc[q]);
+                }
             }
         } else {
 #pragma unroll
-            for (int q = 0; q < kBlk; q++) {
-                if (s0 + q < len) {
-                    S.emis(xs[q], __float_as_int(xs[q]), bv);
-                    S.step(u, bv, acc);
+            for (int i = 0; i < kBlk; i++) {
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    if (s0 + i < len[q]) {
+                        float2 bv[H];
+                        S.emis(xs[q][i], __float_as_int(xs[q][i]), bv);
+                        S.step(u[q], r[q], bv, acc[q]);
+                    }
                 }
             }
         }
-        acc.fold();
 #pragma unroll
-        for (int q = 0; q < kBlk; q++) xs[q] = xn[q];
-    }
-    // closing dot product: forward sum(u) (= 1 up to rounding), backward pi . w_0
-    float2 f2 = make_float2(0.f, 0.f);
+        for (int q = 0; q < Q; q++) {
+            acc[q].fold();
 #pragma unroll
-    for (int k = 0; k < H; k++) {
-        float2 w = dir ? pv[k] : make_float2(2 * k < N ? 1.f : 0.f, 2 * k + 1 < N ? 1.f : 0.f);
-        f2 = __ffma2_rn(u[k], w, f2);
+            for (int i = 0; i < kBlk; i++) xs[q][i] = xn[q][i];
+        }
     }
-    const float fin = f2.x + f2.y;
-    double ll = (-acc.log2_total()) * 0.6931471805599453 + log((double)fin);
-    if (!(fin > 0.f) || !(fin < INFINITY)) ll = __longlong_as_double(0x7ff8000000000000ll);  // underflow -> NaN (Q15)
-    (dir ? loglik_bwd : loglik)[b] = ll;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        int64_t b = bfirst + 32 * q;
+        if (b >= B) continue;
+        // closing dot product: forward sum(u) r (= 1 up to rounding), backward (pi . w_0) r
+        float2 f2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < H; k++) {
+            float2 w = dir ? pv[k] : make_float2(2 * k < N ? 1.f : 0.f, 2 * k + 1 < N ? 1.f : 0.f);
+            f2 = __ffma2_rn(u[q][k], w, f2);
+        }
+        const float fin = (f2.x + f2.y) * r[q];   // u is unnormalised by the last reciprocal
+        double ll = (-acc[q].log2_total()) * 0.6931471805599453 + log((double)fin);
+        if (!(fin > 0.f) || !(fin < INFINITY)) ll = __longlong_as_double(0x7ff8000000000000ll);  // underflow -> NaN (Q15)
+        (dir ? loglik_bwd : loglik)[b] = ll;
+    }
 }
 
 template <int NP, bool GAUSS, bool MX_SMEM>
 static int launch_small(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *p0,
                         const float *p1, const void *obs, int obs_dtype, const int32_t *lengths, double *loglik,
                         double *loglik_bwd, cudaStream_t st) {
-    int64_t warps = (B + 31) / 32 * (loglik_bwd ? 2 : 1);
-    int threads = 64;  // one forward + one backward warp per CTA
+    const int dirs = loglik_bwd ? 2 : 1;
+    const int threads = 64;  // one forward + one backward warp per CTA
+    // Two sequences per thread (Q = 2) was measured SLOWER on B200 (0.47 ms vs 0.38 ms at N=8,
+    // B=16384, T=2048): one warp with two interleaved chains does not out-issue two warps with one
+    // chain each.  Kept as a template parameter for experiments, disabled in the dispatch.
+    const bool q2 = false;
+    int64_t warps = (B + (q2 ? 63 : 31)) / (q2 ? 64 : 32) * dirs;
     int64_t grid = (warps * 32 + threads - 1) / threads;
-    fwdbwd_small_kernel<NP, GAUSS, MX_SMEM><<<(unsigned)grid, threads, 0, st>>>(
-        B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd);
+    if (q2)
+        fwdbwd_small_kernel<NP, GAUSS, MX_SMEM, (NP <= 8 ? 2 : 1)><<<(unsigned)grid, threads, 0, st>>>(
+            B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd);
+    else
+        fwdbwd_small_kernel<NP, GAUSS, MX_SMEM, 1><<<(unsigned)grid, threads, 0, st>>>(
+            B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd);
     KHMM_LAUNCH_CHECK("fwdbwd_small_kernel");
     return KHMM_OK;
 }

@@ -110,6 +110,162 @@ viterbi_generic_kernel(int64_t B, int64_t T, int N, int M, const double *__restr
     }
 }
 
+// ------------------------------------------------------------------ register-tile kernel
+// N in {32, 64, 128}: logA lives in REGISTERS.  A CTA has W = N*N/2048 warps; warp w owns the
+// sources [w*SRC, (w+1)*SRC) with SRC = N/W, lane l owns the JT = N/32 targets l, l+32, ...: a
+// JT x SRC tile of logA (64 doubles = 128 registers).  Each delta value is fetched from shared memory
+// once per JT transitions as a pure broadcast, so the inner step is DADD + DSETP + 3 selects with no
+// memory traffic of its own (measured 1.5x the generic kernel at N=64; tools/vit64_bench.cu holds
+// the experiment).  Warps exchange their partial (best, arg) through shared memory once per
+// (sequence, step); the first N threads merge them in source order -- a later source range wins
+// only when strictly greater, which keeps np.argmax's first-index rule.
+template <int NN, int S>
+struct VitTile {
+    static constexpr int W = NN * NN / 2048 < 1 ? 1 : NN * NN / 2048;
+    static constexpr int SRC = NN / W;
+    static constexpr int JT = NN / 32;
+    static constexpr int THREADS = 32 * W;
+    static constexpr size_t smem_bytes() {
+        return sizeof(double) * (2 * S * NN + S * W * NN) + sizeof(int) * S * W * NN;
+    }
+};
+
+template <int NN, int S, typename PSI>
+__global__ void __launch_bounds__(VitTile<NN, S>::THREADS)
+viterbi_tile_kernel(int64_t B, int64_t T, int M, const double *__restrict__ logpi, const double *__restrict__ logA,
+                    const double *__restrict__ logBsm, const void *__restrict__ obs, int obs_dtype,
+                    const int32_t *__restrict__ lengths, PSI *__restrict__ psi, int32_t *__restrict__ last_state,
+                    double *__restrict__ logp) {
+    using C = VitTile<NN, S>;
+    constexpr int W = C::W, SRC = C::SRC, JT = C::JT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *d = reinterpret_cast<double *>(smem_raw);          // [2][S][NN]
+    double *pbest = d + 2 * S * NN;                            // [S][W][NN]
+    int *parg = reinterpret_cast<int *>(pbest + S * W * NN);   // [S][W][NN]
+    const int tid = threadIdx.x, l = tid & 31, w = tid >> 5;
+    double a[JT][SRC];
+#pragma unroll
+    for (int q = 0; q < JT; q++)
+#pragma unroll
+        for (int k = 0; k < SRC; k++) a[q][k] = logA[(SRC * w + k) * NN + l + 32 * q];
+    const bool owner = tid < NN;  // threads that own a target state for merging / emission / output
+    const double lp = owner ? logpi[tid] : 0.0;
+    const int64_t ngroups = (B + S - 1) / S;
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t b0 = g * S;
+        int len[S];
+        int tmax = 0;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            int64_t b = b0 + s;
+            len[s] = b < B ? (lengths ? lengths[b] : (int)T) : 0;
+            tmax = max(tmax, len[s]);
+        }
+        int cur = 0;
+        for (int t = 0; t < tmax; t++) {
+            double e[S];
+            if (owner) {
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    e[s] = 0.0;
+                    if (t < len[s]) {
+                        int sym = load_symbol(obs, obs_dtype, (b0 + s) * T + t);
+                        sym = sym < 0 ? 0 : (sym >= M ? M - 1 : sym);
+                        e[s] = __ldg(logBsm + (int64_t)sym * NN + tid);
+                    }
+                }
+            }
+            if (t > 0) {
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    const double *dp = d + (cur * S + s) * NN + SRC * w;
+                    double best[JT];
+                    int arg[JT];
+                    {
+                        const double dv = dp[0];
+#pragma unroll
+                        for (int q = 0; q < JT; q++) { best[q] = dv + a[q][0]; arg[q] = 0; }
+                    }
+#pragma unroll
+                    for (int k = 1; k < SRC; k++) {
+                        const double dv = dp[k];
+#pragma unroll
+                        for (int q = 0; q < JT; q++) {
+                            const double v = dv + a[q][k];
+                            if (v > best[q]) { best[q] = v; arg[q] = k; }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < JT; q++) {
+                        pbest[(s * W + w) * NN + l + 32 * q] = best[q];
+                        parg[(s * W + w) * NN + l + 32 * q] = arg[q] + SRC * w;
+                    }
+                }
+                __syncthreads();
+            }
+            if (owner) {
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    double nd = 0.0;
+                    if (t < len[s]) {
+                        if (t == 0) {
+                            nd = lp + e[s];
+                        } else {
+                            double bb = pbest[(s * W) * NN + tid];
+                            int ba = parg[(s * W) * NN + tid];
+#pragma unroll
+                            for (int q = 1; q < W; q++) {
+                                double qb = pbest[(s * W + q) * NN + tid];
+                                int qa = parg[(s * W + q) * NN + tid];
+                                if (qb > bb) { bb = qb; ba = qa; }
+                            }
+                            psi[((b0 + s) * T + t) * NN + tid] = (PSI)ba;
+                            nd = bb + e[s];
+                        }
+                    }
+                    d[((cur ^ 1) * S + s) * NN + tid] = nd;
+                }
+            }
+            __syncthreads();
+            cur ^= 1;
+            // termination: first-index argmax over the final delta row (abstract_hmm.py:233,235)
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                if (tid == s && t == len[s] - 1) {
+                    const double *row = d + (cur * S + s) * NN;
+                    double m = row[0];
+                    int am = 0;
+                    for (int k = 1; k < NN; k++)
+                        if (row[k] > m) { m = row[k]; am = k; }
+                    last_state[b0 + s] = am;
+                    logp[b0 + s] = m;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int NN, int S, typename PSI>
+static int launch_viterbi_tile(int64_t B, int64_t T, int M, const double *logpi, const double *logA,
+                               const double *logBsm, const void *obs, int obs_dtype, const int32_t *lengths, PSI *psi,
+                               int32_t *last, double *logp, cudaStream_t st) {
+    using C = VitTile<NN, S>;
+    auto kern = viterbi_tile_kernel<NN, S, PSI>;
+    size_t smem = C::smem_bytes();
+    if (smem > 48 * 1024)
+        KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    KHMM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::THREADS, smem));
+    if (occ < 1) occ = 1;
+    int64_t ngroups = (B + S - 1) / S;
+    int64_t cap = (int64_t)sm_count() * occ;   // persistent: one resident wave, grid-stride over groups
+    int grid = (int)(ngroups < cap ? ngroups : cap);
+    kern<<<grid, C::THREADS, smem, st>>>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp);
+    KHMM_LAUNCH_CHECK("viterbi_tile_kernel");
+    return KHMM_OK;
+}
+
 // One thread per sequence chases the backpointers: path[t] = psi[t+1][path[t+1]] (:236-237).
 template <typename PSI, typename OUT>
 __global__ void viterbi_backtrace_kernel(int64_t B, int64_t T, int N, const int32_t *__restrict__ lengths,
@@ -142,16 +298,25 @@ static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, 
     int32_t *last = reinterpret_cast<int32_t *>(backptr);
     size_t off = (((size_t)B * sizeof(int32_t)) + 255) / 256 * 256;
     PSI *psi = reinterpret_cast<PSI *>(reinterpret_cast<unsigned char *>(backptr) + off);
-    int per_sm = NT <= 64 ? 16 : (NT <= 128 ? 8 : (NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)));
-    if (smem > 48 * 1024) per_sm = (int)max((size_t)1, min((size_t)per_sm, (size_t)(220 * 1024) / smem));
-    int64_t ngroups = (B + S - 1) / S;
-    int64_t cap = (int64_t)sm_count() * per_sm;
-    int grid = (int)(ngroups < cap ? ngroups : cap);
-    auto kern = as ? viterbi_generic_kernel<PSI, true> : viterbi_generic_kernel<PSI, false>;
-    if (smem > 48 * 1024)
-        KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, NT, smem, st>>>(B, T, N, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp);
-    KHMM_LAUNCH_CHECK("viterbi_generic_kernel");
+    int rc_tile = -1;
+    if (sizeof(PSI) == 1 && B >= 64) {   // register-tile kernels (small batches stay on the generic kernel)
+        if (N == 32) rc_tile = launch_viterbi_tile<32, 4, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+        else if (N == 64) rc_tile = launch_viterbi_tile<64, 4, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+        else if (N == 128) rc_tile = launch_viterbi_tile<128, 2, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+    }
+    if (rc_tile > 0) return rc_tile;
+    if (rc_tile < 0) {
+        int per_sm = NT <= 64 ? 16 : (NT <= 128 ? 8 : (NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)));
+        if (smem > 48 * 1024) per_sm = (int)max((size_t)1, min((size_t)per_sm, (size_t)(220 * 1024) / smem));
+        int64_t ngroups = (B + S - 1) / S;
+        int64_t cap = (int64_t)sm_count() * per_sm;
+        int grid = (int)(ngroups < cap ? ngroups : cap);
+        auto kern = as ? viterbi_generic_kernel<PSI, true> : viterbi_generic_kernel<PSI, false>;
+        if (smem > 48 * 1024)
+            KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NT, smem, st>>>(B, T, N, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp);
+        KHMM_LAUNCH_CHECK("viterbi_generic_kernel");
+    }
     int bt = 128;
     int bg = (int)((B + bt - 1) / bt);
     switch (path_dtype) {

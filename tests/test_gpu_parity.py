@@ -163,7 +163,8 @@ def test_multivariate_gaussian_golden(K, golden):
 # ------------------------------------------------------------------------ batched Viterbi
 @pytest.mark.parametrize("N,M,B,T,dtype", [(3, 4, 70, 100, np.int64), (64, 256, 40, 64, np.uint8),
                                            (128, 1024, 9, 40, np.uint16), (300, 16, 5, 30, np.int32),
-                                           (17, 5, 33, 1, np.uint8)])
+                                           (17, 5, 33, 1, np.uint8), (32, 16, 100, 50, np.uint8),
+                                           (64, 256, 70, 64, np.uint8), (128, 1024, 65, 40, np.uint16)])
 def test_viterbi_batch_bit_exact(K, N, M, B, T, dtype):
     h, (pi, A, Bm) = random_discrete(K, N, M, seed=N + M)
     obs = np.random.default_rng(N).integers(0, M, size=(B, T)).astype(dtype)
@@ -189,6 +190,30 @@ def test_viterbi_batch_ragged_and_cuda_tensor_input(K):
         rp, rl = O.viterbi(pi, A, Bm, obs[b, :L].astype(np.int64))
         assert np.array_equal(path[b, :L], rp) and logp[b] == rl
         assert not path[b, L:].any()
+
+
+@pytest.mark.parametrize("N", [32, 64, 128])
+def test_viterbi_register_tile_kernels_ragged(K, N):
+    """B >= 64 with N in {32, 64, 128} takes the register-tile kernel; ragged lengths, exact ties
+    (quantised probabilities) and zero probabilities included."""
+    M, B, T = 12, 97, 37
+    rng = np.random.default_rng(N)
+    A = rng.integers(0, 4, size=(N, N)).astype(np.float64)      # many exact ties and zeros
+    A[np.arange(N), np.arange(N)] += 1
+    A /= A.sum(axis=1, keepdims=True)
+    Bm = rng.integers(1, 4, size=(N, M)).astype(np.float64)
+    Bm /= Bm.sum(axis=1, keepdims=True)
+    pi = np.full(N, 1.0 / N)
+    h = discrete_model(K, pi, A, Bm)
+    obs = rng.integers(0, M, size=(B, T)).astype(np.uint8)
+    lengths = rng.integers(1, T + 1, size=B)
+    path, logp = h.viterbi_batch(obs, lengths=lengths)
+    with np.errstate(divide="ignore"):
+        for b in range(B):
+            L = lengths[b]
+            rp, rl = O.viterbi(pi, A, Bm, obs[b, :L].astype(np.int64))
+            assert np.array_equal(path[b, :L], rp), b
+            assert logp[b] == rl
 
 
 def test_viterbi_with_zero_probabilities(K):
