@@ -186,6 +186,26 @@ int khmm_fwdbwd_loglik_discrete_f32(int64_t B, int64_t T, int N, int M,
                                     double *loglik, double *loglik_bwd, khmm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Tensor-core forward-backward log-likelihood for large state spaces: N a multiple of 128,
+ * 128 <= N <= 1024, all sequences of length T.  One tcgen05 (kind::tf32, fp32 accumulation in
+ * TMEM, TMA-staged operands) launch per time step computes (B x N) x (N x N) for the forward
+ * (abstract_hmm.py:266-270) and the self-scaled backward (:339-349) recursion together, with the
+ * emission evaluation, scaling and row sums fused in the epilogue.  A and AT: the transition
+ * matrix and its transpose.  workspace: khmm_fwdbwd_loglik_tc_workspace_bytes(B, N) bytes,
+ * 256-byte aligned.  loglik_bwd may be NULL (forward only).  tf32 multiplies: log-likelihoods
+ * agree with the float64 reference to ~1e-6 relative (stated bound 2e-5 in the tests).
+ */
+size_t khmm_fwdbwd_loglik_tc_workspace_bytes(int64_t B, int N);
+int khmm_fwdbwd_loglik_tc_gauss_f32(int64_t B, int64_t T, int N, const float *pi, const float *A, const float *AT,
+                                    const float *mean, const float *sd, const void *obs, int obs_dtype,
+                                    void *workspace, size_t workspace_bytes, double *loglik, double *loglik_bwd,
+                                    khmm_stream_t stream);
+int khmm_fwdbwd_loglik_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A,
+                                       const float *AT, const float *Bsm, const void *obs, int obs_dtype,
+                                       void *workspace, size_t workspace_bytes, double *loglik, double *loglik_bwd,
+                                       khmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Baum-Welch E-step -- the statistics DiscreteHMM.do_pass forms (discrete_hmm.py:117-159)
  * from forward, backward, AbstractHMM.zi (abstract_hmm.py:299-325) and gamma (:291-297),
  * with the reference's weighting (gamma carries c_t, zi carries c_{t+1}, gamma[0] is

@@ -323,15 +323,20 @@ class AbstractHMM(object):
         _, gam = engine.backward(p, ob, real, scale, alpha=alpha, want_beta=False, want_gamma=True, gamma_kind=kind)
         return engine.finish(ob, gam, ll)
 
-    def log_likelihood_batch(self, observations, lengths=None, dtype="float32", backward_check=True):
-        """log P(O_b | model) for every sequence.  For N <= 16 in float32 this is the fused
-        forward+backward register kernel: returns `(loglik, loglik_from_backward)`; otherwise the
-        generic forward (second value None)."""
+    def log_likelihood_batch(self, observations, lengths=None, dtype="float32", backward_check=True,
+                             tensor_cores=True):
+        """log P(O_b | model) for every sequence -> `(loglik, loglik_from_backward | None)`.
+        float32, N <= 16: the fused forward+backward register kernel.  float32, N a multiple of 128
+        (<= 1024), equal lengths and `tensor_cores=True`: the tcgen05 (tf32) recursion, forward and
+        backward together.  Otherwise the generic forward kernel (second value None)."""
         ob = self._prep(observations, lengths)
         real, p = self._real(dtype), self._params()
         t = engine.torch()
         if real == t.float32 and p.N <= _lib.SMALL_N_MAX and p.kind in ("discrete", "gauss"):
             ll, llb = engine.fwdbwd_loglik_small(p, ob, both=backward_check)
+            return engine.finish(ob, ll, llb)
+        if real == t.float32 and tensor_cores and engine.tc_supported(p, ob):
+            ll, llb = engine.fwdbwd_loglik_tc(p, ob, both=backward_check)
             return engine.finish(ob, ll, llb)
         _, _, ll = engine.forward(p, ob, real, want_alpha=False, want_scale=False)
         return engine.finish(ob, ll, None)

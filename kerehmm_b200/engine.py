@@ -274,6 +274,32 @@ def fwdbwd_loglik_small(p: ModelParams, ob: Obs, both=True):
     return ll, llb
 
 
+def tc_supported(p: ModelParams, ob: Obs) -> bool:
+    """The tcgen05 recursion covers N = 128, 256, ..., 1024 with equal-length sequences."""
+    return (p.kind in ("discrete", "gauss") and p.N >= 128 and p.N % 128 == 0 and p.N <= 1024
+            and ob.lengths is None)
+
+
+def fwdbwd_loglik_tc(p: ModelParams, ob: Obs, both=True):
+    """Tensor-core (tcgen05, tf32) forward(+backward) log-likelihood -> (loglik, loglik_bwd|None)."""
+    t = require_cuda()
+    dm = DeviceModel(p, t.float32)
+    dev = device()
+    ll = t.empty((ob.B,), dtype=t.float64, device=dev)
+    llb = t.empty((ob.B,), dtype=t.float64, device=dev) if both else None
+    nbytes = _lib.lib().khmm_fwdbwd_loglik_tc_workspace_bytes(ob.B, p.N)
+    ws = t.empty((nbytes + 256,), dtype=t.uint8, device=dev)
+    off = (-ws.data_ptr()) % 256
+    wsp = ws.data_ptr() + off
+    if p.kind == "gauss":
+        _lib.call("khmm_fwdbwd_loglik_tc_gauss_f32", ob.B, ob.T, p.N, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.mean),
+                  ptr(dm.sd), ptr(ob.tensor), ob.code, wsp, nbytes, ptr(ll), ptr(llb), stream_ptr())
+    else:
+        _lib.call("khmm_fwdbwd_loglik_tc_discrete_f32", ob.B, ob.T, p.N, p.M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT),
+                  ptr(dm.Bsm), ptr(ob.tensor), ob.code, wsp, nbytes, ptr(ll), ptr(llb), stream_ptr())
+    return ll, llb
+
+
 _PATH_CODES = {"uint8": _lib.U8, "int16": _lib.U16, "int32": _lib.I32, "int64": _lib.I64}
 
 
