@@ -111,14 +111,29 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void *smem_tile
     d |= (uint64_t)2 << 61;
     return d;
 }
+// MN-major tf32 operand (the contiguous direction is M or N, K strides by the row pitch): the only legal
+// layout is the 128-byte swizzle with 32-byte atoms (layout type 1; TMA: SWIZZLE_128B_ATOM_32B).  Atom =
+// 32 MN elements (128 B) x 4 K-rows; SBO = distance between 4-row K groups, LBO = distance between
+// 32-element MN blocks.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128a32_desc(const void *smem_tile, uint32_t lbo_bytes,
+                                                               uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
 // advance along K inside the swizzle atom: plain byte offset on the start-address field
 __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
 // kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, M x N tile
 //   [4,6) c_format = 1 | [7,10) a_format = 2 | [10,13) b_format = 2 | [15] a_major = 0 | [16] b_major = 0
 //   | [17,23) N >> 3 | [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_major = false, bool b_mn_major = false) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace tc
@@ -129,7 +144,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D fp32 row-major matrix [rows][cols] -> tiles of box_rows x 32 floats (128 B, SWIZZLE_128B)
-inline int make_tmap_f32_rowmajor(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+inline int make_tmap_f32_rowmajor(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                                  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, uint64_t row_stride_floats = 0) {
     static PFN_encodeTiled encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -138,11 +154,11 @@ inline int make_tmap_f32_rowmajor(CUtensorMap *map, const float *base, uint64_t 
         encode = (PFN_encodeTiled)fn;
     }
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * sizeof(float)};
+    cuuint64_t strides[1] = {(row_stride_floats ? row_stride_floats : cols) * sizeof(float)};
     cuuint32_t box[2] = {32, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
