@@ -236,6 +236,26 @@ int khmm_xi_accumulate_f32(int64_t B, int64_t T, int N, const int32_t *lengths,
 int khmm_xi_accumulate_f64(int64_t B, int64_t T, int N, const int32_t *lengths,
                            const double *alpha, const double *V, double *xi_raw, khmm_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused tensor-core E-step for N = 128 states, equal-length sequences (config 4).  One call does,
+ * for a batch chunk, what the three calls above do -- forward (abstract_hmm.py:250-285), backward
+ * (:327-351), gamma (:291-297), zi summed over t (:299-325, discrete_hmm.py:155) and the count sums of
+ * DiscreteHMM.do_pass (discrete_hmm.py:117-159) with the same reference weighting -- in two persistent
+ * tcgen05 kernels (kind::tf32, fp32 accumulation in TMEM): the forward rows stay in tensor memory as
+ * the next step's A operand and are stashed once in HBM; the backward kernel consumes the stash by
+ * TMA, accumulates zi in TMEM and scatters the emission counts with sector-wide L2 reductions.
+ * Adds into `counts` (same layout as above).  workspace: khmm_estep_tc_workspace_bytes(B,T,N,M)
+ * bytes, 1024-byte aligned (holds the [B][T][128] fp32 stash).  alpha_out / scale_out (may be NULL):
+ * caller-visible copies of the stash W[b][t][:] = c_t * alpha_t and of c[b][t] (used by the tests).
+ * tf32 multiplies: statistics agree with the float64 reference to ~1e-3 relative per (sequence, step)
+ * term, unbiased, so re-estimated parameters converge as 1/sqrt(rows) (tests state the bound).
+ */
+size_t khmm_estep_tc_workspace_bytes(int64_t B, int64_t T, int N, int M);
+int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *AT,
+                               const float *Bsm, const void *obs, int obs_dtype, void *workspace,
+                               size_t workspace_bytes, double *counts, float *alpha_out, float *scale_out,
+                               khmm_stream_t stream);
+
 /* M-step on the device -- discrete_hmm.py:132-161 + util.smooth_probabilities (util.py:39-63),
  * float64, operation for operation.  Reads counts (after the all-reduce), A (old, [N][N]);
  * writes pi_new[N], A_new[N][N], B_new state-major [N][M].  status[0] (device int32) gets a

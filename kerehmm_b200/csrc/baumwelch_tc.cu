@@ -1,0 +1,638 @@
+// Tensor-core Baum-Welch E-step for N = 128 states (config 4: DiscreteHMM 128 x 1024, T = 512).
+//
+// Two persistent tcgen05 kernels per batch chunk replace forward (abstract_hmm.py:250-285), backward
+// (:327-351), gamma (:291-297), zi (:299-325) and the count sums of DiscreteHMM.do_pass
+// (discrete_hmm.py:117-159):
+//
+//   bw_forward_tc_kernel   CTA = one tile of 128 sequences, whole time loop inside the kernel.  The row
+//       W_t = c_t alpha_t (unnormalised: its row sum IS the scale factor c_t) stays in TENSOR MEMORY as
+//       the A operand of the next step's MMA (tcgen05.mma with A in TMEM, A^T as a K-major B operand in
+//       shared memory, loaded once by TMA); the epilogue (thread = sequence = TMEM lane) multiplies the
+//       accumulator by the gathered emission row and by 1/c_{t-1}, writes W_t back to TMEM (tf32-rounded)
+//       and to the HBM stash [B][T][128] (fp32), and keeps c_t / log P.  Two CTAs per SM interleave
+//       their MMAs and epilogues.
+//   bw_backward_tc_kernel  CTA = one tile, time loop backwards, one CTA per SM.  Per step:
+//         MMA1  D1 = V_{t+1} . A^T          (A operand = V in TMEM, B operand = A in shared memory)
+//         MMA2  Xi += W_t^T . V2_{t+1}      (both operands MN-major in shared memory: W_t straight from
+//                                            the stash by TMA, V2 = V / c_t written by the epilogue;
+//                                            Xi accumulates in TMEM over the whole tile = zi summed over t)
+//         epilogue  beta_t = D1 / c_{t+1};  gamma_ref = W_t . beta_t  (= alpha beta c_t, abstract_hmm.py:294);
+//                   V_t = b(o_t) . beta_t -> TMEM (next MMA1) and shared memory (next MMA2);
+//                   gamma_ref row -> TMEM staging;  t = 0: smooth1d(gamma[0]) (discrete_hmm.py:132).
+//         RED warps read the staging area back with the 16x256b shape (a quad of lanes = one 32-byte sector
+//         of a row) and add it into row o_t of an fp32 [M+2][128] table in L2 with red.global.add.v2.f32
+//         (rows M, M+1 collect pi and the t = T-1 rows).  Measured: L2 reductions cost ~0.6 sector-ops per
+//         clock per SM whatever the vector width, so full-sector quads are the cheapest form.
+//   bw_fold_kernel adds the fp32 table replicas into the float64 count buffer (include/khmm.h layout).
+//
+// HBM traffic per (sequence, step): 512 B stash write + 512 B stash read + 6 B observations/scales
+// (the generic path moves 2.5 KB).  Precision: tf32 multiplies, fp32 accumulation; tests state the bound.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace khmm {
+
+using namespace tc;
+
+constexpr int BW_N = 128;
+constexpr int BW_SUB = 128 * 32 * 4;   // one [128 rows][32 fp32] sub-tile (16 KB)
+constexpr int BW_TILE = 4 * BW_SUB;    // 128 x 128 fp32 operand tile (64 KB)
+constexpr int BW_REPL = 8;             // fp32 count-table replicas (shorter fp32 accumulation chains)
+// TMEM columns of the backward kernel
+constexpr uint32_t COL_D1 = 0, COL_V = 128, COL_XI = 256, COL_STG = 384;
+
+__device__ __forceinline__ float bw_round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void red_add_v2(float *p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+static __global__ void bw_round_matrix_kernel(const float *__restrict__ in, float *__restrict__ out, int n) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) out[k] = bw_round_tf32(in[k]);
+}
+
+struct BwObs {
+    const void *obs;
+    int dtype, M;
+    int64_t T;
+    __device__ __forceinline__ int sym(int64_t b, int64_t t) const {
+        int s = load_symbol(obs, dtype, b * T + t);
+        return s < 0 ? 0 : (s >= M ? M - 1 : s);
+    }
+};
+
+// ------------------------------------------------------------------------------- forward
+struct __align__(8) FwdBars {
+    uint64_t mat_full, a_ready, d_full;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(160, 2)
+bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__restrict__ pi,
+                     const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T, float *__restrict__ stash,
+                     float *__restrict__ scale, double *__restrict__ loglik) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    FwdBars *bars = (FwdBars *)(tiles + BW_TILE);
+    const int warp = threadIdx.x >> 5;
+    const int64_t ntiles = (B + 127) / 128;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->mat_full, 1);
+        mbar_init(&bars->a_ready, 128);
+        mbar_init(&bars->d_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(&bars->tmem_base, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;   // columns [0,128): accumulator D, [128,256): A operand W
+
+    if (warp == 4) {
+        if (elect_one()) {
+            tma_prefetch_desc(&mapAT);
+            mbar_arrive_expect_tx(&bars->mat_full, BW_TILE);
+            for (int kb = 0; kb < 4; kb++) tma_load_2d(tiles + kb * BW_SUB, &mapAT, &bars->mat_full, kb * 32, 0);
+            mbar_wait(&bars->mat_full, 0);
+            const uint32_t idesc = make_idesc_tf32(128, 128);
+            uint32_t na = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int64_t t = 1; t < T; t++) {
+                    mbar_wait(&bars->a_ready, na & 1);
+                    na++;
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        uint64_t db = make_kmajor_sw128_desc(tiles + (k >> 2) * BW_SUB);
+                        mma_tf32_ts(tmem, tmem + 128 + k * 8, desc_advance(db, (k & 3) * 32), idesc, k != 0);
+                    }
+                    tc_commit(&bars->d_full);
+                }
+        }
+    } else {
+        const int row = threadIdx.x;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        uint32_t nd = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t b = tile * 128 + row;
+            const bool live = b < B;
+            const int64_t bc = live ? b : B - 1;
+            float r = 1.f;           // 1 / c_{t-1}
+            float prod = 1.f;        // mantissa of prod_t c_t
+            int esum = 0;            // its exponent
+            for (int64_t t = 0; t < T; t++) {
+                const float *brow = Bsm + (int64_t)ob.sym(bc, t) * BW_N;
+                float *srow = stash + (b * T + t) * BW_N;
+                if (t > 0) {
+                    mbar_wait(&bars->d_full, nd & 1);
+                    nd++;
+                    tc_fence_after();
+                }
+                float rowsum = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BW_N; c0 += 32) {
+                    uint32_t acc[32];
+                    float e[32];
+                    if (t > 0) tmem_ld_32x32(tmem + lane_base + c0, acc);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        float4 f = ldg4(brow + c0 + 4 * q);
+                        e[4 * q] = f.x; e[4 * q + 1] = f.y; e[4 * q + 2] = f.z; e[4 * q + 3] = f.w;
+                    }
+                    if (t > 0) {
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            float4 f = ldg4(pi + c0 + 4 * q);
+                            acc[4 * q] = __float_as_uint(f.x); acc[4 * q + 1] = __float_as_uint(f.y);
+                            acc[4 * q + 2] = __float_as_uint(f.z); acc[4 * q + 3] = __float_as_uint(f.w);
+                        }
+                    }
+                    uint32_t w[32];
+#pragma unroll
+                    for (int q = 0; q < 32; q++) {
+                        float v = __uint_as_float(acc[q]) * r * e[q];
+                        rowsum += v;
+                        e[q] = v;
+                        w[q] = __float_as_uint(bw_round_tf32(v));
+                    }
+                    if (t + 1 < T) tmem_st_32x32(tmem + lane_base + 128 + c0, w);
+                    if (live) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            reinterpret_cast<float4 *>(srow + c0)[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+                    }
+                }
+                if (t + 1 < T) {
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&bars->a_ready);
+                }
+                if (live) scale[b * T + t] = rowsum;
+                r = 1.0f / rowsum;
+                int ex;
+                prod = frexpf(prod * rowsum, &ex);
+                esum += ex;
+            }
+            if (live) loglik[b] = (double)esum * 0.6931471805599453 + log((double)prod);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------ backward
+struct __align__(8) BwdBars {
+    uint64_t mat_full, alpha_full, alpha_empty, v_ready, d1_full, mma2_done, stage_full, stage_empty;
+    uint32_t tmem_base;
+};
+
+struct BwdOut {
+    float *tab;        // [BW_REPL][M+2][128] fp32 count table (row M: pi, row M+1: gamma_ref at t = T-1)
+    double *xi;        // counts.xi [128][128]
+    double *flags;     // counts tail + 2
+};
+
+__global__ void __launch_bounds__(320, 1)
+bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapStash,
+                      const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T, const float *__restrict__ scale,
+                      BwdOut out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *sA = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // A, K-major SW128
+    unsigned char *sW = sA + BW_TILE;      // W_t tile, MN-major (TMA, SWIZZLE_128B_ATOM_32B)
+    unsigned char *sV = sW + BW_TILE;      // V2_{t+1} tile, MN-major (written by the epilogue)
+    BwdBars *bars = (BwdBars *)(sV + BW_TILE);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (B + 127) / 128;
+    const int M = ob.M;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->mat_full, 1);
+        mbar_init(&bars->alpha_full, 1);
+        mbar_init(&bars->alpha_empty, 5);
+        mbar_init(&bars->v_ready, 128);
+        mbar_init(&bars->d1_full, 1);
+        mbar_init(&bars->mma2_done, 1);
+        mbar_init(&bars->stage_full, 128);
+        mbar_init(&bars->stage_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 4) {
+        // ------------------------------------------------ TMA producer: A once, then W_t tiles of the stash
+        if (elect_one()) {
+            tma_prefetch_desc(&mapA);
+            tma_prefetch_desc(&mapStash);
+            mbar_arrive_expect_tx(&bars->mat_full, BW_TILE);
+            for (int kb = 0; kb < 4; kb++) tma_load_2d(sA + kb * BW_SUB, &mapA, &bars->mat_full, kb * 32, 0);
+            uint32_t np = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int64_t t = T - 1; t >= 0; t--) {
+                    mbar_wait(&bars->alpha_empty, (np & 1) ^ 1);
+                    np++;
+                    mbar_arrive_expect_tx(&bars->alpha_full, BW_TILE);
+                    for (int c = 0; c < 4; c++)
+                        tma_load_3d(sW + c * BW_SUB, &mapStash, &bars->alpha_full, c * 32, (int)t, (int)(tile * 128));
+                }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            mbar_wait(&bars->mat_full, 0);
+            const uint32_t idesc_k = make_idesc_tf32(128, 128);
+            const uint32_t idesc_mn = make_idesc_tf32(128, 128, true, true);
+            const uint64_t dW = make_mnmajor_sw128a32_desc(sW, BW_SUB, 512);
+            const uint64_t dV = make_mnmajor_sw128a32_desc(sV, BW_SUB, 512);
+            uint32_t nv = 0, nfull = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                nfull++;   // step t = T-1 has no MMA2 (the epilogue releases W_{T-1} twice on our behalf)
+                for (int64_t t = T - 2; t >= 0; t--) {
+                    mbar_wait(&bars->v_ready, nv & 1);
+                    nv++;
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        uint64_t db = make_kmajor_sw128_desc(sA + (k >> 2) * BW_SUB);
+                        mma_tf32_ts(tmem + COL_D1, tmem + COL_V + k * 8, desc_advance(db, (k & 3) * 32), idesc_k, k != 0);
+                    }
+                    tc_commit(&bars->d1_full);
+                    mbar_wait(&bars->alpha_full, nfull & 1);
+                    nfull++;
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        mma_tf32_ss(tmem + COL_XI, desc_advance(dW, k * 1024), desc_advance(dV, k * 1024), idesc_mn,
+                                    (t != T - 2) || k != 0);
+                    tc_commit(&bars->mma2_done);
+                    tc_commit(&bars->alpha_empty);
+                }
+            }
+        }
+    } else if (warp < 4) {
+        // ------------------------------------------------ epilogue: thread = sequence = TMEM lane
+        const int row = threadIdx.x;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const int sw = row & 3;   // Swizzle<2,5,2>: 32-byte chunk index ^= row & 3
+        uint32_t nd = 0, nm = 0, nfull = 0, nstage = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t b = tile * 128 + row;
+            const bool live = b < B;
+            const int64_t bc = live ? b : B - 1;
+            for (int64_t t = T - 1; t >= 0; t--) {
+                const bool last = (t == T - 1);
+                const float *brow = Bsm + (int64_t)ob.sym(bc, t) * BW_N;
+                const float rc1 = last ? 1.f : 1.0f / scale[bc * T + t + 1];
+                const float rcm1 = t > 0 ? 1.0f / scale[bc * T + t - 1] : 0.f;
+                if (!last) {
+                    mbar_wait(&bars->d1_full, nd & 1);
+                    nd++;
+                    tc_fence_after();
+                }
+                mbar_wait(&bars->alpha_full, nfull & 1);
+                nfull++;
+                // gamma_ref chunk: W_t . beta_t  (beta = 1 at t = T-1)
+                auto gchunk = [&](int c0, float (&g)[32], float (&beta)[32]) {
+                    uint32_t acc[32];
+                    if (!last) tmem_ld_32x32(tmem + lane_base + COL_D1 + c0, acc);
+                    const unsigned char *wrow = sW + (c0 >> 5) * BW_SUB + row * 128;
+#pragma unroll
+                    for (int c32 = 0; c32 < 4; c32++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            float4 f = *reinterpret_cast<const float4 *>(wrow + (((c32 ^ sw) << 5) | (h << 4)));
+                            int q = c32 * 8 + h * 4;
+                            g[q] = f.x; g[q + 1] = f.y; g[q + 2] = f.z; g[q + 3] = f.w;
+                        }
+                    if (!last) tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 32; q++) {
+                        beta[q] = last ? 1.f : __uint_as_float(acc[q]) * rc1;
+                        g[q] *= beta[q];
+                    }
+                };
+                float sub = 0.f, inv = 1.f, floorv = 0.f;
+                if (t == 0) {
+                    // pi_new = smooth1d(gamma[0]) in place (discrete_hmm.py:132, util.py:56-60)
+                    int k = 0;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BW_N; c0 += 32) {
+                        float g[32], beta[32];
+                        gchunk(c0, g, beta);
+#pragma unroll
+                        for (int q = 0; q < 32; q++) k += (g[q] < 1e-10f) ? 1 : 0;
+                    }
+                    if (k >= BW_N) {
+                        if (live) atomicAdd(out.flags, 1.0);
+                        k = BW_N - 1;
+                    }
+                    sub = (float)((double)k * 1e-10 / (double)(BW_N - k));
+                    floorv = 1e-10f;
+                    float sum = 0.f;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BW_N; c0 += 32) {
+                        float g[32], beta[32];
+                        gchunk(c0, g, beta);
+#pragma unroll
+                        for (int q = 0; q < 32; q++) sum += fmaxf(g[q] - sub, floorv);
+                    }
+                    inv = 1.0f / sum;
+                }
+                mbar_wait(&bars->stage_empty, (nstage & 1) ^ 1);
+                nstage++;
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < BW_N; c0 += 32) {
+                    float g[32], beta[32];
+                    gchunk(c0, g, beta);
+                    uint32_t u[32];
+#pragma unroll
+                    for (int q = 0; q < 32; q++) u[q] = __float_as_uint(fmaxf(g[q] - sub, floorv) * inv);
+                    tmem_st_32x32(tmem + lane_base + COL_STG + c0, u);
+                    if (t > 0) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            float4 f = ldg4(brow + c0 + 4 * q);
+                            u[4 * q] = __float_as_uint(bw_round_tf32(f.x * beta[4 * q]));
+                            u[4 * q + 1] = __float_as_uint(bw_round_tf32(f.y * beta[4 * q + 1]));
+                            u[4 * q + 2] = __float_as_uint(bw_round_tf32(f.z * beta[4 * q + 2]));
+                            u[4 * q + 3] = __float_as_uint(bw_round_tf32(f.w * beta[4 * q + 3]));
+                        }
+                        tmem_st_32x32(tmem + lane_base + COL_V + c0, u);
+                    }
+                }
+                // W_t has been read: hand the buffer back to the TMA producer (MMA2 adds its own arrival)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->alpha_empty);
+                // t = T-1 has no MMA2: its arrival is made here, inside the same barrier phase (an early
+                // arrival by the MMA thread could land in the previous tile's last phase)
+                if (last && threadIdx.x == 0) mbar_arrive(&bars->alpha_empty);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->stage_full);
+                if (!last) {
+                    // MMA2(t) reads V2_{t+1} from shared memory: wait before overwriting it
+                    mbar_wait(&bars->mma2_done, nm & 1);
+                    nm++;
+                    tc_fence_after();
+                }
+                if (t > 0) {
+                    // V2_t = V_t / c_{t-1} -> shared memory, MN-major Swizzle<2,5,2> (B operand of MMA2(t-1))
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BW_N; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem + lane_base + COL_V + c0, v);
+                        tmem_ld_wait();
+                        unsigned char *vrow = sV + (c0 >> 5) * BW_SUB + row * 128;
+#pragma unroll
+                        for (int c32 = 0; c32 < 4; c32++)
+#pragma unroll
+                            for (int h = 0; h < 2; h++) {
+                                int q = c32 * 8 + h * 4;
+                                float4 f = make_float4(bw_round_tf32(__uint_as_float(v[q]) * rcm1),
+                                                       bw_round_tf32(__uint_as_float(v[q + 1]) * rcm1),
+                                                       bw_round_tf32(__uint_as_float(v[q + 2]) * rcm1),
+                                                       bw_round_tf32(__uint_as_float(v[q + 3]) * rcm1));
+                                *reinterpret_cast<float4 *>(vrow + (((c32 ^ sw) << 5) | (h << 4))) = f;
+                            }
+                    }
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(&bars->v_ready);
+                } else if (T > 1) {
+                    // tile done: Xi[i][j] (lane = i) -> float64 counts
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BW_N; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem + lane_base + COL_XI + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 32; q++) atomicAdd(out.xi + row * BW_N + c0 + q, (double)__uint_as_float(v[q]));
+                    }
+                    tc_fence_before();
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------ RED warps: staging rows -> fp32 count table in L2
+        const int quad = warp & 3;    // TMEM lane quadrant this warp may access
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        float *tab = out.tab + (size_t)(blockIdx.x % BW_REPL) * (size_t)(M + 2) * BW_N;
+        const int colq = 2 * (lane & 3);
+        uint32_t ns = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int64_t bq[4];
+            bool lv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                bq[k] = tile * 128 + quad * 32 + k * 8 + (lane >> 2);
+                lv[k] = bq[k] < B;
+            }
+            for (int64_t t = T - 1; t >= 0; t--) {
+                int sym[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) sym[k] = lv[k] ? ob.sym(bq[k], t) : 0;
+                mbar_wait(&bars->stage_full, ns & 1);
+                ns++;
+                tc_fence_after();
+                uint32_t r[8][16];
+#pragma unroll
+                for (int half = 0; half < 2; half++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        tmem_ld_16x256_x4(tmem + lane_base + ((uint32_t)(half * 16) << 16) + COL_STG + c * 32, r[half * 4 + c]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->stage_empty);
+#pragma unroll
+                for (int half = 0; half < 2; half++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int k = half * 2 + e;   // row = quad*32 + 8k + lane/4
+                        if (!lv[k]) continue;
+                        float *dst = tab + (size_t)sym[k] * BW_N + colq;
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+#pragma unroll
+                            for (int n = 0; n < 4; n++)
+                                red_add_v2(dst + c * 32 + 8 * n, __uint_as_float(r[half * 4 + c][4 * n + 2 * e]),
+                                           __uint_as_float(r[half * 4 + c][4 * n + 2 * e + 1]));
+                        if (t == 0 || t == T - 1) {
+#pragma unroll 1
+                            for (int which = 0; which < 2; which++) {
+                                if ((which == 0 && t != 0) || (which == 1 && t != T - 1)) continue;
+                                float *d2 = tab + (size_t)(M + which) * BW_N + colq;
+#pragma unroll
+                                for (int c = 0; c < 4; c++)
+#pragma unroll
+                                    for (int n = 0; n < 4; n++)
+                                        red_add_v2(d2 + c * 32 + 8 * n, __uint_as_float(r[half * 4 + c][4 * n + 2 * e]),
+                                                   __uint_as_float(r[half * 4 + c][4 * n + 2 * e + 1]));
+                            }
+                        }
+                    }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
+// Fold the fp32 table replicas into the float64 count buffer:
+//   emis_num[k][i] += sum_r tab[r][k][i];  emis_den[i] += sum_k (that);  pi[i] += row M;
+//   gam[i] += emis_den part - row M+1 (gamma_ref summed over t < T-1);  loglik, nseq.
+static __global__ void bw_fold_kernel(const float *__restrict__ tab, int M, double *__restrict__ counts,
+                                      const double *__restrict__ loglik, int64_t B) {
+    const int i = threadIdx.x;   // 128 threads
+    double *c_pi = counts;
+    double *c_gam = c_pi + BW_N + BW_N * BW_N;
+    double *c_num = c_gam + BW_N;
+    double *c_den = c_num + (int64_t)M * BW_N;
+    double *c_tail = c_den + BW_N;
+    const size_t rstride = (size_t)(M + 2) * BW_N;
+    double den = 0.0;
+    for (int k = blockIdx.x; k < M + 2; k += gridDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < BW_REPL; r++) s += (double)tab[r * rstride + (size_t)k * BW_N + i];
+        if (k < M) {
+            c_num[(int64_t)k * BW_N + i] += s;
+            den += s;
+        } else if (k == M) {
+            atomicAdd(c_pi + i, s);
+        } else {
+            atomicAdd(c_gam + i, -s);
+        }
+    }
+    atomicAdd(c_den + i, den);
+    atomicAdd(c_gam + i, den);
+    // log-likelihood sum
+    double ll = 0.0;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + i; b < B; b += (int64_t)gridDim.x * blockDim.x) ll += loglik[b];
+    ll = warp_sum(ll);
+    if ((i & 31) == 0) atomicAdd(c_tail, ll);
+    if (blockIdx.x == 0 && i == 0) atomicAdd(c_tail + 1, (double)B);
+}
+
+struct BwWorkspace {
+    float *stash, *scale, *tab, *Ar, *ATr;
+    double *loglik;
+    size_t bytes;
+};
+
+static BwWorkspace bw_layout(void *ws, int64_t B, int64_t T, int M) {
+    auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+    BwWorkspace w;
+    size_t o = 0;
+    unsigned char *p = (unsigned char *)ws;
+    w.stash = (float *)(p + o);  o += up((size_t)B * T * BW_N * 4);
+    w.scale = (float *)(p + o);  o += up((size_t)B * T * 4);
+    w.tab = (float *)(p + o);    o += up((size_t)BW_REPL * (M + 2) * BW_N * 4);
+    w.Ar = (float *)(p + o);     o += up((size_t)BW_N * BW_N * 4);
+    w.ATr = (float *)(p + o);    o += up((size_t)BW_N * BW_N * 4);
+    w.loglik = (double *)(p + o); o += up((size_t)B * 8);
+    w.bytes = o;
+    return w;
+}
+
+static int make_tmap_stash(CUtensorMap *map, const float *stash, int64_t B, int64_t T) {
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
+        encode = (PFN_encodeTiled)fn;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)BW_N, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)BW_N * 4, (cuuint64_t)T * BW_N * 4};
+    cuuint32_t box[3] = {32, 1, 128};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)stash, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+}  // namespace khmm
+
+using namespace khmm;
+
+extern "C" {
+
+size_t khmm_estep_tc_workspace_bytes(int64_t B, int64_t T, int N, int M) {
+    if (N != BW_N || B < 0 || T < 1 || M < 1) return 0;
+    return bw_layout(nullptr, B, T, M).bytes;
+}
+
+int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *AT,
+                               const float *Bsm, const void *obs, int obs_dtype, void *workspace,
+                               size_t workspace_bytes, double *counts, float *alpha_out, float *scale_out,
+                               khmm_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KHMM_REQUIRE(B >= 0 && T >= 1 && M >= 1, "estep_tc: bad shape");
+    if (N != BW_N) {
+        set_error("estep_tc: the fused tensor-core E-step covers N = %d (got %d)", BW_N, N);
+        return KHMM_ERR_UNSUPPORTED;
+    }
+    if (T > 0x7fffffff || B > 0x7fffff00) {
+        set_error("estep_tc: B and T must fit a 32-bit tensor-map coordinate");
+        return KHMM_ERR_UNSUPPORTED;
+    }
+    if (B == 0) return KHMM_OK;
+    KHMM_REQUIRE(pi && A && AT && Bsm && obs && workspace && counts, "estep_tc: NULL pointer argument");
+    KHMM_REQUIRE(obs_dtype >= KHMM_U8 && obs_dtype <= KHMM_I64, "estep_tc: obs dtype code %d is not an integer type",
+                 obs_dtype);
+    KHMM_REQUIRE(((uintptr_t)workspace & 1023) == 0, "estep_tc: workspace must be 1024-byte aligned");
+    BwWorkspace w = bw_layout(workspace, B, T, M);
+    KHMM_REQUIRE(workspace_bytes >= w.bytes, "estep_tc: workspace too small");
+    if (alpha_out) w.stash = alpha_out;   // caller-visible stash (tests): W_t = c_t alpha_t
+    if (scale_out) w.scale = scale_out;
+    KHMM_REQUIRE(((uintptr_t)w.stash & 15) == 0, "estep_tc: stash must be 16-byte aligned");
+
+    bw_round_matrix_kernel<<<16, 256, 0, st>>>(A, w.Ar, BW_N * BW_N);
+    bw_round_matrix_kernel<<<16, 256, 0, st>>>(AT, w.ATr, BW_N * BW_N);
+    KHMM_CUDA_CHECK(cudaMemsetAsync(w.tab, 0, (size_t)BW_REPL * (M + 2) * BW_N * 4, st));
+    CUtensorMap mapAT, mapA, mapStash;
+    if (make_tmap_f32_rowmajor(&mapAT, w.ATr, BW_N, BW_N, 128) || make_tmap_f32_rowmajor(&mapA, w.Ar, BW_N, BW_N, 128) ||
+        make_tmap_stash(&mapStash, w.stash, B, T)) {
+        set_error("estep_tc: tensor map creation failed");
+        return KHMM_ERR_CUDA;
+    }
+    const int64_t ntiles = (B + 127) / 128;
+    const int sms = sm_count();
+    BwObs ob{obs, obs_dtype, M, T};
+    {
+        size_t smem = BW_TILE + sizeof(FwdBars) + 1024;
+        KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = (int)(ntiles < 2 * sms ? ntiles : 2 * sms);
+        bw_forward_tc_kernel<<<grid, 160, smem, st>>>(mapAT, pi, Bsm, ob, B, T, w.stash, w.scale, w.loglik);
+        KHMM_LAUNCH_CHECK("bw_forward_tc_kernel");
+    }
+    {
+        size_t smem = 3 * (size_t)BW_TILE + sizeof(BwdBars) + 1024;
+        KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = (int)(ntiles < sms ? ntiles : sms);
+        double *c_xi = counts + BW_N;
+        double *c_tail = counts + BW_N + (size_t)BW_N * BW_N + BW_N + (size_t)M * BW_N + BW_N;
+        BwdOut out{w.tab, c_xi, c_tail + 2};
+        bw_backward_tc_kernel<<<grid, 320, smem, st>>>(mapA, mapStash, Bsm, ob, B, T, w.scale, out);
+        KHMM_LAUNCH_CHECK("bw_backward_tc_kernel");
+    }
+    bw_fold_kernel<<<64, 128, 0, st>>>(w.tab, M, counts, w.loglik, B);
+    KHMM_LAUNCH_CHECK("bw_fold_kernel");
+    return KHMM_OK;
+}
+
+}  // extern "C"

@@ -81,38 +81,44 @@ class DiscreteHMM(AbstractHMM):
         t = engine.require_cuda()
         p = self._params()
         ob = self._prep(observations, single=True)
-        counts = engine.estep_discrete(p, ob, t.float64)
+        counts = engine.estep_discrete(p, ob, t.float64, tensor_cores=False)
         self._assign(*engine.mstep_discrete(p, counts))
         if verbose:
             print("do_pass() returning\n  initial: {}\n  transition: {}\n  emission: {}".format(
                 self.initialProbabilities, self.transitionMatrix, self.emission_matrix()))
 
-    def estep_batch(self, observations, lengths=None, dtype="float32", chunk=None, counts=None):
+    def estep_batch(self, observations, lengths=None, dtype="float32", chunk=None, counts=None,
+                    tensor_cores="auto"):
         """Reference-weighted sufficient statistics summed over a batch as an
-        `engine.Counts` on the device -- the buffer that is all-reduced across GPUs."""
+        `engine.Counts` on the device -- the buffer that is all-reduced across GPUs.
+        tensor_cores: True / False / "auto".  The fused tcgen05 (tf32) E-step covers N = 128,
+        float32, equal lengths; "auto" takes it from 2**22 (sequence, step) rows, where its
+        unbiased per-term rounding error has averaged out below the float32 bound."""
         ob = self._prep(observations, lengths)
-        return engine.estep_discrete(self._params(), ob, self._real(dtype), counts=counts, chunk=chunk)
+        return engine.estep_discrete(self._params(), ob, self._real(dtype), counts=counts, chunk=chunk,
+                                     tensor_cores=tensor_cores)
 
-    def do_pass_batch(self, observations, lengths=None, dtype="float32", chunk=None, group=None):
+    def do_pass_batch(self, observations, lengths=None, dtype="float32", chunk=None, group=None,
+                      tensor_cores="auto"):
         """One Baum-Welch pass over a batch of sequences (this rank's shard when torch.distributed
         is initialised: the packed counts are all-reduced before the M-step, which every rank then
         performs identically).  Returns the summed log-likelihood of the batch under the OLD
         parameters."""
         from . import dist
         p = self._params()
-        counts = self.estep_batch(observations, lengths, dtype, chunk)
+        counts = self.estep_batch(observations, lengths, dtype, chunk, tensor_cores=tensor_cores)
         dist.all_reduce_counts(counts.buf, group=group)
         loglik = float(counts.buf[counts.sl["tail"]][0].item())
         self._assign(*engine.mstep_discrete(p, counts))
         return loglik
 
     def train_batch(self, observations, lengths=None, iterations=10, dtype="float32", chunk=None, group=None,
-                    tol=None):
+                    tol=None, tensor_cores="auto"):
         """`iterations` batched Baum-Welch passes; returns the list of per-pass log-likelihoods.
         Stops early when `tol` is given and the log-likelihood gain drops below it."""
         history = []
         for _ in range(iterations):
-            history.append(self.do_pass_batch(observations, lengths, dtype, chunk, group))
+            history.append(self.do_pass_batch(observations, lengths, dtype, chunk, group, tensor_cores))
             if tol is not None and len(history) > 1 and history[-1] - history[-2] <= tol:
                 break
         return history

@@ -376,12 +376,60 @@ def estep_chunk_size(B, T, N, esize, reserve=0.75):
     return int(max(1, min(B, (free * reserve) // per_seq)))
 
 
-def estep_discrete(p: ModelParams, ob: Obs, real, counts: Counts = None, chunk=None):
-    """Accumulate the reference-weighted Baum-Welch statistics of a batch into `counts`."""
+# rows (sequences x steps) from which `tensor_cores="auto"` picks the tf32 E-step: its per-term
+# rounding error (~5e-4, unbiased) averages out as 1/sqrt(rows per count), see DESIGN.md 3.5
+TC_AUTO_MIN_ROWS = 1 << 22
+
+
+def estep_tc_supported(p: ModelParams, ob: Obs, real) -> bool:
+    """The fused tcgen05 E-step covers N = 128, float32, equal-length sequences."""
+    return (p.kind == "discrete" and p.N == 128 and ob.lengths is None and real == torch().float32
+            and ob.T < 2 ** 31)
+
+
+def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=None, stash_out=False):
+    """Fused tensor-core E-step (khmm_estep_tc_discrete_f32).  With `stash_out` also returns the
+    forward stash W[b][t][:] = c_t alpha_t and the scale factors of the LAST chunk (tests)."""
+    t = require_cuda()
+    dm = DeviceModel(p, t.float32)
+    N, M, dev = p.N, p.M, device()
+    counts = counts or Counts(N, M)
+    L = _lib.lib()
+    if chunk is None:
+        free, _ = t.cuda.mem_get_info()
+        per_seq = ob.T * N * 4 + ob.T * 4 + 16
+        chunk = int(max(128, min(ob.B, (free * 0.8) // per_seq)))
+        if chunk < ob.B:
+            chunk -= chunk % 128
+    nb0 = min(chunk, ob.B)
+    nbytes = L.khmm_estep_tc_workspace_bytes(nb0, ob.T, N, M)
+    ws = t.empty((nbytes + 1024,), dtype=t.uint8, device=dev)
+    wsp = ws.data_ptr() + (-ws.data_ptr()) % 1024
+    W = sc = None
+    if stash_out:
+        W = t.zeros((nb0, ob.T, N), dtype=t.float32, device=dev)
+        sc = t.zeros((nb0, ob.T), dtype=t.float32, device=dev)
+    for b0 in range(0, ob.B, chunk):
+        nb = min(chunk, ob.B - b0)
+        obs_c = ob.tensor[b0:b0 + nb]
+        _lib.call("khmm_estep_tc_discrete_f32", nb, ob.T, N, M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.Bsm),
+                  ptr(obs_c), ob.code, wsp, nbytes, ptr(counts.buf), ptr(W), ptr(sc), stream_ptr())
+    if stash_out:
+        return counts, W, sc
+    return counts
+
+
+def estep_discrete(p: ModelParams, ob: Obs, real, counts: Counts = None, chunk=None, tensor_cores="auto"):
+    """Accumulate the reference-weighted Baum-Welch statistics of a batch into `counts`.
+    tensor_cores: True / False / "auto" (tf32 tcgen05 path for N = 128 once the batch is large)."""
     t = require_cuda()
     if p.kind != "discrete":
         raise NotImplementedError("Baum-Welch is defined for discrete emissions "
                                   "(GaussianHMM.do_pass is broken in the reference, SURVEY.md Q9)")
+    if tensor_cores == "auto":
+        tensor_cores = ob.B * ob.T >= TC_AUTO_MIN_ROWS
+    if tensor_cores and estep_tc_supported(p, ob, real):
+        return estep_discrete_tc(p, ob, counts=counts, chunk=chunk)
     dm = DeviceModel(p, real)
     N, M, dev = p.N, p.M, device()
     counts = counts or Counts(N, M)

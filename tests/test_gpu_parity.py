@@ -370,6 +370,75 @@ def test_do_pass_batch_matches_oracle(K, N, M, B, T, dtype):
     np.testing.assert_allclose(h.emission_matrix(), rB, rtol=rtol, atol=1e-14)
 
 
+# tf32 tensor-core E-step: every (sequence, step) term carries an unbiased ~5e-4 relative rounding
+# error (10-bit mantissa operands), so single entries of the statistics are compared at 1e-2 and
+# sums over many terms much tighter; DESIGN.md 3.5 states the bound.
+TC_TERM_RTOL = 1e-2
+
+
+@pytest.mark.parametrize("M,B,T,odt", [(64, 300, 40, np.int64), (1024, 128, 33, np.uint16), (9, 77, 2, np.uint8),
+                                       (16, 130, 1, np.int32)])
+def test_tensor_core_estep_matches_oracle(K, M, B, T, odt):
+    """Fused tcgen05 E-step (N = 128): forward stash, scale factors and all reference-weighted
+    statistics against the float64 oracle, including a partial last tile (B % 128 != 0)."""
+    from kerehmm_b200 import engine
+    N = 128
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=70 + M)
+    obs = np.random.default_rng(71).integers(0, M, size=(B, T)).astype(odt)
+    o64 = obs.astype(np.int64)
+    counts, W, sc = engine.estep_discrete_tc(h._params(), h._prep(obs), stash_out=True)
+    W, sc, c = W.cpu().numpy(), sc.cpu().numpy(), counts.host()
+    alpha, scale = O.forward(pi, A, O.emissions_discrete(Bm, o64))
+    np.testing.assert_allclose(sc, scale, rtol=2e-3)
+    np.testing.assert_allclose(W / sc[..., None], alpha, rtol=TC_TERM_RTOL, atol=1e-6)
+    stats = None
+    for b in range(B):
+        s_ = O.sequence_stats_discrete(pi, A, Bm, o64[b])
+        stats = s_ if stats is None else {k: stats[k] + s_[k] for k in s_}
+    assert c["nseq"] == B and c["flags"] == 0
+    assert np.isclose(c["loglik"], stats["loglik"], rtol=2e-5)
+    np.testing.assert_allclose(c["pi"], stats["pi"], rtol=TC_TERM_RTOL, atol=1e-7)
+    np.testing.assert_allclose(c["emis_den"], stats["emis_den"], rtol=2e-3)
+    np.testing.assert_allclose(c["gam"], stats["gam"], rtol=2e-3, atol=2e-6 * stats["emis_den"].max())
+    np.testing.assert_allclose(c["emis_num"], stats["emis_num"], rtol=TC_TERM_RTOL, atol=1e-7 * stats["emis_num"].max())
+    if T > 1:
+        np.testing.assert_allclose(c["xi_raw"] * A, stats["xi"], rtol=TC_TERM_RTOL, atol=1e-7 * stats["xi"].max())
+    else:
+        assert not c["xi_raw"].any()
+
+
+def test_tensor_core_estep_many_tiles_vs_simt(K):
+    """More tiles than CTAs (each CTA walks several tiles) and chunking: the tf32 statistics against
+    the float32 SIMT path, which is itself pinned to the oracle above.  Sums over ~1e3..1e5 terms
+    agree far tighter than single terms."""
+    N, M, B, T = 128, 32, 148 * 128 * 2 + 300, 6
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=75)
+    obs = np.random.default_rng(76).integers(0, M, size=(B, T)).astype(np.uint8)
+    ref = h.estep_batch(obs, tensor_cores=False).host()
+    for chunk in (None, 128 * 100):
+        c = h.estep_batch(obs, tensor_cores=True, chunk=chunk).host()
+        assert c["nseq"] == B and c["flags"] == 0
+        assert np.isclose(c["loglik"], ref["loglik"], rtol=1e-5)
+        for key in ("pi", "gam", "emis_den", "emis_num", "xi_raw"):
+            np.testing.assert_allclose(c[key], ref[key], rtol=5e-4, err_msg=key)
+
+
+def test_tensor_core_do_pass_batch(K):
+    """One Baum-Welch pass through the public API with tensor_cores=True: re-estimated parameters
+    against the oracle's M-step at the stated tf32 bound; they stay valid distributions."""
+    N, M, B, T = 128, 48, 512, 64
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=77)
+    obs = np.random.default_rng(78).integers(0, M, size=(B, T))
+    stats = O.batch_stats_discrete(pi, A, Bm, obs)
+    rpi, rA, rB = O.mstep_discrete(stats)
+    ll = h.do_pass_batch(obs, tensor_cores=True)
+    assert np.isclose(ll, stats["loglik"], rtol=2e-5)
+    np.testing.assert_allclose(h.transitionMatrix, rA, rtol=2e-3)
+    np.testing.assert_allclose(h.emission_matrix(), rB, rtol=2e-3)
+    np.testing.assert_allclose(h.initialProbabilities, rpi, rtol=2e-3)
+    h.sanity_check()
+
+
 def test_train_batch_matches_oracle_iterations(K):
     """Several batched passes (float64) track the oracle's multi-sequence definition pass by pass.
     (The reference's weighting is not textbook EM, so the likelihood need not increase.)"""
