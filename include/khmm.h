@@ -245,8 +245,10 @@ int khmm_xi_accumulate_f64(int64_t B, int64_t T, int N, const int32_t *lengths,
  * the next step's A operand and are stashed once in HBM; the backward kernel consumes the stash by
  * TMA, accumulates zi in TMEM and scatters the emission counts with sector-wide L2 reductions.
  * Adds into `counts` (same layout as above).  workspace: khmm_estep_tc_workspace_bytes(B,T,N,M)
- * bytes, 1024-byte aligned (holds the [B][T][128] fp32 stash).  alpha_out / scale_out (may be NULL):
- * caller-visible copies of the stash W[b][t][:] = c_t * alpha_t and of c[b][t] (used by the tests).
+ * bytes, 1024-byte aligned (holds the fp32 stash).  alpha_out / scale_out (may be NULL): caller-visible
+ * copies of the stash -- tile-major [ceil(B/128)][T][128][128] floats, W[b/128][t][b%128][:] = c_t * alpha_t,
+ * one contiguous 64 KB block per (tile of 128 sequences, step) -- and of the scale factors, tile-major
+ * [ceil(B/128)][T][128], c[b/128][t][b%128] (used by the tests).
  * tf32 multiplies: statistics agree with the float64 reference to ~1e-3 relative per (sequence, step)
  * term, unbiased, so re-estimated parameters converge as 1/sqrt(rows) (tests state the bound).
  */

@@ -114,6 +114,8 @@ class AbstractHMM(object):
             self.verbose = verbose
         try:
             assert np.isclose(self.initialProbabilities.sum(), 1)
+            if not self.verbose and np.isclose(np.asarray(self.transitionMatrix).sum(axis=1), 1).all():
+                return          # fast path: one vectorised check instead of N Python-level ones
             if self.verbose:
                 print("SANITY CHECK: transmat\n{}".format(self.transitionMatrix))
             for row in range(self.nStates):

@@ -50,6 +50,12 @@ __device__ __forceinline__ void red_add_v2(float *p, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+// 256-bit read-only load (sm_100): one full 32-byte sector per lane, half the L1 wavefronts of two LDG.128
+__device__ __forceinline__ void ldg8(const float *p, float *o) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+                 : "l"(p));
+}
 
 static __global__ void bw_round_matrix_kernel(const float *__restrict__ in, float *__restrict__ out, int n) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) out[k] = bw_round_tf32(in[k]);
@@ -66,25 +72,57 @@ struct BwObs {
 };
 
 // ------------------------------------------------------------------------------- forward
+// The first versions of this kernel did the emission gather and the stash store thread-per-row (each LDG/STG
+// instruction touches 32 different lines: the L1 wavefront path made a step cost 12,000 cycles) and then with
+// one bulk copy per thread (UBLKCP takes uniform operands, so a warp serialises 32 of them: 40 % of the time).
+// Now dedicated warps move rows with fully coalesced accesses -- lane = 16-byte piece of ONE row -- and the
+// epilogue warps only compute.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// arrive on the mbarrier once all cp.async issued so far by this thread have landed (counts as one of the
+// barrier's expected arrivals)
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// round to nearest tf32 for finite positive values: add half an ulp of the 10-bit mantissa, clear 13 bits
+__device__ __forceinline__ uint32_t tf32_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+
+constexpr int FW_PITCH = 528;                  // 512-byte row + 16: thread-per-row 16-byte accesses hit 8 distinct bank groups
+constexpr int FW_EBUF = 128 * FW_PITCH;        // one emission / stash staging buffer (66 KB)
+
 struct __align__(8) FwdBars {
-    uint64_t mat_full, a_ready, d_full;
+    uint64_t mat_full, a_ready, d_full, e_full[2], w_ready[2], buf_free[2];
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(160, 2)
+// Shared memory: A^T (64 KB, K-major SW128) + two row buffers.  Buffer t&1: the gather warps copy the emission
+// rows b(o_t) of the tile into it one step ahead (cp.async, one coalesced 512-byte row per instruction), the
+// epilogue overwrites them IN PLACE with W_t (and parks c_t in the row's pad word), the storer warp streams the
+// rows to the tile-major stash and the scale array with coalesced stores and hands the buffer back.
+// Warps: 0-3 epilogue (thread = sequence = TMEM lane), 4 MMA issuer + TMEM allocator, 5-6 gather, 7 storer.
+__global__ void __launch_bounds__(256, 1)
 bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__restrict__ pi,
                      const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T, float *__restrict__ stash,
                      float *__restrict__ scale, double *__restrict__ loglik) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    FwdBars *bars = (FwdBars *)(tiles + BW_TILE);
-    const int warp = threadIdx.x >> 5;
+    // round up to 1024 B by pointer arithmetic on the shared array (an integer round trip would turn every
+    // later access into a generic LD/ST that the compiler cannot reorder against global stores)
+    unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *ebuf = tiles + BW_TILE;
+    FwdBars *bars = (FwdBars *)(ebuf + 2 * FW_EBUF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntiles = (B + 127) / 128;
 
     if (threadIdx.x == 0) {
         mbar_init(&bars->mat_full, 1);
         mbar_init(&bars->a_ready, 128);
         mbar_init(&bars->d_full, 1);
+        for (int k = 0; k < 2; k++) {
+            mbar_init(&bars->e_full[k], 64);
+            mbar_init(&bars->w_ready[k], 128);
+            mbar_init(&bars->buf_free[k], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 4) tmem_alloc(&bars->tmem_base, 256);
@@ -114,34 +152,84 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__r
                     tc_commit(&bars->d_full);
                 }
         }
+    } else if (warp == 5 || warp == 6) {
+        // ------------------------------------------------ gather: emission rows of step t -> buffer t&1
+        const int rbase = (warp - 5) * 64;
+        uint32_t nuse[2] = {0, 0};
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int64_t b0 = tile * 128 + rbase + lane, b1 = b0 + 32;
+            b0 = b0 < B ? b0 : B - 1;
+            b1 = b1 < B ? b1 : B - 1;
+            for (int64_t t = 0; t < T; t++) {
+                const int buf = (int)(t & 1);
+                const int s0 = ob.sym(b0, t), s1 = ob.sym(b1, t);
+                mbar_wait(&bars->buf_free[buf], (nuse[buf] & 1) ^ 1);
+                nuse[buf]++;
+                unsigned char *dst = ebuf + buf * FW_EBUF + rbase * FW_PITCH + lane * 16;
+#pragma unroll 8
+                for (int k = 0; k < 64; k++) {
+                    const int sy = __shfl_sync(0xffffffffu, k < 32 ? s0 : s1, k & 31);
+                    cp_async16(dst + k * FW_PITCH, Bsm + (int64_t)sy * BW_N + lane * 4);
+                }
+                cp_async_arrive(&bars->e_full[buf]);
+            }
+        }
+    } else if (warp == 7) {
+        // ------------------------------------------------ storer: W_t rows + c_t -> HBM, coalesced
+        uint32_t nuse[2] = {0, 0};
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t left = B - tile * 128;
+            const int nlive = left < 128 ? (int)left : 128;
+            for (int64_t t = 0; t < T; t++) {
+                const int buf = (int)(t & 1);
+                mbar_wait(&bars->w_ready[buf], nuse[buf] & 1);
+                nuse[buf]++;
+                const unsigned char *src = ebuf + buf * FW_EBUF + lane * 16;
+                float4 *dst = reinterpret_cast<float4 *>(stash + ((tile * T + t) * 128) * BW_N) + lane;
+#pragma unroll 8
+                for (int r = 0; r < 128; r++) {
+                    float4 v = *reinterpret_cast<const float4 *>(src + r * FW_PITCH);
+                    if (r >= nlive) v = make_float4(0.f, 0.f, 0.f, 0.f);   // rows past the batch: MMA2 must see zeros
+                    dst[r * 32] = v;
+                }
+                float *sc = scale + (tile * T + t) * 128;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    sc[k * 32 + lane] = *reinterpret_cast<const float *>(ebuf + buf * FW_EBUF + (k * 32 + lane) * FW_PITCH + 512);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->buf_free[buf]);
+            }
+        }
     } else {
         const int row = threadIdx.x;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        uint32_t nd = 0;
+        uint32_t nd = 0, ne[2] = {0, 0};
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t b = tile * 128 + row;
             const bool live = b < B;
-            const int64_t bc = live ? b : B - 1;
             float r = 1.f;           // 1 / c_{t-1}
             float prod = 1.f;        // mantissa of prod_t c_t
             int esum = 0;            // its exponent
             for (int64_t t = 0; t < T; t++) {
-                const float *brow = Bsm + (int64_t)ob.sym(bc, t) * BW_N;
-                float *srow = stash + (b * T + t) * BW_N;
+                const int cur = (int)(t & 1);
+                unsigned char *myrow = ebuf + cur * FW_EBUF + row * FW_PITCH;
                 if (t > 0) {
                     mbar_wait(&bars->d_full, nd & 1);
                     nd++;
                     tc_fence_after();
                 }
+                mbar_wait(&bars->e_full[cur], ne[cur] & 1);
+                ne[cur]++;
                 float rowsum = 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BW_N; c0 += 32) {
                     uint32_t acc[32];
                     float e[32];
                     if (t > 0) tmem_ld_32x32(tmem + lane_base + c0, acc);
+                    float4 *erow = reinterpret_cast<float4 *>(myrow + c0 * 4);
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
-                        float4 f = ldg4(brow + c0 + 4 * q);
+                        float4 f = erow[q];
                         e[4 * q] = f.x; e[4 * q + 1] = f.y; e[4 * q + 2] = f.z; e[4 * q + 3] = f.w;
                     }
                     if (t > 0) {
@@ -160,21 +248,19 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__r
                         float v = __uint_as_float(acc[q]) * r * e[q];
                         rowsum += v;
                         e[q] = v;
-                        w[q] = __float_as_uint(bw_round_tf32(v));
+                        w[q] = tf32_bits(v);
                     }
                     if (t + 1 < T) tmem_st_32x32(tmem + lane_base + 128 + c0, w);
-                    if (live) {
 #pragma unroll
-                        for (int q = 0; q < 8; q++)
-                            reinterpret_cast<float4 *>(srow + c0)[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
-                    }
+                    for (int q = 0; q < 8; q++) erow[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
                 }
+                *reinterpret_cast<float *>(myrow + 512) = rowsum;
                 if (t + 1 < T) {
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(&bars->a_ready);
                 }
-                if (live) scale[b * T + t] = rowsum;
+                mbar_arrive(&bars->w_ready[cur]);
                 r = 1.0f / rowsum;
                 int ex;
                 prod = frexpf(prod * rowsum, &ex);
@@ -200,12 +286,15 @@ struct BwdOut {
     double *flags;     // counts tail + 2
 };
 
-__global__ void __launch_bounds__(320, 1)
+// Warp roles (384 threads): warps 0-3 epilogue (setmaxnreg.inc 232), warps 4-7 count reductions (168),
+// warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator, warps 10-11 idle (96): three warps share one
+// SM sub-partition (16K registers), so the register file is re-split by role.
+__global__ void __launch_bounds__(384, 1)
 bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapStash,
                       const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T, const float *__restrict__ scale,
                       BwdOut out) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *sA = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // A, K-major SW128
+    unsigned char *sA = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // A, K-major SW128
     unsigned char *sW = sA + BW_TILE;      // W_t tile, MN-major (TMA, SWIZZLE_128B_ATOM_32B)
     unsigned char *sV = sW + BW_TILE;      // V2_{t+1} tile, MN-major (written by the epilogue)
     BwdBars *bars = (BwdBars *)(sV + BW_TILE);
@@ -224,14 +313,17 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         mbar_init(&bars->stage_empty, 4);
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(&bars->tmem_base, 512);
+    if (warp == 9) tmem_alloc(&bars->tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    if (warp == 4) {
+    if (warp >= 10) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    } else if (warp == 8) {
         // ------------------------------------------------ TMA producer: A once, then W_t tiles of the stash
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         if (elect_one()) {
             tma_prefetch_desc(&mapA);
             tma_prefetch_desc(&mapStash);
@@ -244,11 +336,12 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                     np++;
                     mbar_arrive_expect_tx(&bars->alpha_full, BW_TILE);
                     for (int c = 0; c < 4; c++)
-                        tma_load_3d(sW + c * BW_SUB, &mapStash, &bars->alpha_full, c * 32, (int)t, (int)(tile * 128));
+                        tma_load_3d(sW + c * BW_SUB, &mapStash, &bars->alpha_full, c * 32, 0, (int)(tile * T + t));
                 }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ------------------------------------------------ MMA issuer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         if (elect_one()) {
             mbar_wait(&bars->mat_full, 0);
             const uint32_t idesc_k = make_idesc_tf32(128, 128);
@@ -282,6 +375,7 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         }
     } else if (warp < 4) {
         // ------------------------------------------------ epilogue: thread = sequence = TMEM lane
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int row = threadIdx.x;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         const int sw = row & 3;   // Swizzle<2,5,2>: 32-byte chunk index ^= row & 3
@@ -293,8 +387,9 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             for (int64_t t = T - 1; t >= 0; t--) {
                 const bool last = (t == T - 1);
                 const float *brow = Bsm + (int64_t)ob.sym(bc, t) * BW_N;
-                const float rc1 = last ? 1.f : 1.0f / scale[bc * T + t + 1];
-                const float rcm1 = t > 0 ? 1.0f / scale[bc * T + t - 1] : 0.f;
+                const float *sct = scale + (tile * T + t) * 128 + row;   // tile-major scale [tile][t][row]
+                const float rc1 = last ? 1.f : 1.0f / sct[128];
+                const float rcm1 = t > 0 ? 1.0f / sct[-128] : 0.f;
                 if (!last) {
                     mbar_wait(&bars->d1_full, nd & 1);
                     nd++;
@@ -354,7 +449,11 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                 tc_fence_after();
 #pragma unroll 1
                 for (int c0 = 0; c0 < BW_N; c0 += 32) {
-                    float g[32], beta[32];
+                    float g[32], beta[32], e[32];
+                    if (t > 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) ldg8(brow + c0 + 8 * q, e + 8 * q);   // in flight during gchunk
+                    }
                     gchunk(c0, g, beta);
                     uint32_t u[32];
 #pragma unroll
@@ -362,13 +461,7 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                     tmem_st_32x32(tmem + lane_base + COL_STG + c0, u);
                     if (t > 0) {
 #pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            float4 f = ldg4(brow + c0 + 4 * q);
-                            u[4 * q] = __float_as_uint(bw_round_tf32(f.x * beta[4 * q]));
-                            u[4 * q + 1] = __float_as_uint(bw_round_tf32(f.y * beta[4 * q + 1]));
-                            u[4 * q + 2] = __float_as_uint(bw_round_tf32(f.z * beta[4 * q + 2]));
-                            u[4 * q + 3] = __float_as_uint(bw_round_tf32(f.w * beta[4 * q + 3]));
-                        }
+                        for (int q = 0; q < 32; q++) u[q] = __float_as_uint(bw_round_tf32(e[q] * beta[q]));
                         tmem_st_32x32(tmem + lane_base + COL_V + c0, u);
                     }
                 }
@@ -424,7 +517,7 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                 }
             }
         }
-    } else {
+    } else if (warp < 8) {
         // ------------------------------------------------ RED warps: staging rows -> fp32 count table in L2
         const int quad = warp & 3;    // TMEM lane quadrant this warp may access
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -446,18 +539,19 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                 mbar_wait(&bars->stage_full, ns & 1);
                 ns++;
                 tc_fence_after();
-                uint32_t r[8][16];
 #pragma unroll
-                for (int half = 0; half < 2; half++)
+                for (int half = 0; half < 2; half++) {
+                    uint32_t r[4][16];
 #pragma unroll
                     for (int c = 0; c < 4; c++)
-                        tmem_ld_16x256_x4(tmem + lane_base + ((uint32_t)(half * 16) << 16) + COL_STG + c * 32, r[half * 4 + c]);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->stage_empty);
-#pragma unroll
-                for (int half = 0; half < 2; half++)
+                        tmem_ld_16x256_x4(tmem + lane_base + ((uint32_t)(half * 16) << 16) + COL_STG + c * 32, r[c]);
+                    tmem_ld_wait();
+                    if (half == 1) {
+                        // the staging area has been read: hand it back before issuing the reductions
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->stage_empty);
+                    }
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
                         const int k = half * 2 + e;   // row = quad*32 + 8k + lane/4
@@ -467,8 +561,8 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                         for (int c = 0; c < 4; c++)
 #pragma unroll
                             for (int n = 0; n < 4; n++)
-                                red_add_v2(dst + c * 32 + 8 * n, __uint_as_float(r[half * 4 + c][4 * n + 2 * e]),
-                                           __uint_as_float(r[half * 4 + c][4 * n + 2 * e + 1]));
+                                red_add_v2(dst + c * 32 + 8 * n, __uint_as_float(r[c][4 * n + 2 * e]),
+                                           __uint_as_float(r[c][4 * n + 2 * e + 1]));
                         if (t == 0 || t == T - 1) {
 #pragma unroll 1
                             for (int which = 0; which < 2; which++) {
@@ -478,17 +572,18 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                                 for (int c = 0; c < 4; c++)
 #pragma unroll
                                     for (int n = 0; n < 4; n++)
-                                        red_add_v2(d2 + c * 32 + 8 * n, __uint_as_float(r[half * 4 + c][4 * n + 2 * e]),
-                                                   __uint_as_float(r[half * 4 + c][4 * n + 2 * e + 1]));
+                                        red_add_v2(d2 + c * 32 + 8 * n, __uint_as_float(r[c][4 * n + 2 * e]),
+                                                   __uint_as_float(r[c][4 * n + 2 * e + 1]));
                             }
                         }
                     }
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem, 512);
+    if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
 // Fold the fp32 table replicas into the float64 count buffer:
@@ -537,8 +632,8 @@ static BwWorkspace bw_layout(void *ws, int64_t B, int64_t T, int M) {
     BwWorkspace w;
     size_t o = 0;
     unsigned char *p = (unsigned char *)ws;
-    w.stash = (float *)(p + o);  o += up((size_t)B * T * BW_N * 4);
-    w.scale = (float *)(p + o);  o += up((size_t)B * T * 4);
+    w.stash = (float *)(p + o);  o += up((size_t)((B + 127) / 128 * 128) * T * BW_N * 4);
+    w.scale = (float *)(p + o);  o += up((size_t)((B + 127) / 128 * 128) * T * 4);
     w.tab = (float *)(p + o);    o += up((size_t)BW_REPL * (M + 2) * BW_N * 4);
     w.Ar = (float *)(p + o);     o += up((size_t)BW_N * BW_N * 4);
     w.ATr = (float *)(p + o);    o += up((size_t)BW_N * BW_N * 4);
@@ -555,9 +650,10 @@ static int make_tmap_stash(CUtensorMap *map, const float *stash, int64_t B, int6
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
         encode = (PFN_encodeTiled)fn;
     }
-    cuuint64_t dims[3] = {(cuuint64_t)BW_N, (cuuint64_t)T, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)BW_N * 4, (cuuint64_t)T * BW_N * 4};
-    cuuint32_t box[3] = {32, 1, 128};
+    // tile-major stash [ntiles * T][128 rows][128]
+    cuuint64_t dims[3] = {(cuuint64_t)BW_N, 128, (cuuint64_t)((B + 127) / 128 * T)};
+    cuuint64_t strides[2] = {(cuuint64_t)BW_N * 4, (cuuint64_t)128 * BW_N * 4};
+    cuuint32_t box[3] = {32, 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)stash, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
@@ -586,7 +682,7 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
         set_error("estep_tc: the fused tensor-core E-step covers N = %d (got %d)", BW_N, N);
         return KHMM_ERR_UNSUPPORTED;
     }
-    if (T > 0x7fffffff || B > 0x7fffff00) {
+    if ((B + 127) / 128 * T > 0x7fffffff) {
         set_error("estep_tc: B and T must fit a 32-bit tensor-map coordinate");
         return KHMM_ERR_UNSUPPORTED;
     }
@@ -597,7 +693,7 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
     KHMM_REQUIRE(((uintptr_t)workspace & 1023) == 0, "estep_tc: workspace must be 1024-byte aligned");
     BwWorkspace w = bw_layout(workspace, B, T, M);
     KHMM_REQUIRE(workspace_bytes >= w.bytes, "estep_tc: workspace too small");
-    if (alpha_out) w.stash = alpha_out;   // caller-visible stash (tests): W_t = c_t alpha_t
+    if (alpha_out) w.stash = alpha_out;   // caller-visible stash (tests): [ceil(B/128)][T][128][128], W_t = c_t alpha_t
     if (scale_out) w.scale = scale_out;
     KHMM_REQUIRE(((uintptr_t)w.stash & 15) == 0, "estep_tc: stash must be 16-byte aligned");
 
@@ -614,10 +710,10 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
     const int sms = sm_count();
     BwObs ob{obs, obs_dtype, M, T};
     {
-        size_t smem = BW_TILE + sizeof(FwdBars) + 1024;
+        size_t smem = BW_TILE + 2 * (size_t)FW_EBUF + sizeof(FwdBars) + 1024;
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int grid = (int)(ntiles < 2 * sms ? ntiles : 2 * sms);
-        bw_forward_tc_kernel<<<grid, 160, smem, st>>>(mapAT, pi, Bsm, ob, B, T, w.stash, w.scale, w.loglik);
+        int grid = (int)(ntiles < sms ? ntiles : sms);
+        bw_forward_tc_kernel<<<grid, 256, smem, st>>>(mapAT, pi, Bsm, ob, B, T, w.stash, w.scale, w.loglik);
         KHMM_LAUNCH_CHECK("bw_forward_tc_kernel");
     }
     {
@@ -627,7 +723,7 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
         double *c_xi = counts + BW_N;
         double *c_tail = counts + BW_N + (size_t)BW_N * BW_N + BW_N + (size_t)M * BW_N + BW_N;
         BwdOut out{w.tab, c_xi, c_tail + 2};
-        bw_backward_tc_kernel<<<grid, 320, smem, st>>>(mapA, mapStash, Bsm, ob, B, T, w.scale, out);
+        bw_backward_tc_kernel<<<grid, 384, smem, st>>>(mapA, mapStash, Bsm, ob, B, T, w.scale, out);
         KHMM_LAUNCH_CHECK("bw_backward_tc_kernel");
     }
     bw_fold_kernel<<<64, 128, 0, st>>>(w.tab, M, counts, w.loglik, B);

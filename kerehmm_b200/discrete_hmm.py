@@ -26,8 +26,8 @@ class DiscreteHMM(AbstractHMM):
     def sanity_check(self):
         """Takes no arguments, like the reference's override (discrete_hmm.py:24-27)."""
         super(DiscreteHMM, self).sanity_check()
-        for dist in self.emissionDistributions:
-            assert np.isclose(dist.probabilities.sum(), 1.)
+        sums = np.array([dist.probabilities.sum() for dist in self.emissionDistributions])
+        assert np.isclose(sums, 1.).all()
 
     # -------------------------------------------------------------------------- packing
     def emission_matrix(self):
@@ -48,9 +48,7 @@ class DiscreteHMM(AbstractHMM):
         self.sanity_check()
         dists = []
         for i in range(self.nStates):
-            d = DiscreteDistribution(n=self.alphabetSize)
-            d.probabilities = Bm[i].copy()
-            dists.append(d)
+            dists.append(DiscreteDistribution.from_probabilities(Bm[i]))
         self.emissionDistributions = np.array(dists)
         self.sanity_check()
         self.transitionMatrix = A

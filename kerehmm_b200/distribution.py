@@ -31,6 +31,14 @@ class DiscreteDistribution(Distribution):
         if randomize:
             self.probabilities = random_simplex(n)
 
+    @classmethod
+    def from_probabilities(cls, probabilities):
+        """A distribution holding a copy of `probabilities` (skips the uniform-table construction)."""
+        d = cls.__new__(cls)
+        d.probabilities = np.array(probabilities, dtype=np.float64)
+        d.n = len(d.probabilities)
+        return d
+
     def get_probability(self, observation, *args, **kwargs):
         return self.probabilities[observation]
 

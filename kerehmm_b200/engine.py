@@ -398,7 +398,7 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
     if chunk is None:
         free, _ = t.cuda.mem_get_info()
         per_seq = ob.T * N * 4 + ob.T * 4 + 16
-        chunk = int(max(128, min(ob.B, (free * 0.8) // per_seq)))
+        chunk = int(max(128, min(ob.B, (free * 0.8) // per_seq - 128)))
         if chunk < ob.B:
             chunk -= chunk % 128
     nb0 = min(chunk, ob.B)
@@ -407,14 +407,16 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
     wsp = ws.data_ptr() + (-ws.data_ptr()) % 1024
     W = sc = None
     if stash_out:
-        W = t.zeros((nb0, ob.T, N), dtype=t.float32, device=dev)
-        sc = t.zeros((nb0, ob.T), dtype=t.float32, device=dev)
+        W = t.zeros(((nb0 + 127) // 128, ob.T, 128, N), dtype=t.float32, device=dev)   # tile-major stash
+        sc = t.zeros(((nb0 + 127) // 128, ob.T, 128), dtype=t.float32, device=dev)           # tile-major c
     for b0 in range(0, ob.B, chunk):
         nb = min(chunk, ob.B - b0)
         obs_c = ob.tensor[b0:b0 + nb]
         _lib.call("khmm_estep_tc_discrete_f32", nb, ob.T, N, M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.Bsm),
                   ptr(obs_c), ob.code, wsp, nbytes, ptr(counts.buf), ptr(W), ptr(sc), stream_ptr())
     if stash_out:
+        W = W.permute(0, 2, 1, 3).reshape(-1, ob.T, N)[:nb0]     # -> [b][t][:]
+        sc = sc.permute(0, 2, 1).reshape(-1, ob.T)[:nb0]
         return counts, W, sc
     return counts
 
