@@ -130,7 +130,9 @@ def cpu_leg(kind, model, obs, cores):
 
 # ------------------------------------------------------------------------ clock sampling
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi polled every 100 ms.  Started BEFORE the warm-up (its start-up takes driver locks and a few
+    hundred ms); only the samples whose timestamp falls inside the timed region are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -144,7 +146,8 @@ class ClockSampler:
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -152,19 +155,31 @@ class ClockSampler:
         self.p.wait()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons, power = [], [], set(), []
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), float(c[3]), c[5:9]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+        os.unlink(self.f.name)
+        sel = rows
+        if t_begin is not None:
+            for slack in (0.0, 0.12, 0.3):      # short timed regions: take the polls nearest to them
+                sel = [r for r in rows if t_begin - slack <= r[0] <= t_end + slack]
+                if sel:
+                    break
+            else:
+                sel = rows
+        sm, mx, reasons, power = [], [], set(), []
+        for _, a, b, c3, flags in sel:
+            sm.append(a); mx.append(b); power.append(c3)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.f.name)
         busy = sorted(sm)[len(sm) // 2:] if sm else []          # the upper half = samples under load
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
@@ -249,12 +264,18 @@ def run_ours(args):
         host_sets = [torch.from_numpy(obs_h.view(np.int16)).pin_memory()]
         ob = engine.prepare_obs(host_sets[0].to(dev), symbols=True, u16_bits=True)
 
+        import ctypes
+        kernel_ms = []          # (forward, backward) device durations of every step, CUDA events inside libkhmm
+
         def step(i):
             from kerehmm_b200 import dist as kdist
             p_ = model._params()
             counts = engine.estep_discrete(p_, ob, torch.float32)
             kdist.all_reduce_counts(counts.buf)
             model._assign(*engine.mstep_discrete(p_, counts))
+            f, b = ctypes.c_float(), ctypes.c_float()
+            _lib.call("khmm_estep_tc_last_kernel_ms", ctypes.byref(f), ctypes.byref(b))
+            kernel_ms.append((f.value, b.value))
 
         def e2e_step(i):
             o = engine.prepare_obs(host_sets[0], symbols=True, u16_bits=True)
@@ -265,12 +286,14 @@ def run_ours(args):
             model._assign(*engine.mstep_discrete(p_, counts))
             return counts.buf[-3:].cpu()
 
-        launches_per_step = 4
-        algo_bytes = B * T * 2
+        launches_per_step = 6      # 2 x bw_round_matrix, bw_forward_tc, bw_backward_tc, bw_fold, mstep_discrete
+        # dominant kernel = bw_backward_tc_kernel: reads the forward stash once (512 B per (sequence, step)), two
+        # scale factors and the 2-byte symbol (twice: epilogue + reduction warps)
+        algo_bytes = B * T * (N * 4 + 8 + 4)
         h2d, d2h = B * T * 2, 24
-        dominant = "xi_accumulate_kernel / backward_generic_kernel<estep>"
-        l2_note = "alpha/V stashes of tens of GB per step (>> L2)"
-        dtype = "f32"
+        dominant = "bw_backward_tc_kernel (tcgen05 kind::tf32, xi in TMEM, L2 count reductions)"
+        l2_note = "forward stash of B*T*512 B per step (34 GB at B=131072, >> L2)"
+        dtype = "tf32 multiply / f32 accumulate"
     elif kind == "c5":
         Bg = B // world if args.strong else B
         model, obs_h = make_gaussian(N, Bg, T, seed + 100 * rank)
@@ -307,18 +330,20 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing
+    sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
     ev0.record(stream)
     for i in range(args.steps):
         step(i)
     ev1.record(stream)
     barrier()
+    wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(wall0, wall1) if sampler else None
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -349,6 +374,19 @@ def run_ours(args):
             roof = {"bound": "tensor", "achieved": tflops, "peak": 1621.0 / 2, "unit": "TFLOP/s",
                     "frac": tflops / (1621.0 / 2), "traffic": None, "kernel": dominant,
                     "peak_source": "half of the measured bf16 burst peak (MEASURED_PEAKS.json): tf32 runs at half the bf16 rate"}
+        elif kind == "c4":
+            fwd_ms = float(np.mean([k[0] for k in kernel_ms[-args.steps:]]))
+            bwd_ms = float(np.mean([k[1] for k in kernel_ms[-args.steps:]]))
+            achieved = algo_bytes / (bwd_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": ncu_traffic, "kernel": dominant, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": bwd_ms,
+                    "forward_kernel": {"name": "bw_forward_tc_kernel", "kernel_ms": fwd_ms,
+                                       "achieved_gbs": B * T * (N * 4 + 4 + 2) / (fwd_ms * 1e-3) / 1e9},
+                    "tensor": {"achieved_tflops": 4.0 * B * T * N * N / (bwd_ms * 1e-3) / 1e12, "peak_tflops": 1621.0 / 2,
+                               "note": "MMA1 + MMA2 of the backward kernel; tf32 peak = half the measured bf16 burst peak"},
+                    "note": "the kernel is bound by L2 reduction (red.global) throughput and LSU occupancy, "
+                            "not by HBM or the tensor pipe (DESIGN.md 3.5)"}
         else:
             achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

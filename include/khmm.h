@@ -258,6 +258,15 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
                                size_t workspace_bytes, double *counts, float *alpha_out, float *scale_out,
                                khmm_stream_t stream);
 
+/* Device durations (CUDA events on the launching stream) of the forward and the backward kernel of the
+ * most recent khmm_estep_tc_discrete_f32 call of this process; waits for that call to finish.  For
+ * measurement (bench.py reports the dominant kernel's roofline from it). */
+int khmm_estep_tc_last_kernel_ms(float *forward_ms_host, float *backward_ms_host);
+
+/* Development hook: arm (device buffer of 8*32 int64) or disarm (NULL) a clock64 timeline of the warp roles
+ * of the backward kernel (block 0, steps 8..15; tools/dbg_bw_trace.py prints it). */
+int khmm_debug_bw_trace(int64_t *dev_buf);
+
 /* M-step on the device -- discrete_hmm.py:132-161 + util.smooth_probabilities (util.py:39-63),
  * float64, operation for operation.  Reads counts (after the all-reduce), A (old, [N][N]);
  * writes pi_new[N], A_new[N][N], B_new state-major [N][M].  status[0] (device int32) gets a

@@ -46,6 +46,9 @@ __device__ __forceinline__ float bw_round_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void red_add_v2(float *p, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
@@ -276,11 +279,29 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__r
 
 // ------------------------------------------------------------------------------ backward
 struct __align__(8) BwdBars {
-    uint64_t mat_full, alpha_full, alpha_empty, v_ready, d1_full, mma2_done, stage_full, stage_empty;
+    uint64_t mat_full, alpha_full, alpha_empty, v_ready, d1_full, mma2_done, stage_full, stage_empty, e_full[2], e_free[2];
     uint32_t tmem_base;
 };
+#ifndef KHMM_RED_DEFER
+#define KHMM_RED_DEFER 1
+#endif
+#ifndef KHMM_RED_PACE_NS
+#define KHMM_RED_PACE_NS 0
+#endif
+constexpr bool RED_DEFER = KHMM_RED_DEFER;
+constexpr int RED_PACE_NS = KHMM_RED_PACE_NS;
+constexpr int BW_ECHUNK = 128 * 128;   // emission rows of one 32-column chunk: [128 rows][128 B], 16-byte pieces XOR (row & 7)
+
+// Optional timeline (development): clock64 stamps of block 0, first tile, backward steps 8..15.
+#define BW_TRACE(ev)                                                                                   \
+    do {                                                                                               \
+        if (out.trace && blockIdx.x == 0 && tile == blockIdx.x && (T - 1 - t) >= 8 && (T - 1 - t) < 16 && \
+            (threadIdx.x & 31) == 0)                                                                   \
+            out.trace[((T - 1 - t) - 8) * 32 + (ev)] = clock64();                                       \
+    } while (0)
 
 struct BwdOut {
+    long long *trace;  // nullptr unless khmm_debug_bw_trace() armed it
     float *tab;        // [BW_REPL][M+2][128] fp32 count table (row M: pi, row M+1: gamma_ref at t = T-1)
     double *xi;        // counts.xi [128][128]
     double *flags;     // counts tail + 2
@@ -297,7 +318,8 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     unsigned char *sA = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // A, K-major SW128
     unsigned char *sW = sA + BW_TILE;      // W_t tile, MN-major (TMA, SWIZZLE_128B_ATOM_32B)
     unsigned char *sV = sW + BW_TILE;      // V2_{t+1} tile, MN-major (written by the epilogue)
-    BwdBars *bars = (BwdBars *)(sV + BW_TILE);
+    unsigned char *sE = sV + BW_TILE;      // two emission chunk buffers filled by the gather warps
+    BwdBars *bars = (BwdBars *)(sE + 2 * BW_ECHUNK);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntiles = (B + 127) / 128;
     const int M = ob.M;
@@ -311,6 +333,10 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         mbar_init(&bars->mma2_done, 1);
         mbar_init(&bars->stage_full, 128);
         mbar_init(&bars->stage_empty, 4);
+        for (int k = 0; k < 2; k++) {
+            mbar_init(&bars->e_full[k], 64);
+            mbar_init(&bars->e_free[k], 4);
+        }
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc(&bars->tmem_base, 512);
@@ -320,7 +346,36 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const uint32_t tmem = bars->tmem_base;
 
     if (warp >= 10) {
+        // ------------------------------------------------ gather warps: emission rows b(o_t), one 32-column chunk
+        // at a time, into shared memory with coalesced cp.async (lane = 16-byte piece, 4 rows per instruction).
+        // A thread-per-row gather touches 32 lines per load instruction and, together with the count
+        // reductions, saturated the LSU (13,000 cycles per step in the first version).
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        const int rbase = (warp - 10) * 64;
+        const int rsub = lane >> 3, piece = lane & 7;
+        uint32_t nchunk = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int64_t b0 = tile * 128 + rbase + lane, b1 = b0 + 32;
+            b0 = b0 < B ? b0 : B - 1;
+            b1 = b1 < B ? b1 : B - 1;
+            for (int64_t t = T - 1; t >= 1; t--) {   // step t = 0 forms no V_t: no emission rows needed
+                const int s0 = ob.sym(b0, t), s1 = ob.sym(b1, t);
+                for (int c = 0; c < 4; c++, nchunk++) {
+                    const int buf = nchunk & 1;
+                    mbar_wait(&bars->e_free[buf], ((nchunk >> 1) & 1) ^ 1);
+                    unsigned char *dstb = sE + buf * BW_ECHUNK;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        const int rr = 4 * k + rsub;                       // row within this warp's 64
+                        const int sy = __shfl_sync(0xffffffffu, k < 8 ? s0 : s1, rr & 31);
+                        const int row = rbase + rr;
+                        cp_async16(dstb + row * 128 + ((piece ^ (row & 7)) << 4),
+                                   Bsm + (int64_t)sy * BW_N + c * 32 + piece * 4);
+                    }
+                    cp_async_arrive(&bars->e_full[buf]);
+                }
+            }
+        }
     } else if (warp == 8) {
         // ------------------------------------------------ TMA producer: A once, then W_t tiles of the stash
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
@@ -334,6 +389,7 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                 for (int64_t t = T - 1; t >= 0; t--) {
                     mbar_wait(&bars->alpha_empty, (np & 1) ^ 1);
                     np++;
+                    BW_TRACE(0);
                     mbar_arrive_expect_tx(&bars->alpha_full, BW_TILE);
                     for (int c = 0; c < 4; c++)
                         tma_load_3d(sW + c * BW_SUB, &mapStash, &bars->alpha_full, c * 32, 0, (int)(tile * T + t));
@@ -354,6 +410,7 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                 for (int64_t t = T - 2; t >= 0; t--) {
                     mbar_wait(&bars->v_ready, nv & 1);
                     nv++;
+                    BW_TRACE(4);
                     tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < 16; k++) {
@@ -361,8 +418,10 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                         mma_tf32_ts(tmem + COL_D1, tmem + COL_V + k * 8, desc_advance(db, (k & 3) * 32), idesc_k, k != 0);
                     }
                     tc_commit(&bars->d1_full);
+                    BW_TRACE(5);
                     mbar_wait(&bars->alpha_full, nfull & 1);
                     nfull++;
+                    BW_TRACE(6);
                     tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < 16; k++)
@@ -370,6 +429,7 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                                     (t != T - 2) || k != 0);
                     tc_commit(&bars->mma2_done);
                     tc_commit(&bars->alpha_empty);
+                    BW_TRACE(7);
                 }
             }
         }
@@ -379,14 +439,14 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         const int row = threadIdx.x;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         const int sw = row & 3;   // Swizzle<2,5,2>: 32-byte chunk index ^= row & 3
-        uint32_t nd = 0, nm = 0, nfull = 0, nstage = 0;
+        const int hb = (row >> 2) & 1;
+        uint32_t nd = 0, nm = 0, nfull = 0, nstage = 0, nchunk = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t b = tile * 128 + row;
             const bool live = b < B;
             const int64_t bc = live ? b : B - 1;
             for (int64_t t = T - 1; t >= 0; t--) {
                 const bool last = (t == T - 1);
-                const float *brow = Bsm + (int64_t)ob.sym(bc, t) * BW_N;
                 const float *sct = scale + (tile * T + t) * 128 + row;   // tile-major scale [tile][t][row]
                 const float rc1 = last ? 1.f : 1.0f / sct[128];
                 const float rcm1 = t > 0 ? 1.0f / sct[-128] : 0.f;
@@ -395,21 +455,27 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                     nd++;
                     tc_fence_after();
                 }
+                if (warp == 0) BW_TRACE(8);
                 mbar_wait(&bars->alpha_full, nfull & 1);
                 nfull++;
+                if (warp == 0) BW_TRACE(9);
                 // gamma_ref chunk: W_t . beta_t  (beta = 1 at t = T-1)
                 auto gchunk = [&](int c0, float (&g)[32], float (&beta)[32]) {
                     uint32_t acc[32];
                     if (!last) tmem_ld_32x32(tmem + lane_base + COL_D1 + c0, acc);
                     const unsigned char *wrow = sW + (c0 >> 5) * BW_SUB + row * 128;
+                    // rows r and r+4 share a 32-byte slot: lanes with (row & 4) read the upper half first so that
+                    // 8 consecutive lanes hit 8 distinct 16-byte bank groups, then the halves are swapped back
 #pragma unroll
-                    for (int c32 = 0; c32 < 4; c32++)
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            float4 f = *reinterpret_cast<const float4 *>(wrow + (((c32 ^ sw) << 5) | (h << 4)));
-                            int q = c32 * 8 + h * 4;
-                            g[q] = f.x; g[q + 1] = f.y; g[q + 2] = f.z; g[q + 3] = f.w;
-                        }
+                    for (int c32 = 0; c32 < 4; c32++) {
+                        const unsigned char *slot = wrow + ((c32 ^ sw) << 5);
+                        float4 x = *reinterpret_cast<const float4 *>(slot + (hb << 4));
+                        float4 y = *reinterpret_cast<const float4 *>(slot + ((hb ^ 1) << 4));
+                        float4 lo = hb ? y : x, hi = hb ? x : y;
+                        int q = c32 * 8;
+                        g[q] = lo.x; g[q + 1] = lo.y; g[q + 2] = lo.z; g[q + 3] = lo.w;
+                        g[q + 4] = hi.x; g[q + 5] = hi.y; g[q + 6] = hi.z; g[q + 7] = hi.w;
+                    }
                     if (!last) tmem_ld_wait();
 #pragma unroll
                     for (int q = 0; q < 32; q++) {
@@ -446,26 +512,42 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                 }
                 mbar_wait(&bars->stage_empty, (nstage & 1) ^ 1);
                 nstage++;
+                if (warp == 0) BW_TRACE(10);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c0 = 0; c0 < BW_N; c0 += 32) {
-                    float g[32], beta[32], e[32];
-                    if (t > 0) {
-#pragma unroll
-                        for (int q = 0; q < 4; q++) ldg8(brow + c0 + 8 * q, e + 8 * q);   // in flight during gchunk
-                    }
+                    float g[32], beta[32];
                     gchunk(c0, g, beta);
                     uint32_t u[32];
+                    // staging column 16*blk + 8*n2 + 2*j + e holds logical column 16*blk + 4*j + 2*n2 + e, so that the
+                    // four registers a lane gets from two adjacent 16x256b repetitions are 4 CONSECUTIVE columns
+                    // (one red.v4 per lane, a quad = 64 contiguous bytes of a row)
 #pragma unroll
-                    for (int q = 0; q < 32; q++) u[q] = __float_as_uint(fmaxf(g[q] - sub, floorv) * inv);
+                    for (int q = 0; q < 32; q++) {
+                        const int lq = (q & 16) | ((q & 6) << 1) | ((q & 8) >> 2) | (q & 1);
+                        u[q] = __float_as_uint(fmaxf(g[lq] - sub, floorv) * inv);
+                    }
                     tmem_st_32x32(tmem + lane_base + COL_STG + c0, u);
                     if (t > 0) {
+                        const int buf = nchunk & 1;
+                        mbar_wait(&bars->e_full[buf], (nchunk >> 1) & 1);
+                        nchunk++;
+                        const unsigned char *erow = sE + buf * BW_ECHUNK + row * 128;
 #pragma unroll
-                        for (int q = 0; q < 32; q++) u[q] = __float_as_uint(bw_round_tf32(e[q] * beta[q]));
+                        for (int q = 0; q < 8; q++) {
+                            float4 f = *reinterpret_cast<const float4 *>(erow + ((q ^ (row & 7)) << 4));
+                            u[4 * q] = tf32_bits(f.x * beta[4 * q]);
+                            u[4 * q + 1] = tf32_bits(f.y * beta[4 * q + 1]);
+                            u[4 * q + 2] = tf32_bits(f.z * beta[4 * q + 2]);
+                            u[4 * q + 3] = tf32_bits(f.w * beta[4 * q + 3]);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->e_free[buf]);
                         tmem_st_32x32(tmem + lane_base + COL_V + c0, u);
                     }
                 }
                 // W_t has been read: hand the buffer back to the TMA producer (MMA2 adds its own arrival)
+                if (warp == 0) BW_TRACE(11);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->alpha_empty);
                 // t = T-1 has no MMA2: its arrival is made here, inside the same barrier phase (an early
@@ -474,12 +556,14 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars->stage_full);
+                if (warp == 0) BW_TRACE(12);
                 if (!last) {
                     // MMA2(t) reads V2_{t+1} from shared memory: wait before overwriting it
                     mbar_wait(&bars->mma2_done, nm & 1);
                     nm++;
                     tc_fence_after();
                 }
+                if (warp == 0) BW_TRACE(13);
                 if (t > 0) {
                     // V2_t = V_t / c_{t-1} -> shared memory, MN-major Swizzle<2,5,2> (B operand of MMA2(t-1))
 #pragma unroll 1
@@ -489,20 +573,21 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                         tmem_ld_wait();
                         unsigned char *vrow = sV + (c0 >> 5) * BW_SUB + row * 128;
 #pragma unroll
-                        for (int c32 = 0; c32 < 4; c32++)
+                        for (int q = 0; q < 32; q++) v[q] = tf32_bits(__uint_as_float(v[q]) * rcm1);
 #pragma unroll
-                            for (int h = 0; h < 2; h++) {
-                                int q = c32 * 8 + h * 4;
-                                float4 f = make_float4(bw_round_tf32(__uint_as_float(v[q]) * rcm1),
-                                                       bw_round_tf32(__uint_as_float(v[q + 1]) * rcm1),
-                                                       bw_round_tf32(__uint_as_float(v[q + 2]) * rcm1),
-                                                       bw_round_tf32(__uint_as_float(v[q + 3]) * rcm1));
-                                *reinterpret_cast<float4 *>(vrow + (((c32 ^ sw) << 5) | (h << 4))) = f;
-                            }
+                        for (int c32 = 0; c32 < 4; c32++) {
+                            const int q = c32 * 8;
+                            uint4 lo = make_uint4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                            uint4 hi = make_uint4(v[q + 4], v[q + 5], v[q + 6], v[q + 7]);
+                            unsigned char *slot = vrow + ((c32 ^ sw) << 5);
+                            *reinterpret_cast<uint4 *>(slot + (hb << 4)) = hb ? hi : lo;          // same conflict-free order
+                            *reinterpret_cast<uint4 *>(slot + ((hb ^ 1) << 4)) = hb ? lo : hi;
+                        }
                     }
                     fence_proxy_async();
                     tc_fence_before();
                     mbar_arrive(&bars->v_ready);
+                    if (warp == 0) BW_TRACE(14);
                 } else if (T > 1) {
                     // tile done: Xi[i][j] (lane = i) -> float64 counts
 #pragma unroll 1
@@ -522,8 +607,8 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         const int quad = warp & 3;    // TMEM lane quadrant this warp may access
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         float *tab = out.tab + (size_t)(blockIdx.x % BW_REPL) * (size_t)(M + 2) * BW_N;
-        const int colq = 2 * (lane & 3);
-        uint32_t ns = 0;
+        const int colq = 4 * (lane & 3);   // a quad covers 16 consecutive columns with one red.v4 per lane
+        uint32_t ns = 0, nvr = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             int64_t bq[4];
             bool lv[4];
@@ -538,6 +623,7 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                 for (int k = 0; k < 4; k++) sym[k] = lv[k] ? ob.sym(bq[k], t) : 0;
                 mbar_wait(&bars->stage_full, ns & 1);
                 ns++;
+                if (warp == 4) BW_TRACE(16);
                 tc_fence_after();
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
@@ -551,6 +637,13 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars->stage_empty);
+                        if (warp == 4) BW_TRACE(17);
+                    }
+                    if (RED_DEFER && half == 0 && t > 0) {
+                        // LSU scheduling: the reductions (16 cycles of LSU time each) would otherwise sit in front of
+                        // the epilogue's V2 stores; let them run under the next step's MMA instead
+                        mbar_wait(&bars->v_ready, nvr & 1);
+                        nvr++;
                     }
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
@@ -558,11 +651,16 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                         if (!lv[k]) continue;
                         float *dst = tab + (size_t)sym[k] * BW_N + colq;
 #pragma unroll
-                        for (int c = 0; c < 4; c++)
+                        for (int c = 0; c < 4; c++) {
 #pragma unroll
-                            for (int n = 0; n < 4; n++)
-                                red_add_v2(dst + c * 32 + 8 * n, __uint_as_float(r[c][4 * n + 2 * e]),
-                                           __uint_as_float(r[c][4 * n + 2 * e + 1]));
+                            for (int n = 0; n < 4; n += 2)
+                                red_add_v4(dst + c * 32 + 8 * n, __uint_as_float(r[c][4 * n + 2 * e]),
+                                           __uint_as_float(r[c][4 * n + 2 * e + 1]), __uint_as_float(r[c][4 * n + 4 + 2 * e]),
+                                           __uint_as_float(r[c][4 * n + 4 + 2 * e + 1]));
+                            // pace the reductions: a burst fills the LSU queue and blocks the epilogue's shared-memory
+                            // traffic and the MMA operand fetches behind ~16 cycles of L2 reduction work per instruction
+                            if (RED_PACE_NS) asm volatile("nanosleep.u32 %0;" ::"n"(RED_PACE_NS));
+                        }
                         if (t == 0 || t == T - 1) {
 #pragma unroll 1
                             for (int which = 0; which < 2; which++) {
@@ -571,9 +669,11 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll
                                 for (int c = 0; c < 4; c++)
 #pragma unroll
-                                    for (int n = 0; n < 4; n++)
-                                        red_add_v2(d2 + c * 32 + 8 * n, __uint_as_float(r[c][4 * n + 2 * e]),
-                                                   __uint_as_float(r[c][4 * n + 2 * e + 1]));
+                                    for (int n = 0; n < 4; n += 2)
+                                        red_add_v4(d2 + c * 32 + 8 * n, __uint_as_float(r[c][4 * n + 2 * e]),
+                                                   __uint_as_float(r[c][4 * n + 2 * e + 1]),
+                                                   __uint_as_float(r[c][4 * n + 4 + 2 * e]),
+                                                   __uint_as_float(r[c][4 * n + 4 + 2 * e + 1]));
                             }
                         }
                     }
@@ -621,6 +721,9 @@ static __global__ void bw_fold_kernel(const float *__restrict__ tab, int M, doub
     if (blockIdx.x == 0 && i == 0) atomicAdd(c_tail + 1, (double)B);
 }
 
+static long long *g_bw_trace = nullptr;
+static cudaEvent_t g_bw_ev[3] = {nullptr, nullptr, nullptr};   // around the forward and backward launches of the last call
+
 struct BwWorkspace {
     float *stash, *scale, *tab, *Ar, *ATr;
     double *loglik;
@@ -666,6 +769,20 @@ static int make_tmap_stash(CUtensorMap *map, const float *stash, int64_t B, int6
 using namespace khmm;
 
 extern "C" {
+
+// development hook: device buffer of 8*32 int64 for the backward timeline (NULL disarms it)
+int khmm_debug_bw_trace(int64_t *dev_buf) {
+    g_bw_trace = (long long *)dev_buf;
+    return KHMM_OK;
+}
+
+int khmm_estep_tc_last_kernel_ms(float *forward_ms, float *backward_ms) {
+    KHMM_REQUIRE(g_bw_ev[2] != nullptr, "estep_tc_last_kernel_ms: no tensor-core E-step has been launched");
+    KHMM_CUDA_CHECK(cudaEventSynchronize(g_bw_ev[2]));
+    if (forward_ms) KHMM_CUDA_CHECK(cudaEventElapsedTime(forward_ms, g_bw_ev[0], g_bw_ev[1]));
+    if (backward_ms) KHMM_CUDA_CHECK(cudaEventElapsedTime(backward_ms, g_bw_ev[1], g_bw_ev[2]));
+    return KHMM_OK;
+}
 
 size_t khmm_estep_tc_workspace_bytes(int64_t B, int64_t T, int N, int M) {
     if (N != BW_N || B < 0 || T < 1 || M < 1) return 0;
@@ -713,18 +830,23 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
         size_t smem = BW_TILE + 2 * (size_t)FW_EBUF + sizeof(FwdBars) + 1024;
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = (int)(ntiles < sms ? ntiles : sms);
+        for (int k = 0; k < 3; k++)
+            if (!g_bw_ev[k]) KHMM_CUDA_CHECK(cudaEventCreate(&g_bw_ev[k]));
+        KHMM_CUDA_CHECK(cudaEventRecord(g_bw_ev[0], st));
         bw_forward_tc_kernel<<<grid, 256, smem, st>>>(mapAT, pi, Bsm, ob, B, T, w.stash, w.scale, w.loglik);
         KHMM_LAUNCH_CHECK("bw_forward_tc_kernel");
+        KHMM_CUDA_CHECK(cudaEventRecord(g_bw_ev[1], st));
     }
     {
-        size_t smem = 3 * (size_t)BW_TILE + sizeof(BwdBars) + 1024;
+        size_t smem = 3 * (size_t)BW_TILE + 2 * (size_t)BW_ECHUNK + sizeof(BwdBars) + 1024;
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = (int)(ntiles < sms ? ntiles : sms);
         double *c_xi = counts + BW_N;
         double *c_tail = counts + BW_N + (size_t)BW_N * BW_N + BW_N + (size_t)M * BW_N + BW_N;
-        BwdOut out{w.tab, c_xi, c_tail + 2};
+        BwdOut out{g_bw_trace, w.tab, c_xi, c_tail + 2};
         bw_backward_tc_kernel<<<grid, 384, smem, st>>>(mapA, mapStash, Bsm, ob, B, T, w.scale, out);
         KHMM_LAUNCH_CHECK("bw_backward_tc_kernel");
+        KHMM_CUDA_CHECK(cudaEventRecord(g_bw_ev[2], st));
     }
     bw_fold_kernel<<<64, 128, 0, st>>>(w.tab, M, counts, w.loglik, B);
     KHMM_LAUNCH_CHECK("bw_fold_kernel");
