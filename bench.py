@@ -94,7 +94,8 @@ def _cpu_chunk(args):
     return time.perf_counter() - t0
 
 
-CPU_SAMPLE = {"c2": (8192, 2048), "c3": (16, 512), "c4": (16, 128), "c5": (8, 16)}
+# bounded samples: ~10-20 core-seconds of the NumPy port each (sized on the 8-core build box)
+CPU_SAMPLE = {"c2": (8192, 2048), "c3": (1024, 1024), "c4": (1024, 512), "c5": (16, 32)}
 
 
 def cpu_params(kind, model):
@@ -292,6 +293,9 @@ def run_ours(args):
         algo_bytes = B * T * (N * 4 + 8 + 4)
         h2d, d2h = B * T * 2, 24
         dominant = "bw_backward_tc_kernel (tcgen05 kind::tf32, xi in TMEM, L2 count reductions)"
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=18944 (ncu --set full,
+        # profiles/r1_ncu_c4_bw_backward_tc_summary.csv), scaled to this batch: traffic ~ algorithmic bytes
+        ncu_traffic = (5.037033e9 + 0.004398e9) * (B * T) / (18944.0 * 512.0)
         l2_note = "forward stash of B*T*512 B per step (34 GB at B=131072, >> L2)"
         dtype = "tf32 multiply / f32 accumulate"
     elif kind == "c5":

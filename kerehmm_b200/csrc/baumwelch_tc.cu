@@ -522,10 +522,18 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                     // staging column 16*blk + 8*n2 + 2*j + e holds logical column 16*blk + 4*j + 2*n2 + e, so that the
                     // four registers a lane gets from two adjacent 16x256b repetitions are 4 CONSECUTIVE columns
                     // (one red.v4 per lane, a quad = 64 contiguous bytes of a row)
+                    if (t == 0) {
 #pragma unroll
-                    for (int q = 0; q < 32; q++) {
-                        const int lq = (q & 16) | ((q & 6) << 1) | ((q & 8) >> 2) | (q & 1);
-                        u[q] = __float_as_uint(fmaxf(g[lq] - sub, floorv) * inv);
+                        for (int q = 0; q < 32; q++) {
+                            const int lq = (q & 16) | ((q & 6) << 1) | ((q & 8) >> 2) | (q & 1);
+                            u[q] = __float_as_uint(fmaxf(g[lq] - sub, floorv) * inv);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; q++) {
+                            const int lq = (q & 16) | ((q & 6) << 1) | ((q & 8) >> 2) | (q & 1);
+                            u[q] = __float_as_uint(g[lq]);
+                        }
                     }
                     tmem_st_32x32(tmem + lane_base + COL_STG + c0, u);
                     if (t > 0) {

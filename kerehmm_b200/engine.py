@@ -387,6 +387,29 @@ def estep_tc_supported(p: ModelParams, ob: Obs, real) -> bool:
             and ob.T < 2 ** 31)
 
 
+_ws_cache = {}
+
+
+def workspace(nbytes: int, align: int = 1024):
+    """A cached, aligned device scratch buffer of at least `nbytes` (one per device, grown on demand).
+    The tensor-core E-step stash is tens of GB: re-allocating it every iteration costs a cudaMalloc of
+    that size whenever the caching allocator has let the block go."""
+    t = torch()
+    dev = device()
+    buf = _ws_cache.get(dev.index)
+    if buf is None or buf.numel() < nbytes + align:
+        _ws_cache.pop(dev.index, None)
+        buf = None
+        buf = t.empty((nbytes + align,), dtype=t.uint8, device=dev)
+        _ws_cache[dev.index] = buf
+    return buf, buf.data_ptr() + (-buf.data_ptr()) % align
+
+
+def release_workspace():
+    """Drop the cached scratch buffers (they are otherwise kept for the life of the process)."""
+    _ws_cache.clear()
+
+
 def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=None, stash_out=False):
     """Fused tensor-core E-step (khmm_estep_tc_discrete_f32).  With `stash_out` also returns the
     forward stash W[b][t][:] = c_t alpha_t and the scale factors of the LAST chunk (tests)."""
@@ -396,15 +419,20 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
     counts = counts or Counts(N, M)
     L = _lib.lib()
     if chunk is None:
-        free, _ = t.cuda.mem_get_info()
-        per_seq = ob.T * N * 4 + ob.T * 4 + 16
-        chunk = int(max(128, min(ob.B, (free * 0.8) // per_seq - 128)))
-        if chunk < ob.B:
-            chunk -= chunk % 128
+        cached = _ws_cache.get(dev.index)
+        if cached is not None and cached.numel() >= L.khmm_estep_tc_workspace_bytes(ob.B, ob.T, N, M) + 1024:
+            chunk = ob.B                      # the whole batch fits the scratch buffer we already hold
+        else:
+            free, _ = t.cuda.mem_get_info()
+            if cached is not None:
+                free += cached.numel()
+            per_seq = ob.T * N * 4 + ob.T * 4 + 16
+            chunk = int(max(128, min(ob.B, (free * 0.8) // per_seq - 128)))
+            if chunk < ob.B:
+                chunk -= chunk % 128
     nb0 = min(chunk, ob.B)
     nbytes = L.khmm_estep_tc_workspace_bytes(nb0, ob.T, N, M)
-    ws = t.empty((nbytes + 1024,), dtype=t.uint8, device=dev)
-    wsp = ws.data_ptr() + (-ws.data_ptr()) % 1024
+    ws, wsp = workspace(nbytes)
     W = sc = None
     if stash_out:
         W = t.zeros(((nb0 + 127) // 128, ob.T, 128, N), dtype=t.float32, device=dev)   # tile-major stash
