@@ -325,7 +325,8 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
             }
         }
     // 256-wide column tiles when N allows: 25 % less L2 operand traffic per MAC and half the CTAs
-    const int BN = (N % 256 == 0) ? 256 : 128;
+    // (small batches -- e.g. a strong-scaling shard -- keep 128-wide tiles so that more SMs get a CTA)
+    const int BN = (N % 256 == 0 && (Bp / TC_BM) * (N / 256) * ndir >= sm_count()) ? 256 : 128;
     // forward: out[j] = sum_i W[i] A[i][j]  -> B-operand rows j, K index i: AT[j][i]
     // backward: out[i] = sum_j A[i][j] w[j] -> B-operand rows i, K index j: A[i][j]
     if (make_tmap_f32_rowmajor(&mapM[0], ATr, N, N, BN) || make_tmap_f32_rowmajor(&mapM[1], Ar, N, N, BN)) {
