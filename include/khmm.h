@@ -263,8 +263,8 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
  * measurement (bench.py reports the dominant kernel's roofline from it). */
 int khmm_estep_tc_last_kernel_ms(float *forward_ms_host, float *backward_ms_host);
 
-/* Development hook: arm (device buffer of 8*32 int64) or disarm (NULL) a clock64 timeline of the warp roles
- * of the backward kernel (block 0, steps 8..15; tools/dbg_bw_trace.py prints it). */
+/* Development hook: arm (device buffer of 2*8*32 int64) or disarm (NULL) a clock64 timeline of the warp roles
+ * of the backward and forward kernels (block 0, steps 8..15; tools/dbg_bw_trace.py prints it). */
 int khmm_debug_bw_trace(int64_t *dev_buf);
 
 /* M-step on the device -- discrete_hmm.py:132-161 + util.smooth_probabilities (util.py:39-63),

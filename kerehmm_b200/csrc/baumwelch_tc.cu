@@ -91,29 +91,50 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
 // round to nearest tf32 for finite positive values: add half an ulp of the 10-bit mantissa, clear 13 bits
 __device__ __forceinline__ uint32_t tf32_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
-constexpr int FW_PITCH = 528;                  // 512-byte row + 16: thread-per-row 16-byte accesses hit 8 distinct bank groups
-constexpr int FW_EBUF = 128 * FW_PITCH;        // one emission / stash staging buffer (66 KB)
+constexpr int FW_EBUF = BW_TILE;   // one emission / stash staging buffer: 4 sub-tiles [128 rows][128 B], SWIZZLE_128B
 
 struct __align__(8) FwdBars {
     uint64_t mat_full, a_ready, d_full, e_full[2], w_ready[2], buf_free[2];
     uint32_t tmem_base;
 };
 
-// Shared memory: A^T (64 KB, K-major SW128) + two row buffers.  Buffer t&1: the gather warps copy the emission
-// rows b(o_t) of the tile into it one step ahead (cp.async, one coalesced 512-byte row per instruction), the
-// epilogue overwrites them IN PLACE with W_t (and parks c_t in the row's pad word), the storer warp streams the
-// rows to the tile-major stash and the scale array with coalesced stores and hands the buffer back.
-// Warps: 0-3 epilogue (thread = sequence = TMEM lane), 4 MMA issuer + TMEM allocator, 5-6 gather, 7 storer.
-__global__ void __launch_bounds__(256, 1)
-bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__restrict__ pi,
-                     const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T, float *__restrict__ stash,
-                     float *__restrict__ scale, double *__restrict__ loglik) {
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Shared memory: A^T (64 KB, K-major SW128) + two row buffers in the TMA box layout (4 sub-tiles of
+// [128 rows][32 floats], 16-byte pieces XOR (row & 7): thread-per-row LDS/STS.128 is conflict-free).  Buffer t&1:
+// the gather warps copy the emission rows b(o_t) of the tile into it one step ahead (cp.async, lane = 16-byte
+// piece, 4 rows per instruction), the epilogue overwrites them IN PLACE with W_t, and ONE thread sends the
+// whole 64 KB tile to the tile-major stash with four TMA tensor stores (plus one 512-byte bulk store for c_t).
+// Measured history of this kernel (clock64 timeline, tools/dbg_bw_trace.py): thread-per-row LDG/STG 12,000
+// cycles per step (32 L1 wavefronts per instruction); per-thread bulk copies 10,000 (UBLKCP serialises 32 per
+// warp); a storer warp doing LDS+STG per row 5,200 (the storer alone took 4,500).
+// Warps: 0-3 epilogue (thread = sequence = TMEM lane), 4 MMA issuer + TMEM allocator, 5-8 gather, 9 storer.
+__global__ void __launch_bounds__(320, 1)
+bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_constant__ CUtensorMap mapStashSt,
+                     const float *__restrict__ pi, const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T,
+                     float *__restrict__ scale, double *__restrict__ loglik, long long *trace) {
+#define FW_TRACE(ev)                                                                                      \
+    do {                                                                                                  \
+        if (trace && blockIdx.x == 0 && tile == blockIdx.x && t >= 8 && t < 16 && (threadIdx.x & 31) == 0) \
+            trace[256 + (t - 8) * 32 + (ev)] = clock64();                                                 \
+    } while (0)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // round up to 1024 B by pointer arithmetic on the shared array (an integer round trip would turn every
     // later access into a generic LD/ST that the compiler cannot reorder against global stores)
     unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *ebuf = tiles + BW_TILE;
-    FwdBars *bars = (FwdBars *)(ebuf + 2 * FW_EBUF);
+    float *csm = reinterpret_cast<float *>(ebuf + 2 * FW_EBUF);   // [2][128] scale factors of the step in flight
+    FwdBars *bars = (FwdBars *)(csm + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntiles = (B + 127) / 128;
 
@@ -122,7 +143,7 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__r
         mbar_init(&bars->a_ready, 128);
         mbar_init(&bars->d_full, 1);
         for (int k = 0; k < 2; k++) {
-            mbar_init(&bars->e_full[k], 64);
+            mbar_init(&bars->e_full[k], 128);
             mbar_init(&bars->w_ready[k], 128);
             mbar_init(&bars->buf_free[k], 1);
         }
@@ -146,6 +167,7 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__r
                 for (int64_t t = 1; t < T; t++) {
                     mbar_wait(&bars->a_ready, na & 1);
                     na++;
+                    FW_TRACE(0);
                     tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < 16; k++) {
@@ -153,59 +175,63 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__r
                         mma_tf32_ts(tmem, tmem + 128 + k * 8, desc_advance(db, (k & 3) * 32), idesc, k != 0);
                     }
                     tc_commit(&bars->d_full);
+                    FW_TRACE(1);
                 }
         }
-    } else if (warp == 5 || warp == 6) {
+    } else if (warp >= 5 && warp <= 8) {
         // ------------------------------------------------ gather: emission rows of step t -> buffer t&1
-        const int rbase = (warp - 5) * 64;
+        const int rbase = (warp - 5) * 32;          // this warp's 32 rows
+        const int rsub = lane >> 3, piece = lane & 7;
         uint32_t nuse[2] = {0, 0};
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            int64_t b0 = tile * 128 + rbase + lane, b1 = b0 + 32;
+            int64_t b0 = tile * 128 + rbase + lane;
             b0 = b0 < B ? b0 : B - 1;
-            b1 = b1 < B ? b1 : B - 1;
             for (int64_t t = 0; t < T; t++) {
                 const int buf = (int)(t & 1);
-                const int s0 = ob.sym(b0, t), s1 = ob.sym(b1, t);
+                const int s0 = ob.sym(b0, t);
                 mbar_wait(&bars->buf_free[buf], (nuse[buf] & 1) ^ 1);
                 nuse[buf]++;
-                unsigned char *dst = ebuf + buf * FW_EBUF + rbase * FW_PITCH + lane * 16;
-#pragma unroll 8
-                for (int k = 0; k < 64; k++) {
-                    const int sy = __shfl_sync(0xffffffffu, k < 32 ? s0 : s1, k & 31);
-                    cp_async16(dst + k * FW_PITCH, Bsm + (int64_t)sy * BW_N + lane * 4);
+                if (warp == 5) FW_TRACE(4);
+                unsigned char *dstb = ebuf + buf * FW_EBUF;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int rr = 4 * k + rsub;
+                    const int sy = __shfl_sync(0xffffffffu, s0, rr);
+                    const int row = rbase + rr;
+                    const float *src = Bsm + (int64_t)sy * BW_N + piece * 4;
+                    unsigned char *d = dstb + row * 128 + ((piece ^ (row & 7)) << 4);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) cp_async16(d + c * BW_SUB, src + c * 32);
                 }
                 cp_async_arrive(&bars->e_full[buf]);
+                if (warp == 5) FW_TRACE(5);
             }
         }
-    } else if (warp == 7) {
-        // ------------------------------------------------ storer: W_t rows + c_t -> HBM, coalesced
-        uint32_t nuse[2] = {0, 0};
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t left = B - tile * 128;
-            const int nlive = left < 128 ? (int)left : 128;
-            for (int64_t t = 0; t < T; t++) {
-                const int buf = (int)(t & 1);
-                mbar_wait(&bars->w_ready[buf], nuse[buf] & 1);
-                nuse[buf]++;
-                const unsigned char *src = ebuf + buf * FW_EBUF + lane * 16;
-                float4 *dst = reinterpret_cast<float4 *>(stash + ((tile * T + t) * 128) * BW_N) + lane;
-#pragma unroll 8
-                for (int r = 0; r < 128; r++) {
-                    float4 v = *reinterpret_cast<const float4 *>(src + r * FW_PITCH);
-                    if (r >= nlive) v = make_float4(0.f, 0.f, 0.f, 0.f);   // rows past the batch: MMA2 must see zeros
-                    dst[r * 32] = v;
+    } else if (warp == 9) {
+        // ------------------------------------------------ storer: one thread, TMA tensor stores of the W_t tile
+        if (elect_one()) {
+            tma_prefetch_desc(&mapStashSt);
+            uint32_t nuse[2] = {0, 0};
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int64_t t = 0; t < T; t++) {
+                    const int buf = (int)(t & 1);
+                    mbar_wait(&bars->w_ready[buf], nuse[buf] & 1);
+                    nuse[buf]++;
+                    FW_TRACE(8);
+                    for (int c = 0; c < 4; c++)
+                        tma_store_3d(&mapStashSt, ebuf + buf * FW_EBUF + c * BW_SUB, c * 32, 0, (int)(tile * T + t));
+                    bulk_store(scale + (tile * T + t) * 128, csm + buf * 128, 512);
+                    bulk_commit();
+                    bulk_wait_read0();          // shared memory has been read: the gather warps may refill the buffer
+                    mbar_arrive(&bars->buf_free[buf]);
+                    FW_TRACE(9);
                 }
-                float *sc = scale + (tile * T + t) * 128;
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    sc[k * 32 + lane] = *reinterpret_cast<const float *>(ebuf + buf * FW_EBUF + (k * 32 + lane) * FW_PITCH + 512);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->buf_free[buf]);
-            }
+            bulk_wait0();
         }
-    } else {
+    } else if (warp < 4) {
         const int row = threadIdx.x;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const int sw7 = row & 7;
         uint32_t nd = 0, ne[2] = {0, 0};
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t b = tile * 128 + row;
@@ -215,24 +241,26 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__r
             int esum = 0;            // its exponent
             for (int64_t t = 0; t < T; t++) {
                 const int cur = (int)(t & 1);
-                unsigned char *myrow = ebuf + cur * FW_EBUF + row * FW_PITCH;
+                unsigned char *myrow = ebuf + cur * FW_EBUF + row * 128;
                 if (t > 0) {
                     mbar_wait(&bars->d_full, nd & 1);
                     nd++;
                     tc_fence_after();
                 }
+                if (warp == 0) FW_TRACE(12);
                 mbar_wait(&bars->e_full[cur], ne[cur] & 1);
                 ne[cur]++;
+                if (warp == 0) FW_TRACE(13);
                 float rowsum = 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BW_N; c0 += 32) {
                     uint32_t acc[32];
                     float e[32];
                     if (t > 0) tmem_ld_32x32(tmem + lane_base + c0, acc);
-                    float4 *erow = reinterpret_cast<float4 *>(myrow + c0 * 4);
+                    unsigned char *erow = myrow + (c0 >> 5) * BW_SUB;
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
-                        float4 f = erow[q];
+                        float4 f = *reinterpret_cast<const float4 *>(erow + ((q ^ sw7) << 4));
                         e[4 * q] = f.x; e[4 * q + 1] = f.y; e[4 * q + 2] = f.z; e[4 * q + 3] = f.w;
                     }
                     if (t > 0) {
@@ -250,20 +278,23 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const float *__r
                     for (int q = 0; q < 32; q++) {
                         float v = __uint_as_float(acc[q]) * r * e[q];
                         rowsum += v;
-                        e[q] = v;
+                        e[q] = live ? v : 0.f;   // rows past the batch: the backward MMA2 must see zeros
                         w[q] = tf32_bits(v);
                     }
                     if (t + 1 < T) tmem_st_32x32(tmem + lane_base + 128 + c0, w);
 #pragma unroll
-                    for (int q = 0; q < 8; q++) erow[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+                    for (int q = 0; q < 8; q++)
+                        *reinterpret_cast<float4 *>(erow + ((q ^ sw7) << 4)) = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
                 }
-                *reinterpret_cast<float *>(myrow + 512) = rowsum;
+                csm[cur * 128 + row] = rowsum;
                 if (t + 1 < T) {
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(&bars->a_ready);
                 }
+                fence_proxy_async();         // the tile leaves through the async proxy (TMA store)
                 mbar_arrive(&bars->w_ready[cur]);
+                if (warp == 0) FW_TRACE(14);
                 r = 1.0f / rowsum;
                 int ex;
                 prod = frexpf(prod * rowsum, &ex);
@@ -753,7 +784,7 @@ static BwWorkspace bw_layout(void *ws, int64_t B, int64_t T, int M) {
     return w;
 }
 
-static int make_tmap_stash(CUtensorMap *map, const float *stash, int64_t B, int64_t T) {
+static int make_tmap_stash(CUtensorMap *map, const float *stash, int64_t B, int64_t T, CUtensorMapSwizzle swz) {
     static PFN_encodeTiled encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -767,7 +798,7 @@ static int make_tmap_stash(CUtensorMap *map, const float *stash, int64_t B, int6
     cuuint32_t box[3] = {32, 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)stash, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
@@ -778,7 +809,7 @@ using namespace khmm;
 
 extern "C" {
 
-// development hook: device buffer of 8*32 int64 for the backward timeline (NULL disarms it)
+// development hook: device buffer of 2*8*32 int64 for the backward + forward timelines (NULL disarms it)
 int khmm_debug_bw_trace(int64_t *dev_buf) {
     g_bw_trace = (long long *)dev_buf;
     return KHMM_OK;
@@ -825,9 +856,10 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
     bw_round_matrix_kernel<<<16, 256, 0, st>>>(A, w.Ar, BW_N * BW_N);
     bw_round_matrix_kernel<<<16, 256, 0, st>>>(AT, w.ATr, BW_N * BW_N);
     KHMM_CUDA_CHECK(cudaMemsetAsync(w.tab, 0, (size_t)BW_REPL * (M + 2) * BW_N * 4, st));
-    CUtensorMap mapAT, mapA, mapStash;
+    CUtensorMap mapAT, mapA, mapStash, mapStashSt;
     if (make_tmap_f32_rowmajor(&mapAT, w.ATr, BW_N, BW_N, 128) || make_tmap_f32_rowmajor(&mapA, w.Ar, BW_N, BW_N, 128) ||
-        make_tmap_stash(&mapStash, w.stash, B, T)) {
+        make_tmap_stash(&mapStash, w.stash, B, T, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        make_tmap_stash(&mapStashSt, w.stash, B, T, CU_TENSOR_MAP_SWIZZLE_128B)) {
         set_error("estep_tc: tensor map creation failed");
         return KHMM_ERR_CUDA;
     }
@@ -835,13 +867,13 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
     const int sms = sm_count();
     BwObs ob{obs, obs_dtype, M, T};
     {
-        size_t smem = BW_TILE + 2 * (size_t)FW_EBUF + sizeof(FwdBars) + 1024;
+        size_t smem = BW_TILE + 2 * (size_t)FW_EBUF + 2 * 128 * sizeof(float) + sizeof(FwdBars) + 1024;
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = (int)(ntiles < sms ? ntiles : sms);
         for (int k = 0; k < 3; k++)
             if (!g_bw_ev[k]) KHMM_CUDA_CHECK(cudaEventCreate(&g_bw_ev[k]));
         KHMM_CUDA_CHECK(cudaEventRecord(g_bw_ev[0], st));
-        bw_forward_tc_kernel<<<grid, 256, smem, st>>>(mapAT, pi, Bsm, ob, B, T, w.stash, w.scale, w.loglik);
+        bw_forward_tc_kernel<<<grid, 320, smem, st>>>(mapAT, mapStashSt, pi, Bsm, ob, B, T, w.scale, w.loglik, g_bw_trace);
         KHMM_LAUNCH_CHECK("bw_forward_tc_kernel");
         KHMM_CUDA_CHECK(cudaEventRecord(g_bw_ev[1], st));
     }

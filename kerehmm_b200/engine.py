@@ -288,9 +288,7 @@ def fwdbwd_loglik_tc(p: ModelParams, ob: Obs, both=True):
     ll = t.empty((ob.B,), dtype=t.float64, device=dev)
     llb = t.empty((ob.B,), dtype=t.float64, device=dev) if both else None
     nbytes = _lib.lib().khmm_fwdbwd_loglik_tc_workspace_bytes(ob.B, p.N)
-    ws = t.empty((nbytes + 256,), dtype=t.uint8, device=dev)
-    off = (-ws.data_ptr()) % 256
-    wsp = ws.data_ptr() + off
+    ws, wsp = workspace(nbytes, 256)
     if p.kind == "gauss":
         _lib.call("khmm_fwdbwd_loglik_tc_gauss_f32", ob.B, ob.T, p.N, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.mean),
                   ptr(dm.sd), ptr(ob.tensor), ob.code, wsp, nbytes, ptr(ll), ptr(llb), stream_ptr())
@@ -319,9 +317,9 @@ def viterbi(p: ModelParams, ob: Obs, path_dtype=None):
     path = t.zeros((ob.B, ob.T), dtype=path_dtype, device=dev)
     logp = t.empty((ob.B,), dtype=t.float64, device=dev)
     ws_bytes = _lib.lib().khmm_viterbi_workspace_bytes(ob.B, ob.T, N)
-    ws = t.empty((ws_bytes,), dtype=t.uint8, device=dev)
+    ws, wsp = workspace(ws_bytes, 256)      # cached: the backpointer workspace is 17 GB at config 3
     _lib.call("khmm_viterbi_discrete_f64", ob.B, ob.T, N, M, ptr(d_logpi), ptr(d_logA), ptr(d_logBsm),
-              ptr(ob.tensor), ob.code, ptr(ob.lengths), ptr(ws), ws_bytes, ptr(path), _PATH_CODES[pname],
+              ptr(ob.tensor), ob.code, ptr(ob.lengths), wsp, ws_bytes, ptr(path), _PATH_CODES[pname],
               ptr(logp), stream_ptr())
     return path, logp
 

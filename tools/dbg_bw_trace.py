@@ -13,13 +13,20 @@ obs = np.random.default_rng(1004).integers(0, M, size=(B, T)).astype(np.uint16)
 ob = engine.prepare_obs(torch.from_numpy(obs.view(np.int16)).cuda(), symbols=True, u16_bits=True)
 p = h._params()
 engine.estep_discrete_tc(p, ob)
-tr = torch.zeros(8 * 32, dtype=torch.int64, device="cuda")
+tr = torch.zeros(2 * 8 * 32, dtype=torch.int64, device="cuda")
 L = _lib.lib()
 L.khmm_debug_bw_trace(tr.data_ptr())
 engine.estep_discrete_tc(p, ob)
 torch.cuda.synchronize()
 L.khmm_debug_bw_trace(None)
-a = tr.cpu().numpy().reshape(8, 32)
+full = tr.cpu().numpy()
+a = full[:256].reshape(8, 32)
+f = full[256:].reshape(8, 32)
+fn = {0: 'mma:a_ready ok', 1: 'mma:issued', 4: 'gat:buf_free ok', 5: 'gat:issued', 8: 'sto:w_ready ok', 9: 'sto:done', 12: 'epi:d_full ok', 13: 'epi:e_full ok', 14: 'epi:done'}
+fb = f[0, 12]
+for s_ in range(4, 8):
+    ev = sorted((int(f[s_, k] - fb), fn[k]) for k in fn if f[s_, k])
+    print('FWD step', s_ + 8, ' | '.join('%s @%d' % (n, c) for c, n in ev))
 names = {0: "tma:alpha_empty ok", 4: "mma:v_ready ok", 5: "mma:MMA1 issued", 6: "mma:alpha_full ok", 7: "mma:MMA2 issued",
          8: "epi:d1_full ok", 9: "epi:alpha_full ok", 10: "epi:stage_empty ok", 11: "epi:passA done", 12: "epi:stage_full sent",
          13: "epi:mma2_done ok", 14: "epi:v_ready sent", 16: "red:stage_full ok", 17: "red:staging read"}
