@@ -118,8 +118,10 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // Measured history of this kernel (clock64 timeline, tools/dbg_bw_trace.py): thread-per-row LDG/STG 12,000
 // cycles per step (32 L1 wavefronts per instruction); per-thread bulk copies 10,000 (UBLKCP serialises 32 per
 // warp); a storer warp doing LDS+STG per row 5,200 (the storer alone took 4,500).
-// Warps: 0-3 epilogue (thread = sequence = TMEM lane), 4 MMA issuer + TMEM allocator, 5-8 gather, 9 storer.
-__global__ void __launch_bounds__(320, 1)
+// Warps: 0-7 epilogue (thread = sequence = TMEM lane; warps 0-3 own columns 0-63, warps 4-7 columns 64-127 of
+// the same rows, the two halves of a row sum meet in shared memory), 8 MMA issuer + TMEM allocator, 9-10 gather,
+// 11 storer.
+__global__ void __launch_bounds__(384, 1)
 bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_constant__ CUtensorMap mapStashSt,
                      const float *__restrict__ pi, const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T,
                      float *__restrict__ scale, double *__restrict__ loglik, long long *trace) {
@@ -134,28 +136,29 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
     unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *ebuf = tiles + BW_TILE;
     float *csm = reinterpret_cast<float *>(ebuf + 2 * FW_EBUF);   // [2][128] scale factors of the step in flight
-    FwdBars *bars = (FwdBars *)(csm + 256);
+    float *psm = csm + 256;                                       // [2 parities][2 halves][128] partial row sums
+    FwdBars *bars = (FwdBars *)(psm + 512);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntiles = (B + 127) / 128;
 
     if (threadIdx.x == 0) {
         mbar_init(&bars->mat_full, 1);
-        mbar_init(&bars->a_ready, 128);
+        mbar_init(&bars->a_ready, 256);
         mbar_init(&bars->d_full, 1);
         for (int k = 0; k < 2; k++) {
-            mbar_init(&bars->e_full[k], 128);
-            mbar_init(&bars->w_ready[k], 128);
+            mbar_init(&bars->e_full[k], 64);
+            mbar_init(&bars->w_ready[k], 256);
             mbar_init(&bars->buf_free[k], 1);
         }
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(&bars->tmem_base, 256);
+    if (warp == 8) tmem_alloc(&bars->tmem_base, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;   // columns [0,128): accumulator D, [128,256): A operand W
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (elect_one()) {
             tma_prefetch_desc(&mapAT);
             mbar_arrive_expect_tx(&bars->mat_full, BW_TILE);
@@ -178,25 +181,26 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                     FW_TRACE(1);
                 }
         }
-    } else if (warp >= 5 && warp <= 8) {
+    } else if (warp == 9 || warp == 10) {
         // ------------------------------------------------ gather: emission rows of step t -> buffer t&1
-        const int rbase = (warp - 5) * 32;          // this warp's 32 rows
+        const int rbase = (warp - 9) * 64;          // this warp's 64 rows
         const int rsub = lane >> 3, piece = lane & 7;
         uint32_t nuse[2] = {0, 0};
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            int64_t b0 = tile * 128 + rbase + lane;
+            int64_t b0 = tile * 128 + rbase + lane, b1 = b0 + 32;
             b0 = b0 < B ? b0 : B - 1;
+            b1 = b1 < B ? b1 : B - 1;
             for (int64_t t = 0; t < T; t++) {
                 const int buf = (int)(t & 1);
-                const int s0 = ob.sym(b0, t);
+                const int s0 = ob.sym(b0, t), s1 = ob.sym(b1, t);
                 mbar_wait(&bars->buf_free[buf], (nuse[buf] & 1) ^ 1);
                 nuse[buf]++;
-                if (warp == 5) FW_TRACE(4);
+                if (warp == 9) FW_TRACE(4);
                 unsigned char *dstb = ebuf + buf * FW_EBUF;
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
+                for (int k = 0; k < 16; k++) {
                     const int rr = 4 * k + rsub;
-                    const int sy = __shfl_sync(0xffffffffu, s0, rr);
+                    const int sy = __shfl_sync(0xffffffffu, k < 8 ? s0 : s1, rr & 31);
                     const int row = rbase + rr;
                     const float *src = Bsm + (int64_t)sy * BW_N + piece * 4;
                     unsigned char *d = dstb + row * 128 + ((piece ^ (row & 7)) << 4);
@@ -204,10 +208,10 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                     for (int c = 0; c < 4; c++) cp_async16(d + c * BW_SUB, src + c * 32);
                 }
                 cp_async_arrive(&bars->e_full[buf]);
-                if (warp == 5) FW_TRACE(5);
+                if (warp == 9) FW_TRACE(5);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 11) {
         // ------------------------------------------------ storer: one thread, TMA tensor stores of the W_t tile
         if (elect_one()) {
             tma_prefetch_desc(&mapStashSt);
@@ -228,9 +232,10 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                 }
             bulk_wait0();
         }
-    } else if (warp < 4) {
-        const int row = threadIdx.x;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    } else if (warp < 8) {
+        const int row = threadIdx.x & 127;
+        const int half = warp >> 2;                  // column half: chunks {0,1} or {2,3}
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const int sw7 = row & 7;
         uint32_t nd = 0, ne[2] = {0, 0};
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -253,7 +258,7 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                 if (warp == 0) FW_TRACE(13);
                 float rowsum = 0.f;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BW_N; c0 += 32) {
+                for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
                     uint32_t acc[32];
                     float e[32];
                     if (t > 0) tmem_ld_32x32(tmem + lane_base + c0, acc);
@@ -286,7 +291,11 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                     for (int q = 0; q < 8; q++)
                         *reinterpret_cast<float4 *>(erow + ((q ^ sw7) << 4)) = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
                 }
-                csm[cur * 128 + row] = rowsum;
+                // the two column halves of a row exchange their partial sums (named barrier of the two warps)
+                psm[(cur * 2 + half) * 128 + row] = rowsum;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
+                rowsum += psm[(cur * 2 + (half ^ 1)) * 128 + row];
+                if (half == 0) csm[cur * 128 + row] = rowsum;
                 if (t + 1 < T) {
                     tmem_st_wait();
                     tc_fence_before();
@@ -300,12 +309,12 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                 prod = frexpf(prod * rowsum, &ex);
                 esum += ex;
             }
-            if (live) loglik[b] = (double)esum * 0.6931471805599453 + log((double)prod);
+            if (live && half == 0) loglik[b] = (double)esum * 0.6931471805599453 + log((double)prod);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, 256);
+    if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
 // ------------------------------------------------------------------------------ backward
@@ -867,13 +876,13 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
     const int sms = sm_count();
     BwObs ob{obs, obs_dtype, M, T};
     {
-        size_t smem = BW_TILE + 2 * (size_t)FW_EBUF + 2 * 128 * sizeof(float) + sizeof(FwdBars) + 1024;
+        size_t smem = BW_TILE + 2 * (size_t)FW_EBUF + 6 * 128 * sizeof(float) + sizeof(FwdBars) + 1024;
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = (int)(ntiles < sms ? ntiles : sms);
         for (int k = 0; k < 3; k++)
             if (!g_bw_ev[k]) KHMM_CUDA_CHECK(cudaEventCreate(&g_bw_ev[k]));
         KHMM_CUDA_CHECK(cudaEventRecord(g_bw_ev[0], st));
-        bw_forward_tc_kernel<<<grid, 320, smem, st>>>(mapAT, mapStashSt, pi, Bsm, ob, B, T, w.scale, w.loglik, g_bw_trace);
+        bw_forward_tc_kernel<<<grid, 384, smem, st>>>(mapAT, mapStashSt, pi, Bsm, ob, B, T, w.scale, w.loglik, g_bw_trace);
         KHMM_LAUNCH_CHECK("bw_forward_tc_kernel");
         KHMM_CUDA_CHECK(cudaEventRecord(g_bw_ev[1], st));
     }
