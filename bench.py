@@ -94,8 +94,8 @@ def _cpu_chunk(args):
     return time.perf_counter() - t0
 
 
-# bounded samples: ~10-20 core-seconds of the NumPy port each (sized on the 8-core build box)
-CPU_SAMPLE = {"c2": (8192, 2048), "c3": (1024, 1024), "c4": (1024, 512), "c5": (16, 32)}
+# bounded samples: a few seconds of wall time of the NumPy port on the GPU box's 16+ host cores each
+CPU_SAMPLE = {"c2": (16384, 2048), "c3": (8192, 1024), "c4": (8192, 512), "c5": (32, 32)}
 
 
 def cpu_params(kind, model):
