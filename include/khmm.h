@@ -267,6 +267,26 @@ int khmm_estep_tc_last_kernel_ms(float *forward_ms_host, float *backward_ms_host
  * of the backward and forward kernels (block 0, steps 8..15; tools/dbg_bw_trace.py prints it). */
 int khmm_debug_bw_trace(int64_t *dev_buf);
 
+/* ---------------------------------------------------------------------------------------
+ * Batched ancestral sampling -- AbstractHMM.simulate / transition / emit (abstract_hmm.py:444-469,
+ * distribution.py:38-39, :157-161).  Per step: transition (from pi for the first step, then from row
+ * A[current]), then emit from the new state.  cum_pi[N], cumA[N][N] (row-wise), cumB[N][M] (state-major,
+ * row-wise) are the float64 CDFs numpy.random.choice builds (cumsum(p) / cumsum(p)[-1]); the kernel does
+ * choice's right-sided searchsorted.  Gaussian emissions: mean + sd * z, z by Box-Muller in float64.
+ * uniforms == NULL: Philox4x32-10 keyed by `seed`, counter = (sequence, step) -- a sequence's stream is
+ * independent of the batch shape.  uniforms != NULL: [B][T][3] float64 in [0,1) used instead
+ * (state draw, emission draw, second Box-Muller draw): with identical uniforms states and symbols are
+ * identical to the NumPy procedure (tests).  The reference's MT19937 stream is not reproduced.
+ * states/symbols: [B][T] int32; values: [B][T] float64. */
+int khmm_simulate_discrete(int64_t B, int64_t T, int N, int M, const double *cum_pi, const double *cumA,
+                           const double *cumB, uint64_t seed, const double *uniforms, int32_t *states,
+                           int32_t *symbols, khmm_stream_t stream);
+int khmm_simulate_gauss(int64_t B, int64_t T, int N, const double *cum_pi, const double *cumA, const double *mean,
+                        const double *sd, uint64_t seed, const double *uniforms, int32_t *states, double *values,
+                        khmm_stream_t stream);
+/* Known-answer hook for the generator: n blocks of (4 counter words, 2 key words) -> 4 output words each. */
+int khmm_philox4x32_10(int n, const uint32_t *ctr_key, uint32_t *out, khmm_stream_t stream);
+
 /* M-step on the device -- discrete_hmm.py:132-161 + util.smooth_probabilities (util.py:39-63),
  * float64, operation for operation.  Reads counts (after the all-reduce), A (old, [N][N]);
  * writes pi_new[N], A_new[N][N], B_new state-major [N][M].  status[0] (device int32) gets a

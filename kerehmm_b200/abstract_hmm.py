@@ -288,6 +288,18 @@ class AbstractHMM(object):
             emissions.append(self.emit())
         return SimulationResult(states=states, emissions=emissions)
 
+    def simulate_batch(self, n_sequences, iterations, seed=0, uniforms=None, to_host=True):
+        """`n_sequences` independent `simulate(iterations)` runs on the device -> `SimulationResult`
+        with `states` (B, T) int32 and `emissions` (B, T) (int32 symbols / float64 values).  Same
+        procedure as the reference (transition, then emit, per step; numpy.random.choice's CDF search)
+        driven by a counter-based Philox4x32-10 stream keyed by `seed`; the reference's global-RNG
+        stream is not reproduced, so agreement with `simulate` is distributional.  `uniforms`
+        (B, T, 3) overrides the generator (tests)."""
+        states, em = engine.simulate(self._params(), int(n_sequences), int(iterations), seed, uniforms)
+        if to_host:
+            states, em = states.cpu().numpy(), em.cpu().numpy()
+        return SimulationResult(states=states, emissions=em)
+
     # ------------------------------------------------------------------ batched engine
     @staticmethod
     def _real(dtype):

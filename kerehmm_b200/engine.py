@@ -500,3 +500,39 @@ def mstep_discrete(p: ModelParams, counts: Counts):
     if st & 4:
         raise AssertionError("sanity_check failed: a re-estimated distribution does not sum to 1")
     return pi_new.cpu().numpy(), A_new.cpu().numpy(), B_new.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------- sampling
+def _cdf(p):
+    """The CDF numpy.random.choice(p=...) searches: cumsum(p) / cumsum(p)[-1] (last axis)."""
+    c = np.cumsum(np.asarray(p, dtype=np.float64), axis=-1)
+    return c / c[..., -1:]
+
+
+def simulate(p: ModelParams, B: int, T: int, seed: int = 0, uniforms=None):
+    """Batched AbstractHMM.simulate on the device -> (states[B][T] int32, emissions[B][T]) device tensors
+    (int32 symbols for discrete models, float64 values for 1-D Gaussians)."""
+    t = require_cuda()
+    dev = device()
+    if B < 0 or T < 1:
+        raise ValueError("simulate needs B >= 0 and T >= 1")
+    cum_pi, cumA = _dev(_cdf(p.pi), t.float64), _dev(_cdf(p.A), t.float64)
+    U = None
+    if uniforms is not None:
+        U = t.as_tensor(np.ascontiguousarray(uniforms, dtype=np.float64)).to(dev)
+        if tuple(U.shape) != (B, T, 3):
+            raise ValueError("uniforms must have shape (B, T, 3)")
+    states = t.empty((B, T), dtype=t.int32, device=dev)
+    if p.kind == "discrete":
+        cumB = _dev(_cdf(p.B), t.float64)
+        out = t.empty((B, T), dtype=t.int32, device=dev)
+        _lib.call("khmm_simulate_discrete", B, T, p.N, p.M, ptr(cum_pi), ptr(cumA), ptr(cumB), int(seed) & (2 ** 64 - 1),
+                  ptr(U), ptr(states), ptr(out), stream_ptr())
+    elif p.kind == "gauss":
+        mean, sd = _dev(p.mean, t.float64), _dev(p.sd, t.float64)
+        out = t.empty((B, T), dtype=t.float64, device=dev)
+        _lib.call("khmm_simulate_gauss", B, T, p.N, ptr(cum_pi), ptr(cumA), ptr(mean), ptr(sd), int(seed) & (2 ** 64 - 1),
+                  ptr(U), ptr(states), ptr(out), stream_ptr())
+    else:
+        raise NotImplementedError("batched sampling covers discrete and 1-D Gaussian emissions")
+    return states, out

@@ -346,3 +346,35 @@ def fwdbwd_loglik_batch(pi, A, E):
     alpha, scale = forward(pi, A, E)
     beta = backward(A, E, scale)
     return loglik(scale), alpha, beta
+
+
+# ----------------------------------------------------------------------------- sampling
+def simulate_from_uniforms(pi, A, U, Bm=None, mean=None, sd=None):
+    """`AbstractHMM.simulate` (abstract_hmm.py:458-469: per step `transition()` :449-456, then `emit()`
+    :444-447) for a batch, with the uniform draws given explicitly: U[b, t] = (state draw, emission draw,
+    second Box-Muller draw).  `numpy.random.choice(range(n), p=p)` is restated as NumPy implements it:
+    cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, side="right").  Discrete emission
+    (distribution.py:38-39) is another `choice`; the Gaussian one (distribution.py:157-161,
+    `norm(loc=mean, scale=variance).rvs()`) is mean + sd*z with z by Box-Muller -- the reference draws z
+    from NumPy's generator instead, so only the distribution, not the stream, is comparable."""
+    def cdf(p):
+        c = np.cumsum(np.asarray(p, dtype=np.float64), axis=-1)
+        return c / c[..., -1:]
+    U = np.asarray(U, dtype=np.float64)
+    Bn, T = U.shape[:2]
+    cpi, cA = cdf(pi), cdf(A)
+    cB = cdf(Bm) if Bm is not None else None
+    states = np.zeros((Bn, T), dtype=np.int64)
+    out = np.zeros((Bn, T), dtype=np.int64 if Bm is not None else np.float64)
+    for b in range(Bn):
+        cur = None
+        for t in range(T):
+            row = cpi if cur is None else cA[cur]
+            cur = min(int(np.searchsorted(row, U[b, t, 0], side="right")), len(row) - 1)
+            states[b, t] = cur
+            if Bm is not None:
+                out[b, t] = min(int(np.searchsorted(cB[cur], U[b, t, 1], side="right")), cB.shape[1] - 1)
+            else:
+                z = np.sqrt(-2.0 * np.log(1.0 - U[b, t, 1])) * np.cos(2.0 * np.pi * U[b, t, 2])
+                out[b, t] = mean[cur] + sd[cur] * z
+    return states, out

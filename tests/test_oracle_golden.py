@@ -220,3 +220,15 @@ def test_oracle_against_live_reference_if_present():
     new = O.do_pass_discrete(pi, A, Bm, obs)
     np.testing.assert_allclose(new[1], h.transitionMatrix, rtol=1e-11)
     np.testing.assert_allclose(new[2], np.stack([d.probabilities for d in h.emissionDistributions]), rtol=1e-11)
+
+
+# ------------------------------------------------------------------------------ sampling
+@pytest.mark.parametrize("name", ["small", "wide"])
+def test_simulate_restatement_matches_reference_golden(name):
+    """`simulate` of the real reference (tests/golden/simulate_golden.npz, oracle/make_golden_simulate.py):
+    with the MT19937 doubles the reference's numpy.random.choice calls consumed, the oracle's sampling
+    procedure returns the reference's states and emissions exactly."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "simulate_golden.npz"))
+    s, e = O.simulate_from_uniforms(g[name + "_pi"], g[name + "_A"], g[name + "_uniforms"], Bm=g[name + "_B"])
+    assert np.array_equal(s, g[name + "_states"]) and np.array_equal(e, g[name + "_emissions"])
