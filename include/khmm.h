@@ -287,6 +287,30 @@ int khmm_simulate_gauss(int64_t B, int64_t T, int N, const double *cum_pi, const
 /* Known-answer hook for the generator: n blocks of (4 counter words, 2 key words) -> 4 output words each. */
 int khmm_philox4x32_10(int n, const uint32_t *ctr_key, uint32_t *out, khmm_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Baum-Welch for 1-D Gaussian emissions -- an EXTENSION: GaussianHMM.do_pass (gaussian_hmm.py:29-124) is
+ * stale code that raises at HEAD, so this is textbook EM on the reference's scaled recursions:
+ * gamma = alpha*beta, xi_t = alpha_t(i) A_ij b_j(x_{t+1}) beta_{t+1}(j) / c_{t+1}; pi = mean of smooth1d(gamma_0),
+ * A rows = smooth1d(rownorm(xi/gam)) (util.py:56-60; the 2-D rule of util.py:46-55 raises for rows with several
+ * tiny entries); mean_i = sum gamma x / sum gamma,
+ * sd_i = sqrt(max(sum gamma x^2 / sum gamma - mean_i^2, sd_min^2)) (sd = the `variance` attribute).
+ * Call order per chunk: khmm_forward_gauss_* -> khmm_backward_gauss_* (beta) -> khmm_estep_gauss_* (adds
+ * into counts, writes V[b][t][j] = b_j(x_t) beta_t(j) / c_t) -> khmm_xi_accumulate_* (alpha, V, counts.xi)
+ * -> all-reduce -> khmm_mstep_gauss_f64.  counts: khmm_counts_len_gauss(N) doubles
+ *   [ pi: N | xi_raw: N*N | gam: N | S0 = sum gamma: N | S1 = sum gamma x: N | S2 = sum gamma x^2: N |
+ *     loglik_sum, nseq, flags ].
+ * mstep status bits: 1 ZeroDivisionError case (every entry of a row < 1e-10), 4 sanity_check failure,
+ * 8 a state with no posterior mass (mean undefined). */
+size_t khmm_counts_len_gauss(int N);
+int khmm_estep_gauss_f32(int64_t B, int64_t T, int N, const float *mean, const float *sd, const void *obs,
+                         int obs_dtype, const int32_t *lengths, const float *alpha, const float *beta,
+                         const float *scale, float *V, double *counts, khmm_stream_t stream);
+int khmm_estep_gauss_f64(int64_t B, int64_t T, int N, const double *mean, const double *sd, const void *obs,
+                         int obs_dtype, const int32_t *lengths, const double *alpha, const double *beta,
+                         const double *scale, double *V, double *counts, khmm_stream_t stream);
+int khmm_mstep_gauss_f64(int N, const double *counts, const double *A, double sd_min, double *pi_new, double *A_new,
+                         double *mean_new, double *sd_new, int32_t *status, khmm_stream_t stream);
+
 /* M-step on the device -- discrete_hmm.py:132-161 + util.smooth_probabilities (util.py:39-63),
  * float64, operation for operation.  Reads counts (after the all-reduce), A (old, [N][N]);
  * writes pi_new[N], A_new[N][N], B_new state-major [N][M].  status[0] (device int32) gets a

@@ -17,7 +17,8 @@ GAMMA_REFERENCE, GAMMA_POSTERIOR = 0, 1
 SMALL_N_MAX = 16
 
 _SCALARS = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
-            "int32_t": ctypes.c_int32, "uint64_t": ctypes.c_uint64, "uint32_t": ctypes.c_uint32}
+            "int32_t": ctypes.c_int32, "uint64_t": ctypes.c_uint64, "uint32_t": ctypes.c_uint32,
+            "double": ctypes.c_double, "float": ctypes.c_float}
 
 
 class KhmmError(RuntimeError):

@@ -536,3 +536,84 @@ def simulate(p: ModelParams, B: int, T: int, seed: int = 0, uniforms=None):
     else:
         raise NotImplementedError("batched sampling covers discrete and 1-D Gaussian emissions")
     return states, out
+
+
+# ------------------------------------------------------------- Gaussian Baum-Welch (extension)
+class GaussCounts:
+    """View helpers over the packed float64 count buffer of the Gaussian E-step (include/khmm.h)."""
+
+    def __init__(self, N, buf=None):
+        t = require_cuda()
+        self.N = N
+        n = _lib.lib().khmm_counts_len_gauss(N)
+        self.buf = buf if buf is not None else t.zeros((n,), dtype=t.float64, device=device())
+        o = 0
+        self.sl = {}
+        for name, size in (("pi", N), ("xi", N * N), ("gam", N), ("s0", N), ("s1", N), ("s2", N), ("tail", 3)):
+            self.sl[name] = slice(o, o + size)
+            o += size
+
+    def host(self):
+        h = self.buf.cpu().numpy()
+        N = self.N
+        return dict(pi=h[self.sl["pi"]], xi_raw=h[self.sl["xi"]].reshape(N, N), gam=h[self.sl["gam"]],
+                    s0=h[self.sl["s0"]], s1=h[self.sl["s1"]], s2=h[self.sl["s2"]],
+                    loglik=h[self.sl["tail"]][0], nseq=h[self.sl["tail"]][1], flags=h[self.sl["tail"]][2])
+
+
+def estep_gauss(p: ModelParams, ob: Obs, real, counts: GaussCounts = None, chunk=None):
+    """Textbook-EM statistics of a batch for 1-D Gaussian emissions (extension, include/khmm.h)."""
+    t = require_cuda()
+    if p.kind != "gauss":
+        raise NotImplementedError("Gaussian Baum-Welch covers 1-D Gaussian emissions")
+    dm = DeviceModel(p, real)
+    N, dev = p.N, device()
+    counts = counts or GaussCounts(N)
+    esize = 4 if real == t.float32 else 8
+    if chunk is None:
+        free, _ = t.cuda.mem_get_info()
+        chunk = int(max(1, min(ob.B, (free * 0.7) // (ob.T * N * esize * 3 + ob.T * esize + 64))))
+    sfx = dm.suffix
+    nb0 = min(chunk, ob.B)
+    alpha = t.empty((nb0, ob.T, N), dtype=real, device=dev)
+    beta = t.empty_like(alpha)
+    V = t.empty_like(alpha)
+    scale = t.empty((nb0, ob.T), dtype=real, device=dev)
+    xi_ptr = counts.buf[counts.sl["xi"]].data_ptr()
+    for b0 in range(0, ob.B, chunk):
+        nb = min(chunk, ob.B - b0)
+        obs_c = ob.tensor[b0:b0 + nb]
+        len_c = None if ob.lengths is None else ob.lengths[b0:b0 + nb]
+        _lib.call("khmm_forward_gauss_" + sfx, nb, ob.T, N, ptr(dm.pi), ptr(dm.A), ptr(dm.mean), ptr(dm.sd), ptr(obs_c),
+                  ob.code, ptr(len_c), ptr(alpha), ptr(scale), None, stream_ptr())
+        _lib.call("khmm_backward_gauss_" + sfx, nb, ob.T, N, ptr(dm.AT), ptr(dm.mean), ptr(dm.sd), ptr(obs_c), ob.code,
+                  ptr(len_c), ptr(scale), None, ptr(beta), None, _lib.GAMMA_POSTERIOR, stream_ptr())
+        _lib.call("khmm_estep_gauss_" + sfx, nb, ob.T, N, ptr(dm.mean), ptr(dm.sd), ptr(obs_c), ob.code, ptr(len_c),
+                  ptr(alpha), ptr(beta), ptr(scale), ptr(V), ptr(counts.buf), stream_ptr())
+        _lib.call("khmm_xi_accumulate_" + sfx, nb, ob.T, N, ptr(len_c), ptr(alpha), ptr(V), xi_ptr, stream_ptr())
+    return counts
+
+
+def mstep_gauss(p: ModelParams, counts: GaussCounts, sd_min: float = 1e-6):
+    """Device M-step -> (pi, A, mean, sd) float64 NumPy."""
+    t = require_cuda()
+    N, dev = p.N, device()
+    A_old = _dev(p.A, t.float64)
+    pi_new = t.empty((N,), dtype=t.float64, device=dev)
+    A_new = t.empty((N, N), dtype=t.float64, device=dev)
+    mean_new = t.empty((N,), dtype=t.float64, device=dev)
+    sd_new = t.empty((N,), dtype=t.float64, device=dev)
+    status = t.zeros((1,), dtype=t.int32, device=dev)
+    _lib.call("khmm_mstep_gauss_f64", N, ptr(counts.buf), ptr(A_old), float(sd_min), ptr(pi_new), ptr(A_new),
+              ptr(mean_new), ptr(sd_new), ptr(status), stream_ptr())
+    st = int(status.item())
+    if st & 1:
+        raise ZeroDivisionError("float division by zero")
+    if st & 2:
+        raise ValueError("operands could not be broadcast together "
+                         "(smooth_probabilities 2-D path with 2 <= k < n small entries, util.py:51-53)")
+    if st & 8:
+        raise ValueError("a state received no posterior mass: its mean and variance are undefined")
+    if st & 4:
+        raise AssertionError("sanity_check failed: a re-estimated distribution does not sum to 1")
+    return pi_new.cpu().numpy(), A_new.cpu().numpy(), mean_new.cpu().numpy(), sd_new.cpu().numpy()

@@ -56,3 +56,38 @@ class GaussianHMM(AbstractHMM):
         SURVEY.md Q9).  There are no semantics to reproduce; a Gaussian M-step is listed as a
         next-step extension."""
         raise TypeError("backward() missing 1 required positional argument: 'scale_coefficients'")
+
+    # ------------------------------------------------- batched Baum-Welch (extension, SURVEY.md 8(f))
+    def estep_batch(self, observations, lengths=None, dtype="float32", chunk=None, counts=None):
+        """Textbook-EM sufficient statistics of a batch (1-D Gaussian emissions) as an
+        `engine.GaussCounts` on the device.  EXTENSION: the reference's Gaussian training is broken at
+        HEAD (see `do_pass`), so there are no reference semantics here; `DESIGN.md` states the definition."""
+        ob = self._prep(observations, lengths)
+        return engine.estep_gauss(self._params(), ob, self._real(dtype), counts=counts, chunk=chunk)
+
+    def do_pass_batch(self, observations, lengths=None, dtype="float32", chunk=None, group=None, sd_min=1e-6):
+        """One EM pass over a batch (this rank's shard under torch.distributed: the packed counts are
+        all-reduced before the M-step).  Re-estimates pi, A (smoothed like the discrete path), means and
+        standard deviations (`variance` attribute); returns the batch log-likelihood under the OLD
+        parameters, which textbook EM never decreases."""
+        from . import dist
+        p = self._params()
+        counts = self.estep_batch(observations, lengths, dtype, chunk)
+        dist.all_reduce_counts(counts.buf, group=group)
+        loglik = float(counts.buf[counts.sl["tail"]][0].item())
+        pi, A, mean, sd = engine.mstep_gauss(p, counts, sd_min)
+        self.initialProbabilities = pi
+        self.transitionMatrix = A
+        self.emissionDistributions = [GaussianDistribution(1, mean=float(m), variance=float(s)) for m, s in zip(mean, sd)]
+        self.sanity_check()
+        return loglik
+
+    def train_batch(self, observations, lengths=None, iterations=10, dtype="float32", chunk=None, group=None,
+                    tol=None, sd_min=1e-6):
+        """`iterations` EM passes; returns the per-pass log-likelihoods (non-decreasing up to rounding)."""
+        history = []
+        for _ in range(iterations):
+            history.append(self.do_pass_batch(observations, lengths, dtype, chunk, group, sd_min))
+            if tol is not None and len(history) > 1 and history[-1] - history[-2] <= tol:
+                break
+        return history

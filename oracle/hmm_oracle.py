@@ -378,3 +378,44 @@ def simulate_from_uniforms(pi, A, U, Bm=None, mean=None, sd=None):
                 z = np.sqrt(-2.0 * np.log(1.0 - U[b, t, 1])) * np.cos(2.0 * np.pi * U[b, t, 2])
                 out[b, t] = mean[cur] + sd[cur] * z
     return states, out
+
+
+# ------------------------------------------------------ Gaussian Baum-Welch (EXTENSION, no reference)
+def batch_stats_gauss(pi, A, mean, sd, obs_batch, lengths=None):
+    """Textbook-EM statistics for 1-D Gaussian emissions on the reference's scaled recursions.  EXTENSION:
+    `GaussianHMM.do_pass` (gaussian_hmm.py:29-124) raises at HEAD, so nothing here is pinned by
+    the reference beyond `forward`/`backward`/`smooth_probabilities`, which are.  gamma = alpha*beta;
+    xi_t = alpha_t(i) A_ij b_j(x_{t+1}) beta_{t+1}(j) / c_{t+1}; pi part = smooth1d(gamma_0) per sequence."""
+    N = A.shape[0]
+    acc = dict(pi=np.zeros(N), xi=np.zeros((N, N)), gam=np.zeros(N), s0=np.zeros(N), s1=np.zeros(N), s2=np.zeros(N),
+               loglik=0.0, nseq=0.0)
+    obs_batch = np.asarray(obs_batch, dtype=np.float64)
+    for b in range(obs_batch.shape[0]):
+        x = obs_batch[b] if lengths is None else obs_batch[b, :lengths[b]]
+        E = emissions_gaussian_1d(mean, sd, x)
+        alpha, c = forward(pi, A, E)
+        beta = backward(A, E, c)
+        g = alpha * beta
+        acc["pi"] += smooth_probabilities(g[0].copy())
+        acc["xi"] += A * (alpha[:-1].T @ (E[1:] * beta[1:] / c[1:, None]))
+        acc["gam"] += g[:-1].sum(axis=0)
+        acc["s0"] += g.sum(axis=0)
+        acc["s1"] += g.T @ x
+        acc["s2"] += g.T @ (x * x)
+        acc["loglik"] += loglik(c)
+        acc["nseq"] += 1.0
+    return acc
+
+
+def mstep_gauss(stats, sd_min=1e-6):
+    """pi = mean of the per-sequence smooth1d(gamma_0); A = smooth1d of every row of rownorm(xi / gam)
+    (util.py:56-60); mean = S1/S0; sd = sqrt(max(S2/S0 - mean^2, sd_min^2))."""
+    pi_new = stats["pi"] / stats["nseq"]
+    A_new = stats["xi"] / stats["gam"][:, None]
+    A_new /= A_new.sum(axis=1, keepdims=True)
+    for i in range(A_new.shape[0]):          # the 1-D rule per row: the 2-D rule raises for >= 2 tiny entries
+        A_new[i] /= A_new[i].sum()
+        smooth_probabilities(A_new[i])
+    mean = stats["s1"] / stats["s0"]
+    sd = np.sqrt(np.maximum(stats["s2"] / stats["s0"] - mean * mean, sd_min * sd_min))
+    return pi_new, A_new, mean, sd
