@@ -411,6 +411,13 @@ def run_ours(args):
             "roofline": roof,
             "clocks": clocks,
         }
+        if kind == "c3":
+            # 2 FP64-pipe instructions (DADD + DSETP) per transition; measured DADD rate 18.4e12/s (profiles/r1_microbench_pipes.json)
+            out["roofline"]["fp64_pipe"] = {"achieved_transitions_per_s": transitions / world / (ms_per_step * 1e-3),
+                                            "pipe_bound_transitions_per_s": 18.4e12 / 2,
+                                            "frac": transitions / world / (ms_per_step * 1e-3) / (18.4e12 / 2),
+                                            "note": "bit-exact float64 max-plus: FP64/ALU-issue bound, not HBM bound; "
+                                                    "the backpointer stream is 0.8 % of HBM (DESIGN.md 3.2)"}
         if kind in ("c2",):
             flops = transitions / world * 4.0          # 2 (forward) + 2 (backward) flop per transition
             out["roofline"]["fp32_simt"] = {"achieved_tflops": flops / (ms_per_step * 1e-3) / 1e12,

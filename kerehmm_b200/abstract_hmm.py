@@ -343,9 +343,14 @@ class AbstractHMM(object):
         float32, N <= 16: the fused forward+backward register kernel.  float32, N a multiple of 128
         (<= 1024), equal lengths and `tensor_cores=True`: the tcgen05 (tf32) recursion, forward and
         backward together.  Otherwise the generic forward kernel (second value None)."""
-        ob = self._prep(observations, lengths)
         real, p = self._real(dtype), self._params()
         t = engine.torch()
+        if (real == t.float32 and lengths is None and p.N <= _lib.SMALL_N_MAX and p.kind in ("discrete", "gauss")):
+            # large host batch: copies of later row blocks overlap the kernel on earlier ones
+            out = engine.fwdbwd_loglik_small_host(p, observations, both=backward_check)
+            if out is not None:
+                return out
+        ob = self._prep(observations, lengths)
         if real == t.float32 and p.N <= _lib.SMALL_N_MAX and p.kind in ("discrete", "gauss"):
             ll, llb = engine.fwdbwd_loglik_small(p, ob, both=backward_check)
             return engine.finish(ob, ll, llb)

@@ -274,6 +274,67 @@ def fwdbwd_loglik_small(p: ModelParams, ob: Obs, both=True):
     return ll, llb
 
 
+def fwdbwd_loglik_small_host(p: ModelParams, obs, both=True, nchunks=4, min_bytes=16 << 20):
+    """Host-buffer variant of `fwdbwd_loglik_small`: the batch is cut into `nchunks` row blocks whose
+    host->device copies run on a side stream while the kernel works on the previous block, so the call
+    costs about max(copy, compute) instead of their sum.  Returns None when the input is not a large,
+    equal-length host batch (the caller then takes the plain path).  -> (loglik, loglik_bwd|None) NumPy."""
+    t = require_cuda()
+    if isinstance(obs, t.Tensor):
+        x = obs
+    else:
+        a = np.asarray(obs)
+        if a.dtype == np.uint16 or a.dtype.kind not in "iuf" or a.dtype == np.int8:
+            return None
+        x = t.from_numpy(np.ascontiguousarray(a))
+    symbols = p.kind == "discrete"
+    if x.is_cuda or x.dim() != 2 or x.numel() * x.element_size() < min_bytes or p.N > _lib.SMALL_N_MAX:
+        return None
+    if symbols:
+        name = str(x.dtype).replace("torch.", "")
+        if name not in ("uint8", "int32", "int64"):
+            return None
+        code = _INT_CODES[name]
+    else:
+        if x.dtype not in (t.float32, t.float64):
+            return None
+        code = _lib.F32 if x.dtype == t.float32 else _lib.F64
+    x = x.contiguous()
+    B, T = int(x.shape[0]), int(x.shape[1])
+    dev = device()
+    main = t.cuda.current_stream()
+    side = t.cuda.Stream(device=dev)
+    xd = t.empty((B, T), dtype=x.dtype, device=dev)
+    ll = t.empty((B,), dtype=t.float64, device=dev)
+    llb = t.empty((B,), dtype=t.float64, device=dev) if both else None
+    dm = DeviceModel(p, t.float32)
+    bounds = [(B * k) // nchunks for k in range(nchunks + 1)]
+    side.wait_stream(main)
+    events = []
+    with t.cuda.stream(side):
+        for k in range(nchunks):
+            b0, b1 = bounds[k], bounds[k + 1]
+            if b1 > b0:
+                xd[b0:b1].copy_(x[b0:b1], non_blocking=True)
+            ev = t.cuda.Event()
+            ev.record(side)
+            events.append(ev)
+    for k in range(nchunks):
+        b0, b1 = bounds[k], bounds[k + 1]
+        if b1 <= b0:
+            continue
+        main.wait_event(events[k])
+        lk, lbk = ll[b0:b1], (llb[b0:b1] if both else None)
+        if p.kind == "gauss":
+            _lib.call("khmm_fwdbwd_loglik_gauss_f32", b1 - b0, T, p.N, ptr(dm.pi), ptr(dm.A), ptr(dm.mean), ptr(dm.sd),
+                      ptr(xd[b0:b1]), code, None, ptr(lk), ptr(lbk), main.cuda_stream)
+        else:
+            _lib.call("khmm_fwdbwd_loglik_discrete_f32", b1 - b0, T, p.N, p.M, ptr(dm.pi), ptr(dm.A), ptr(dm.Bsm),
+                      ptr(xd[b0:b1]), code, None, ptr(lk), ptr(lbk), main.cuda_stream)
+    xd.record_stream(main)
+    return ll.cpu().numpy(), (llb.cpu().numpy() if both else None)
+
+
 def tc_supported(p: ModelParams, ob: Obs) -> bool:
     """The tcgen05 recursion covers N = 128, 256, ..., 1024 with equal-length sequences."""
     return (p.kind in ("discrete", "gauss") and p.N >= 128 and p.N % 128 == 0 and p.N <= 1024

@@ -536,3 +536,20 @@ def test_fwdbwd_config2_shape_properties(K):
     gam, ll3 = h.posterior_batch(obs[:64])
     np.testing.assert_allclose(gam.sum(axis=2), 1.0, rtol=1e-4)
     np.testing.assert_allclose(ll3, ll[:64], rtol=F32_RTOL)
+
+
+def test_loglik_host_batch_pipelined_path_matches_device_path(K):
+    """A large host batch takes the copy/compute-overlapped path (row blocks on a side stream); its results
+    equal the device-resident path bit for bit (same kernel, same rows)."""
+    import torch
+    np.random.seed(91)
+    pi, A, mean, sd = O.random_gaussian_model(8)
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(92)
+    x = (mean[rng.integers(0, 8, size=(5000, 1024))] + rng.standard_normal((5000, 1024))).astype(np.float32)
+    ll_h, llb_h = h.log_likelihood_batch(x)                                   # 20 MB host array -> pipelined
+    ll_d, llb_d = h.log_likelihood_batch(torch.from_numpy(x).cuda())          # device tensor -> plain
+    assert isinstance(ll_h, np.ndarray) and ll_h.shape == (5000,)
+    assert np.array_equal(ll_h, ll_d.cpu().numpy()) and np.array_equal(llb_h, llb_d.cpu().numpy())
+    ll_p, _ = h.log_likelihood_batch(torch.from_numpy(x).pin_memory(), backward_check=False)
+    assert np.array_equal(ll_p, ll_h)
