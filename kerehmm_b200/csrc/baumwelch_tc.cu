@@ -323,11 +323,13 @@ struct __align__(8) BwdBars {
     uint32_t tmem_base;
 };
 #ifndef KHMM_RED_DEFER
-#define KHMM_RED_DEFER 1
+#define KHMM_RED_DEFER 0
 #endif
 #ifndef KHMM_RED_PACE_NS
-#define KHMM_RED_PACE_NS 0
+#define KHMM_RED_PACE_NS 40
 #endif
+// measured at c4 size (backward kernel): no pacing 19.2-19.6 ms, 40-60 ns per reduction 16.3-16.8 ms, 80-120 ns 18.4 ms,
+// 200 ns 32 ms (the reduction warps become the critical path); deferring the burst behind v_ready: no gain
 constexpr bool RED_DEFER = KHMM_RED_DEFER;
 constexpr int RED_PACE_NS = KHMM_RED_PACE_NS;
 constexpr int BW_ECHUNK = 128 * 128;   // emission rows of one 32-column chunk: [128 rows][128 B], 16-byte pieces XOR (row & 7)
@@ -701,13 +703,14 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
 #pragma unroll
-                            for (int n = 0; n < 4; n += 2)
+                            for (int n = 0; n < 4; n += 2) {
                                 red_add_v4(dst + c * 32 + 8 * n, __uint_as_float(r[c][4 * n + 2 * e]),
                                            __uint_as_float(r[c][4 * n + 2 * e + 1]), __uint_as_float(r[c][4 * n + 4 + 2 * e]),
                                            __uint_as_float(r[c][4 * n + 4 + 2 * e + 1]));
-                            // pace the reductions: a burst fills the LSU queue and blocks the epilogue's shared-memory
-                            // traffic and the MMA operand fetches behind ~16 cycles of L2 reduction work per instruction
-                            if (RED_PACE_NS) asm volatile("nanosleep.u32 %0;" ::"n"(RED_PACE_NS));
+                                // optional pacing: a burst of reductions fills the LSU queue and delays the epilogue's
+                                // shared-memory traffic and the MMA operand fetches behind it
+                                if (RED_PACE_NS) asm volatile("nanosleep.u32 %0;" ::"n"(RED_PACE_NS));
+                            }
                         }
                         if (t == 0 || t == T - 1) {
 #pragma unroll 1
