@@ -324,7 +324,7 @@ def run_ours(args):
         launches_per_step = (T - 1) + 2
         algo_bytes = None
         h2d, d2h = B * T * 4, 2 * B * 8
-        dominant = "tc_step_kernel (tcgen05 kind::tf32)"
+        dominant = "tc_step_persist_kernel (tcgen05 kind::tf32, double-buffered TMEM)"
         l2_note = "W ping-pong rows 2 x 2 x 16.8 MB + A/AT 8.4 MB stay L2 resident by design"
         dtype = "tf32 multiply / f32 accumulate"
 

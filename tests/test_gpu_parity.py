@@ -553,3 +553,20 @@ def test_loglik_host_batch_pipelined_path_matches_device_path(K):
     assert np.array_equal(ll_h, ll_d.cpu().numpy()) and np.array_equal(llb_h, llb_d.cpu().numpy())
     ll_p, _ = h.log_likelihood_batch(torch.from_numpy(x).pin_memory(), backward_check=False)
     assert np.array_equal(ll_p, ll_h)
+
+
+def test_tensor_core_loglik_persistent_tiles(K):
+    """N = 512 with more (row tile, column tile, direction) jobs than SMs: the persistent per-step kernel
+    (double-buffered TMEM accumulators, several jobs per CTA) against the float64 oracle."""
+    import torch
+    N, B, T = 512, 38 * 128, 6
+    np.random.seed(95)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(96)
+    x = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T))).astype(np.float32)
+    ll, llb = h.log_likelihood_batch(torch.from_numpy(x).cuda())
+    ref = O.fwdbwd_loglik_batch(pi, A, O.emissions_gaussian_1d(mean, sd, x.astype(np.float64)))
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    np.testing.assert_allclose(ll.cpu().numpy(), ref, rtol=5e-5)
+    np.testing.assert_allclose(llb.cpu().numpy(), ref, rtol=5e-5)
