@@ -321,10 +321,10 @@ def run_ours(args):
         def e2e_step(i):
             return model.log_likelihood_batch(host_sets[0])[0]
 
-        launches_per_step = (T - 1) + 2
+        launches_per_step = 5      # 2 x tc_round_matrix, tc_init, tc_recursion (all T-1 steps), tc_final
         algo_bytes = None
         h2d, d2h = B * T * 4, 2 * B * 8
-        dominant = "tc_step_persist_kernel (tcgen05 kind::tf32, double-buffered TMEM)"
+        dominant = "tc_recursion_kernel (tcgen05 kind::tf32, one cooperative launch for all steps)"
         l2_note = "W ping-pong rows 2 x 2 x 16.8 MB + A/AT 8.4 MB stay L2 resident by design"
         dtype = "tf32 multiply / f32 accumulate"
 

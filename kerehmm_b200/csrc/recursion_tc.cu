@@ -29,6 +29,9 @@ using namespace tc;
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;   // TC_BN: psum / workspace granularity (column tile of 128)
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;       // one 128 x 32 fp32 operand tile
+#ifndef KHMM_TC_WHOLE
+#define KHMM_TC_WHOLE 1
+#endif
 #ifndef KHMM_TC_PERSIST
 #define KHMM_TC_PERSIST 1
 #endif
@@ -569,6 +572,199 @@ tc_step_persist_pair_kernel(const __grid_constant__ CUtensorMap mapXf, const __g
     tc_step_persist_body<GAUSS, true>(mapXf, mapXb, mapMf, mapMb, df, db, em, B, T, N, step, mtiles, ndir);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Whole-recursion kernel (N % 256 == 0): ONE cooperative launch runs every time step.  The work of a step is a
+// set of independent CHAINS -- (row tile of 128 sequences, direction) -- each made of N/256 column-tile jobs
+// that only depend on the same chain's jobs of the previous step.  Lanes (chain, column tile) are dealt to the
+// CTAs round-robin once; every CTA walks (step, its lanes) in order and waits for a job's inputs on a per-chain
+// completion counter in global memory (release by the producing epilogue, acquire by the consuming TMA
+// producer) instead of on a kernel boundary.  This removes what bounds the launch-per-step kernels (measured:
+// 37.8 ms at c5 for 17 us of MMA time per 37 us step): the per-step prologue, the exposed last epilogue, the
+// launch gap and the wave tail of 256 jobs on 148 SMs -- chains drift apart freely, so an SM never idles
+// at a step boundary.  Progress: a job only waits for jobs that precede it in every CTA's (step, lane) order, so
+// the globally smallest unfinished job can always run (all CTAs are co-resident: cooperative launch).
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_chain(const uint32_t *ctr, uint32_t need) {
+    for (uint32_t spin = 0; ld_acquire_u32(ctr) < need; ++spin) {
+        __nanosleep(64);
+        if (spin > (1u << 26)) __trap();      // a scheduling bug traps instead of hanging the GPU
+    }
+}
+
+template <bool GAUSS>
+__global__ void __launch_bounds__(192, 1)
+tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_constant__ CUtensorMap mapXf1,
+                    const __grid_constant__ CUtensorMap mapXb0, const __grid_constant__ CUtensorMap mapXb1,
+                    const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df, TcDir db,
+                    TcEmis em, int64_t B, int64_t T, int N, int mtiles, int ndir, uint32_t *done) {
+    constexpr int BN = 256;
+    constexpr int STAGE_BYTES = TC_TILE_BYTES + BN * TC_BK * 4;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    TcPBars<false> *bars = (TcPBars<false> *)(tiles + TC_STAGES * STAGE_BYTES);
+    float *sp = (float *)(bars + 1);  // [2 accumulators][3][256] emission constants of the job in that accumulator
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = N / TC_BK, NT = N / 128, ntile_n = N / BN;
+    const int nlanes = mtiles * ntile_n * ndir;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    // lane -> (row tile, column tile, direction); the row tile runs fastest so that neighbouring CTAs share a matrix tile
+    auto decode = [&](int ln, int &m0, int &n0, int &dir, int &chain) {
+        const int mt = ln % mtiles;
+        const int rest = ln / mtiles;
+        n0 = (rest % ntile_n) * BN;
+        dir = rest / ntile_n;
+        m0 = mt * TC_BM;
+        chain = dir * mtiles + mt;
+    };
+
+    if (warp == 4) {
+        if (elect_one()) {
+            tma_prefetch_desc(&mapXf0); tma_prefetch_desc(&mapXf1); tma_prefetch_desc(&mapMf);
+            if (ndir > 1) { tma_prefetch_desc(&mapXb0); tma_prefetch_desc(&mapXb1); tma_prefetch_desc(&mapMb); }
+            uint32_t it = 0;
+            for (int64_t step = 1; step < T; step++) {
+                const int src = (int)((step - 1) & 1);
+                for (int ln = blockIdx.x; ln < nlanes; ln += gridDim.x) {
+                    int m0, n0, dir, chain;
+                    decode(ln, m0, n0, dir, chain);
+                    // inputs: W_{step-1} of this chain = all its column-tile jobs of the previous step
+                    wait_chain(done + chain, (uint32_t)(ntile_n * (step - 1)));
+                    asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes -> TMA reads
+                    const CUtensorMap *mapX = dir ? (src ? &mapXb1 : &mapXb0) : (src ? &mapXf1 : &mapXf0);
+                    const CUtensorMap *mapM = dir ? &mapMb : &mapMf;
+                    for (int kb = 0; kb < nkb; kb++, it++) {
+                        int s = it % TC_STAGES;
+                        uint32_t ph = (it / TC_STAGES) & 1;
+                        mbar_wait(&bars->empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
+                        tma_load_2d(tiles + s * STAGE_BYTES, mapX, &bars->full[s], kb * TC_BK, m0);
+                        tma_load_2d(tiles + s * STAGE_BYTES + TC_TILE_BYTES, mapM, &bars->full[s], kb * TC_BK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+            uint32_t it = 0, nj = 0;
+            for (int64_t step = 1; step < T; step++)
+                for (int ln = blockIdx.x; ln < nlanes; ln += gridDim.x, nj++) {
+                    const int a = nj & 1;
+                    mbar_wait(&bars->tmem_empty[a], ((nj >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+                    tc_fence_after();
+                    for (int kb = 0; kb < nkb; kb++, it++) {
+                        int s = it % TC_STAGES;
+                        uint32_t ph = (it / TC_STAGES) & 1;
+                        mbar_wait(&bars->full[s], ph);
+                        tc_fence_after();
+                        uint64_t da = make_kmajor_sw128_desc(tiles + s * STAGE_BYTES);
+                        uint64_t dbb = make_kmajor_sw128_desc(tiles + s * STAGE_BYTES + TC_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; k++)
+                            mma_tf32_ss(tmem + a * BN, desc_advance(da, k * 32), desc_advance(dbb, k * 32), idesc, (kb | k) != 0);
+                        tc_commit(&bars->empty[s]);
+                    }
+                    tc_commit(&bars->tmem_full[a]);
+                }
+        }
+    } else {
+        uint32_t nj = 0;
+        for (int64_t step = 1; step < T; step++) {
+            const int src = (int)((step - 1) & 1), dst = (int)(step & 1);
+            for (int ln = blockIdx.x; ln < nlanes; ln += gridDim.x, nj++) {
+                const int a = nj & 1;
+                int m0, n0, dir, chain;
+                decode(ln, m0, n0, dir, chain);
+                const TcDir d = dir ? db : df;
+                float *spa = sp + a * 3 * BN;
+                if (GAUSS) {
+                    for (int c = threadIdx.x; c < BN; c += 128) {
+                        int j = n0 + c;
+                        float sd = em.p1[j];
+                        spa[c] = em.p0[j];
+                        spa[BN + c] = -0.5f * 1.4426950408889634f / (sd * sd);
+                        spa[2 * BN + c] = -log2f(sd * 2.5066282746310002f);
+                    }
+                }
+                // the previous step's row sums of this chain come from other CTAs: acquire them
+                wait_chain(done + chain, (uint32_t)(ntile_n * (step - 1)));
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int64_t b = m0 + warp * 32 + lane;
+                const bool live = b < B;
+                const int64_t t = dir ? (T - 1 - step) : step;
+                float r = 0.f, x = 0.f;
+                const float *brow = nullptr;
+                if (live) {
+                    const float *ps = d.psum + (b * 2 + src) * NT;
+                    float c = 0.f;
+                    for (int k = 0; k < NT; k++) c += __ldcg(ps + k);     // written by other SMs: bypass L1
+                    r = 1.0f / c;
+                    if (n0 == 0) d.logacc[b] += log((double)c);
+                    if (GAUSS) {
+                        x = load_real<float>(em.obs, em.obs_dtype, b * T + t);
+                    } else {
+                        int sym = load_symbol(em.obs, em.obs_dtype, b * T + t);
+                        sym = sym < 0 ? 0 : (sym >= em.M ? em.M - 1 : sym);
+                        brow = em.p0 + (int64_t)sym * N + n0;
+                    }
+                }
+                mbar_wait(&bars->tmem_full[a], (nj >> 1) & 1);
+                tc_fence_after();
+                float rowsum = 0.f;
+                float *out = d.W + (b * 2 + dst) * N + n0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    if (c0 == 128) {
+                        if (live) d.psum[(b * 2 + dst) * NT + (n0 >> 7)] = rowsum;
+                        rowsum = 0.f;
+                    }
+                    uint32_t acc[32];
+                    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + a * BN + c0, acc);
+                    tmem_ld_wait();
+                    if (live) {
+                        float v[32];
+#pragma unroll
+                        for (int q = 0; q < 32; q++) {
+                            v[q] = __uint_as_float(acc[q]) * r * tc_emission<GAUSS, BN>(em, spa, c0 + q, x, brow);
+                            rowsum += v[q];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            reinterpret_cast<float4 *>(out + c0)[q] = make_float4(round_tf32(v[4 * q]), round_tf32(v[4 * q + 1]),
+                                                                                  round_tf32(v[4 * q + 2]), round_tf32(v[4 * q + 3]));
+                    }
+                }
+                if (live) d.psum[(b * 2 + dst) * NT + (n0 >> 7) + 1] = rowsum;
+                // accumulator a may be overwritten
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->tmem_empty[a]);
+                // publish the job: every thread's W / row-sum / log-accumulator stores, then one release increment
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done + chain) : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
 // step 0: W_0 = start . b(o_first): start = pi (forward, t = 0) or ones (backward, t = T-1)
 template <bool GAUSS>
 __global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__restrict__ pi, int64_t B, int64_t T, int N) {
@@ -633,7 +829,8 @@ static size_t tc_workspace_floats(int64_t B, int N) {
     int NT = N / TC_BN;
     int64_t Bp = (B + TC_BM - 1) / TC_BM * TC_BM;
     // per direction: W [Bp][2][N], psum [Bp][2][NT], logacc [Bp] doubles (2 floats each)
-    return (size_t)2 * ((size_t)Bp * 2 * N + (size_t)Bp * 2 * NT + (size_t)Bp * 2) + (size_t)2 * N * N + 64;
+    // + per-chain completion counters of the whole-recursion kernel (2 directions x row tiles)
+    return (size_t)2 * ((size_t)Bp * 2 * N + (size_t)Bp * 2 * NT + (size_t)Bp * 2) + (size_t)2 * N * N + 2 * (size_t)(Bp / TC_BM) + 64;
 }
 
 template <bool GAUSS>
@@ -659,6 +856,7 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
     }
     float *Ar = p;  p += (size_t)N * N;     // tf32-rounded copies of A and AT
     float *ATr = p; p += (size_t)N * N;
+    uint32_t *done = (uint32_t *)p; p += 2 * (size_t)(Bp / TC_BM);
     tc_round_matrix_kernel<<<64, 256, 0, st>>>(A, Ar, N * N);
     tc_round_matrix_kernel<<<64, 256, 0, st>>>(AT, ATr, N * N);
     const int ndir = loglik_bwd ? 2 : 1;
@@ -702,7 +900,27 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
         return KHMM_ERR_CUDA;
     }
     const bool pair = KHMM_TC_PAIR && BN == 256 && ((Bp / TC_BM) % 2 == 0);
-    if (KHMM_TC_PERSIST && BN == 256) {
+    int coop = 0;
+    if (KHMM_TC_WHOLE && BN == 256) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    }
+    if (coop) {
+        // one cooperative launch for all T-1 steps
+        const int mtiles = (int)(Bp / TC_BM);
+        const int nlanes = mtiles * (N / 256) * ndir;
+        int grid = nlanes < sm_count() ? nlanes : sm_count();
+        size_t smem = TC_STAGES * (size_t)(TC_TILE_BYTES + 256 * TC_BK * 4) + sizeof(TcPBars<false>) + 2 * 3 * 256 * sizeof(float) + 1024;
+        auto kern = tc_recursion_kernel<GAUSS>;
+        KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KHMM_CUDA_CHECK(cudaMemsetAsync(done, 0, 2 * (size_t)mtiles * sizeof(uint32_t), st));
+        int Ni = N, mt = mtiles, nd = ndir;
+        int64_t Bv = B, Tv = T;
+        void *args[] = {&mapX[0][0], &mapX[0][1], &mapX[1][0], &mapX[1][1], &mapM[0], &mapM[1], &d[0], &d[1], &em,
+                        &Bv, &Tv, &Ni, &mt, &nd, &done};
+        KHMM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(192), args, smem, st));
+    } else if (KHMM_TC_PERSIST && BN == 256) {
         const int mtiles = (int)(Bp / TC_BM);
         const bool ppair = KHMM_TC_PERSIST_PAIR && (mtiles % 2 == 0);
         CUtensorMap mapH[2];
