@@ -195,15 +195,19 @@ int khmm_fwdbwd_loglik_discrete_f32(int64_t B, int64_t T, int N, int M,
  * 256-byte aligned.  loglik_bwd may be NULL (forward only).  tf32 multiplies: log-likelihoods
  * agree with the float64 reference to ~1e-6 relative (stated bound 2e-5 in the tests).
  */
+/* operand_precision */
+#define KHMM_TC_TF32 0 /* tf32 operands (10-bit mantissa), fp32 accumulation */
+#define KHMM_TC_BF16 1 /* bf16 operands (8-bit mantissa), fp32 accumulation: twice the MMA rate; needs N % 256 == 0 and
+                          >= one (128 sequences x 256 states x direction) job per SM, else KHMM_ERR_UNSUPPORTED */
 size_t khmm_fwdbwd_loglik_tc_workspace_bytes(int64_t B, int N);
 int khmm_fwdbwd_loglik_tc_gauss_f32(int64_t B, int64_t T, int N, const float *pi, const float *A, const float *AT,
                                     const float *mean, const float *sd, const void *obs, int obs_dtype,
                                     void *workspace, size_t workspace_bytes, double *loglik, double *loglik_bwd,
-                                    khmm_stream_t stream);
+                                    int operand_precision, khmm_stream_t stream);
 int khmm_fwdbwd_loglik_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A,
                                        const float *AT, const float *Bsm, const void *obs, int obs_dtype,
                                        void *workspace, size_t workspace_bytes, double *loglik, double *loglik_bwd,
-                                       khmm_stream_t stream);
+                                       int operand_precision, khmm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Baum-Welch E-step -- the statistics DiscreteHMM.do_pass forms (discrete_hmm.py:117-159)

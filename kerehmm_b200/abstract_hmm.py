@@ -342,7 +342,8 @@ class AbstractHMM(object):
         """log P(O_b | model) for every sequence -> `(loglik, loglik_from_backward | None)`.
         float32, N <= 16: the fused forward+backward register kernel.  float32, N a multiple of 128
         (<= 1024), equal lengths and `tensor_cores=True`: the tcgen05 (tf32) recursion, forward and
-        backward together.  Otherwise the generic forward kernel (second value None)."""
+        backward together; `tensor_cores="bf16"` uses bf16 operands (twice the MMA rate; N % 256 == 0 and
+        large batches, else tf32).  Otherwise the generic forward kernel (second value None)."""
         real, p = self._real(dtype), self._params()
         t = engine.torch()
         if (real == t.float32 and lengths is None and p.N <= _lib.SMALL_N_MAX and p.kind in ("discrete", "gauss")):
@@ -355,7 +356,8 @@ class AbstractHMM(object):
             ll, llb = engine.fwdbwd_loglik_small(p, ob, both=backward_check)
             return engine.finish(ob, ll, llb)
         if real == t.float32 and tensor_cores and engine.tc_supported(p, ob):
-            ll, llb = engine.fwdbwd_loglik_tc(p, ob, both=backward_check)
+            prec = engine.TC_BF16 if tensor_cores == "bf16" else engine.TC_TF32
+            ll, llb = engine.fwdbwd_loglik_tc(p, ob, both=backward_check, precision=prec)
             return engine.finish(ob, ll, llb)
         _, _, ll = engine.forward(p, ob, real, want_alpha=False, want_scale=False)
         return engine.finish(ob, ll, None)

@@ -21,6 +21,8 @@
 // ~1e-6 relative (tests/test_gpu_parity.py states the bound); alpha itself is only good to ~1e-3,
 // which is why the float32 SIMT kernels remain the parity path for alpha/beta outputs.
 #include "common.cuh"
+#include <cuda_bf16.h>
+
 #include "tcgen05.cuh"
 
 namespace khmm {
@@ -68,6 +70,10 @@ __device__ __forceinline__ float round_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
+}
+
+__global__ void tc_to_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, int n) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) out[k] = __float2bfloat16_rn(in[k]);
 }
 
 __global__ void tc_round_matrix_kernel(const float *__restrict__ in, float *__restrict__ out, int n) {
@@ -583,6 +589,11 @@ tc_step_persist_pair_kernel(const __grid_constant__ CUtensorMap mapXf, const __g
 // launch gap and the wave tail of 256 jobs on 148 SMs -- chains drift apart freely, so an SM never idles
 // at a step boundary.  Progress: a job only waits for jobs that precede it in every CTA's (step, lane) order, so
 // the globally smallest unfinished job can always run (all CTAs are co-resident: cooperative launch).
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {   // round to nearest even, lo in the low half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -595,7 +606,10 @@ __device__ __forceinline__ void wait_chain(const uint32_t *ctr, uint32_t need) {
     }
 }
 
-template <bool GAUSS>
+// BF16 = true: bf16 operands (tcgen05 kind::f16, fp32 accumulation): a k-block of 128-byte rows then holds 64
+// elements instead of 32, i.e. twice the K per byte staged and twice the MMA rate.  Measured on the c5 shape the
+// log-likelihood moves by < 2e-6 relative (the rounding errors of 1,024 states average out).
+template <bool GAUSS, bool BF16>
 __global__ void __launch_bounds__(192, 1)
 tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_constant__ CUtensorMap mapXf1,
                     const __grid_constant__ CUtensorMap mapXb0, const __grid_constant__ CUtensorMap mapXb1,
@@ -608,7 +622,8 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
     TcPBars<false> *bars = (TcPBars<false> *)(tiles + TC_STAGES * STAGE_BYTES);
     float *sp = (float *)(bars + 1);  // [2 accumulators][3][256] emission constants of the job in that accumulator
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = N / TC_BK, NT = N / 128, ntile_n = N / BN;
+    constexpr int BKE = BF16 ? 64 : TC_BK;       // elements per 128-byte k-block row
+    const int nkb = N / BKE, NT = N / 128, ntile_n = N / BN;
     const int nlanes = mtiles * ntile_n * ndir;
 
     if (threadIdx.x == 0) {
@@ -651,15 +666,15 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
                         uint32_t ph = (it / TC_STAGES) & 1;
                         mbar_wait(&bars->empty[s], ph ^ 1);
                         mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
-                        tma_load_2d(tiles + s * STAGE_BYTES, mapX, &bars->full[s], kb * TC_BK, m0);
-                        tma_load_2d(tiles + s * STAGE_BYTES + TC_TILE_BYTES, mapM, &bars->full[s], kb * TC_BK, n0);
+                        tma_load_2d(tiles + s * STAGE_BYTES, mapX, &bars->full[s], kb * BKE, m0);
+                        tma_load_2d(tiles + s * STAGE_BYTES + TC_TILE_BYTES, mapM, &bars->full[s], kb * BKE, n0);
                     }
                 }
             }
         }
     } else if (warp == 5) {
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+            const uint32_t idesc = BF16 ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN);
             uint32_t it = 0, nj = 0;
             for (int64_t step = 1; step < T; step++)
                 for (int ln = blockIdx.x; ln < nlanes; ln += gridDim.x, nj++) {
@@ -674,8 +689,10 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
                         uint64_t da = make_kmajor_sw128_desc(tiles + s * STAGE_BYTES);
                         uint64_t dbb = make_kmajor_sw128_desc(tiles + s * STAGE_BYTES + TC_TILE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 8; k++)
-                            mma_tf32_ss(tmem + a * BN, desc_advance(da, k * 32), desc_advance(dbb, k * 32), idesc, (kb | k) != 0);
+                        for (int k = 0; k < 4; k++) {      // 32 bytes of K per MMA: 8 tf32 or 16 bf16 elements
+                            if (BF16) mma_bf16_ss(tmem + a * BN, desc_advance(da, k * 32), desc_advance(dbb, k * 32), idesc, (kb | k) != 0);
+                            else mma_tf32_ss(tmem + a * BN, desc_advance(da, k * 32), desc_advance(dbb, k * 32), idesc, (kb | k) != 0);
+                        }
                         tc_commit(&bars->empty[s]);
                     }
                     tc_commit(&bars->tmem_full[a]);
@@ -726,6 +743,7 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
                 tc_fence_after();
                 float rowsum = 0.f;
                 float *out = d.W + (b * 2 + dst) * N + n0;
+                uint32_t *outh = reinterpret_cast<uint32_t *>(d.W) + (((b * 2 + dst) * N + n0) >> 1);   // bf16 pairs
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     if (c0 == 128) {
@@ -742,10 +760,18 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
                             v[q] = __uint_as_float(acc[q]) * r * tc_emission<GAUSS, BN>(em, spa, c0 + q, x, brow);
                             rowsum += v[q];
                         }
+                        if (BF16) {
 #pragma unroll
-                        for (int q = 0; q < 8; q++)
-                            reinterpret_cast<float4 *>(out + c0)[q] = make_float4(round_tf32(v[4 * q]), round_tf32(v[4 * q + 1]),
-                                                                                  round_tf32(v[4 * q + 2]), round_tf32(v[4 * q + 3]));
+                            for (int q = 0; q < 4; q++)
+                                reinterpret_cast<uint4 *>(outh + (c0 >> 1))[q] =
+                                    make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                               pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; q++)
+                                reinterpret_cast<float4 *>(out + c0)[q] = make_float4(round_tf32(v[4 * q]), round_tf32(v[4 * q + 1]),
+                                                                                      round_tf32(v[4 * q + 2]), round_tf32(v[4 * q + 3]));
+                        }
                     }
                 }
                 if (live) d.psum[(b * 2 + dst) * NT + (n0 >> 7) + 1] = rowsum;
@@ -766,7 +792,7 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
 }
 
 // step 0: W_0 = start . b(o_first): start = pi (forward, t = 0) or ones (backward, t = T-1)
-template <bool GAUSS>
+template <bool GAUSS, bool BF16 = false>
 __global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__restrict__ pi, int64_t B, int64_t T, int N) {
     const int dir = blockIdx.y;
     const TcDir d = dir ? db : df;
@@ -793,7 +819,8 @@ __global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__res
             e = brow[j];
         }
         float v = (dir ? 1.f : pi[j]) * e;
-        d.W[(b * 2 + 0) * N + j] = round_tf32(v);
+        if (BF16) reinterpret_cast<__nv_bfloat16 *>(d.W)[(b * 2 + 0) * N + j] = __float2bfloat16_rn(v);
+        else d.W[(b * 2 + 0) * N + j] = round_tf32(v);
         float s = warp_sum(v);
         __syncthreads();
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -804,6 +831,7 @@ __global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__res
 }
 
 // closing: forward log P = logacc + log c_{T-1}; backward log P = logacc + log(pi . w_0)
+template <bool BF16 = false>
 __global__ void tc_final_kernel(TcDir df, TcDir db, const float *__restrict__ pi, int64_t B, int64_t T, int N,
                                 double *__restrict__ loglik, double *__restrict__ loglik_bwd) {
     const int dir = blockIdx.y;
@@ -811,8 +839,12 @@ __global__ void tc_final_kernel(TcDir df, TcDir db, const float *__restrict__ pi
     const int64_t b = blockIdx.x;
     const int slot = (int)((T - 1) & 1);
     const float *w = d.W + (b * 2 + slot) * N;
+    const __nv_bfloat16 *wh = reinterpret_cast<const __nv_bfloat16 *>(d.W) + (b * 2 + slot) * N;
     float s = 0.f;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) s += dir ? w[j] * pi[j] : w[j];
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const float wj = BF16 ? __bfloat162float(wh[j]) : w[j];
+        s += dir ? wj * pi[j] : wj;
+    }
     __shared__ float red[32];
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -835,7 +867,9 @@ static size_t tc_workspace_floats(int64_t B, int N) {
 
 template <bool GAUSS>
 static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, const float *AT, TcEmis em, void *ws,
-                  size_t ws_bytes, double *loglik, double *loglik_bwd, cudaStream_t st) {
+                  size_t ws_bytes, double *loglik, double *loglik_bwd, int precision, cudaStream_t st) {
+    KHMM_REQUIRE(precision == KHMM_TC_TF32 || precision == KHMM_TC_BF16, "fwdbwd_loglik_tc: unknown operand precision %d", precision);
+    const bool bf16 = precision == KHMM_TC_BF16;
     KHMM_REQUIRE(B >= 0 && T >= 1, "fwdbwd_loglik_tc: bad shape");
     if (N < TC_BN || N % TC_BN != 0 || N > 1024) {
         set_error("fwdbwd_loglik_tc: N=%d must be a multiple of %d in [%d, 1024]", N, TC_BN, TC_BN);
@@ -857,10 +891,23 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
     float *Ar = p;  p += (size_t)N * N;     // tf32-rounded copies of A and AT
     float *ATr = p; p += (size_t)N * N;
     uint32_t *done = (uint32_t *)p; p += 2 * (size_t)(Bp / TC_BM);
-    tc_round_matrix_kernel<<<64, 256, 0, st>>>(A, Ar, N * N);
-    tc_round_matrix_kernel<<<64, 256, 0, st>>>(AT, ATr, N * N);
     const int ndir = loglik_bwd ? 2 : 1;
-    tc_init_kernel<GAUSS><<<dim3((unsigned)B, ndir), 128, 0, st>>>(d[0], d[1], em, pi, B, T, N);
+    if (bf16) {
+        int dev = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (!(N % 256 == 0 && coop && (Bp / TC_BM) * (N / 256) * ndir >= sm_count())) {
+            set_error("fwdbwd_loglik_tc: bf16 operands need N %% 256 == 0 and at least one job per SM");
+            return KHMM_ERR_UNSUPPORTED;
+        }
+        tc_to_bf16_kernel<<<64, 256, 0, st>>>(A, (__nv_bfloat16 *)Ar, N * N);
+        tc_to_bf16_kernel<<<64, 256, 0, st>>>(AT, (__nv_bfloat16 *)ATr, N * N);
+        tc_init_kernel<GAUSS, true><<<dim3((unsigned)B, ndir), 128, 0, st>>>(d[0], d[1], em, pi, B, T, N);
+    } else {
+        tc_round_matrix_kernel<<<64, 256, 0, st>>>(A, Ar, N * N);
+        tc_round_matrix_kernel<<<64, 256, 0, st>>>(AT, ATr, N * N);
+        tc_init_kernel<GAUSS, false><<<dim3((unsigned)B, ndir), 128, 0, st>>>(d[0], d[1], em, pi, B, T, N);
+    }
     KHMM_LAUNCH_CHECK("tc_init_kernel");
     // tensor maps: the W buffer [Bp][2][N] is addressed as a 2-D matrix whose row b is (b, slot):
     // base = W + slot*N, row stride = 2*N floats -> one map per (direction, slot)
@@ -878,11 +925,13 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
                 }
                 encode = (PFN_encodeTiled)fn;
             }
+            const size_t esz = bf16 ? 2 : 4;
             cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)Bp};
-            cuuint64_t strides[1] = {(cuuint64_t)2 * N * sizeof(float)};
-            cuuint32_t box[2] = {TC_BK, TC_BM};
+            cuuint64_t strides[1] = {(cuuint64_t)2 * N * esz};
+            cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 64 : TC_BK), TC_BM};
             cuuint32_t estr[2] = {1, 1};
-            CUresult r = encode(&mapX[k][slot], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)(d[k].W + (size_t)slot * N),
+            CUresult r = encode(&mapX[k][slot], bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                                (void *)((char *)d[k].W + (size_t)slot * N * esz),
                                 dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
@@ -895,13 +944,14 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
     const int BN = (N % 256 == 0 && (Bp / TC_BM) * (N / 256) * ndir >= sm_count()) ? 256 : 128;
     // forward: out[j] = sum_i W[i] A[i][j]  -> B-operand rows j, K index i: AT[j][i]
     // backward: out[i] = sum_j A[i][j] w[j] -> B-operand rows i, K index j: A[i][j]
-    if (make_tmap_f32_rowmajor(&mapM[0], ATr, N, N, BN) || make_tmap_f32_rowmajor(&mapM[1], Ar, N, N, BN)) {
+    if (bf16 ? (make_tmap_bf16_rowmajor(&mapM[0], ATr, N, N, BN) || make_tmap_bf16_rowmajor(&mapM[1], Ar, N, N, BN))
+             : (make_tmap_f32_rowmajor(&mapM[0], ATr, N, N, BN) || make_tmap_f32_rowmajor(&mapM[1], Ar, N, N, BN))) {
         set_error("tensor map creation for the transition matrix failed");
         return KHMM_ERR_CUDA;
     }
     const bool pair = KHMM_TC_PAIR && BN == 256 && ((Bp / TC_BM) % 2 == 0);
     int coop = 0;
-    if (KHMM_TC_WHOLE && BN == 256) {
+    if ((KHMM_TC_WHOLE || bf16) && BN == 256) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
@@ -912,7 +962,7 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
         const int nlanes = mtiles * (N / 256) * ndir;
         int grid = nlanes < sm_count() ? nlanes : sm_count();
         size_t smem = TC_STAGES * (size_t)(TC_TILE_BYTES + 256 * TC_BK * 4) + sizeof(TcPBars<false>) + 2 * 3 * 256 * sizeof(float) + 1024;
-        auto kern = tc_recursion_kernel<GAUSS>;
+        auto kern = bf16 ? tc_recursion_kernel<GAUSS, true> : tc_recursion_kernel<GAUSS, false>;
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KHMM_CUDA_CHECK(cudaMemsetAsync(done, 0, 2 * (size_t)mtiles * sizeof(uint32_t), st));
         int Ni = N, mt = mtiles, nd = ndir;
@@ -975,7 +1025,8 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
     }
     KHMM_LAUNCH_CHECK("tc_step_kernel");
     }
-    tc_final_kernel<<<dim3((unsigned)B, ndir), 256, 0, st>>>(d[0], d[1], pi, B, T, N, loglik, loglik_bwd);
+    if (bf16) tc_final_kernel<true><<<dim3((unsigned)B, ndir), 256, 0, st>>>(d[0], d[1], pi, B, T, N, loglik, loglik_bwd);
+    else tc_final_kernel<false><<<dim3((unsigned)B, ndir), 256, 0, st>>>(d[0], d[1], pi, B, T, N, loglik, loglik_bwd);
     KHMM_LAUNCH_CHECK("tc_final_kernel");
     return KHMM_OK;
 }
@@ -993,22 +1044,25 @@ size_t khmm_fwdbwd_loglik_tc_workspace_bytes(int64_t B, int N) {
 
 int khmm_fwdbwd_loglik_tc_gauss_f32(int64_t B, int64_t T, int N, const float *pi, const float *A, const float *AT,
                                     const float *mean, const float *sd, const void *obs, int obs_dtype, void *workspace,
-                                    size_t workspace_bytes, double *loglik, double *loglik_bwd, khmm_stream_t stream) {
+                                    size_t workspace_bytes, double *loglik, double *loglik_bwd, int operand_precision,
+                                    khmm_stream_t stream) {
     KHMM_REQUIRE(B == 0 || (mean && sd && obs), "fwdbwd_loglik_tc_gauss: NULL pointer argument");
     KHMM_REQUIRE(obs_dtype == KHMM_F32 || obs_dtype == KHMM_F64, "gauss: obs dtype code %d is not f32/f64", obs_dtype);
     TcEmis em{1, mean, sd, obs, obs_dtype, 0};
-    return run_tc<true>(B, T, N, pi, A, AT, em, workspace, workspace_bytes, loglik, loglik_bwd, (cudaStream_t)stream);
+    return run_tc<true>(B, T, N, pi, A, AT, em, workspace, workspace_bytes, loglik, loglik_bwd, operand_precision,
+                        (cudaStream_t)stream);
 }
 
 int khmm_fwdbwd_loglik_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A,
                                        const float *AT, const float *Bsm, const void *obs, int obs_dtype,
                                        void *workspace, size_t workspace_bytes, double *loglik, double *loglik_bwd,
-                                       khmm_stream_t stream) {
+                                       int operand_precision, khmm_stream_t stream) {
     KHMM_REQUIRE(B == 0 || (Bsm && obs && M >= 1), "fwdbwd_loglik_tc_discrete: NULL pointer argument");
     KHMM_REQUIRE(obs_dtype >= KHMM_U8 && obs_dtype <= KHMM_I64, "discrete: obs dtype code %d is not an integer type",
                  obs_dtype);
     TcEmis em{0, Bsm, nullptr, obs, obs_dtype, M};
-    return run_tc<false>(B, T, N, pi, A, AT, em, workspace, workspace_bytes, loglik, loglik_bwd, (cudaStream_t)stream);
+    return run_tc<false>(B, T, N, pi, A, AT, em, workspace, workspace_bytes, loglik, loglik_bwd, operand_precision,
+                         (cudaStream_t)stream);
 }
 
 }  // extern "C"

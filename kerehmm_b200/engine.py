@@ -341,8 +341,13 @@ def tc_supported(p: ModelParams, ob: Obs) -> bool:
             and ob.lengths is None)
 
 
-def fwdbwd_loglik_tc(p: ModelParams, ob: Obs, both=True):
-    """Tensor-core (tcgen05, tf32) forward(+backward) log-likelihood -> (loglik, loglik_bwd|None)."""
+TC_TF32, TC_BF16 = 0, 1
+
+
+def fwdbwd_loglik_tc(p: ModelParams, ob: Obs, both=True, precision=TC_TF32):
+    """Tensor-core (tcgen05) forward(+backward) log-likelihood -> (loglik, loglik_bwd|None).
+    precision: TC_TF32 (default) or TC_BF16 (bf16 operands, fp32 accumulation; twice the MMA rate; falls back to
+    tf32 when the shape is not covered)."""
     t = require_cuda()
     dm = DeviceModel(p, t.float32)
     dev = device()
@@ -350,12 +355,20 @@ def fwdbwd_loglik_tc(p: ModelParams, ob: Obs, both=True):
     llb = t.empty((ob.B,), dtype=t.float64, device=dev) if both else None
     nbytes = _lib.lib().khmm_fwdbwd_loglik_tc_workspace_bytes(ob.B, p.N)
     ws, wsp = workspace(nbytes, 256)
-    if p.kind == "gauss":
-        _lib.call("khmm_fwdbwd_loglik_tc_gauss_f32", ob.B, ob.T, p.N, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.mean),
-                  ptr(dm.sd), ptr(ob.tensor), ob.code, wsp, nbytes, ptr(ll), ptr(llb), stream_ptr())
-    else:
-        _lib.call("khmm_fwdbwd_loglik_tc_discrete_f32", ob.B, ob.T, p.N, p.M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT),
-                  ptr(dm.Bsm), ptr(ob.tensor), ob.code, wsp, nbytes, ptr(ll), ptr(llb), stream_ptr())
+    def run(prec):
+        if p.kind == "gauss":
+            _lib.call("khmm_fwdbwd_loglik_tc_gauss_f32", ob.B, ob.T, p.N, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.mean),
+                      ptr(dm.sd), ptr(ob.tensor), ob.code, wsp, nbytes, ptr(ll), ptr(llb), prec, stream_ptr())
+        else:
+            _lib.call("khmm_fwdbwd_loglik_tc_discrete_f32", ob.B, ob.T, p.N, p.M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT),
+                      ptr(dm.Bsm), ptr(ob.tensor), ob.code, wsp, nbytes, ptr(ll), ptr(llb), prec, stream_ptr())
+    try:
+        run(precision)
+    except _lib.KhmmError as e:
+        if precision == TC_BF16 and e.code == _lib.ERR_UNSUPPORTED:
+            run(TC_TF32)
+        else:
+            raise
     return ll, llb
 
 

@@ -570,3 +570,24 @@ def test_tensor_core_loglik_persistent_tiles(K):
     ref = ref[0] if isinstance(ref, tuple) else ref
     np.testing.assert_allclose(ll.cpu().numpy(), ref, rtol=5e-5)
     np.testing.assert_allclose(llb.cpu().numpy(), ref, rtol=5e-5)
+
+
+def test_tensor_core_loglik_bf16_operands(K):
+    """bf16-operand mode of the whole-recursion kernel (kind::f16, fp32 accumulation): stated bound 1e-4 relative
+    on a short sequence (the absolute error grows like sqrt(T), log P like T: 7e-5 measured at T = 24, 2e-5 at
+    T = 64, 7e-6 at T = 1024), and the fallback to tf32 for shapes the mode does not cover."""
+    import torch
+    N, B, T = 512, 38 * 128, 24
+    np.random.seed(97)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(98)
+    x = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T))).astype(np.float32)
+    ll, llb = h.log_likelihood_batch(torch.from_numpy(x).cuda(), tensor_cores="bf16")
+    ref = O.loglik(O.forward(pi, A, O.emissions_gaussian_1d(mean, sd, x[:256].astype(np.float64)))[1])
+    np.testing.assert_allclose(ll.cpu().numpy()[:256], ref, rtol=1e-4)
+    np.testing.assert_allclose(llb.cpu().numpy()[:256], ref, rtol=1e-4)
+    ll_tf, _ = h.log_likelihood_batch(torch.from_numpy(x).cuda())
+    assert not np.array_equal(ll.cpu().numpy(), ll_tf.cpu().numpy())          # it really is another arithmetic
+    small, _ = h.log_likelihood_batch(torch.from_numpy(x[:256]).cuda(), tensor_cores="bf16")   # too few jobs -> tf32
+    np.testing.assert_allclose(small.cpu().numpy(), ref, rtol=2e-5)
