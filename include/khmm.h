@@ -270,6 +270,8 @@ int khmm_estep_tc_last_kernel_ms(float *forward_ms_host, float *backward_ms_host
 /* Development hook: arm (device buffer of 2*8*32 int64) or disarm (NULL) a clock64 timeline of the warp roles
  * of the backward and forward kernels (block 0, steps 8..15; tools/dbg_bw_trace.py prints it). */
 int khmm_debug_bw_trace(int64_t *dev_buf);
+/* Same for the whole-recursion kernel (device buffer of 4*2*16 int64: block 0, steps 8..11, its two lanes). */
+int khmm_debug_rc_trace(int64_t *dev_buf);
 
 /* ---------------------------------------------------------------------------------------
  * Batched ancestral sampling -- AbstractHMM.simulate / transition / emit (abstract_hmm.py:444-469,

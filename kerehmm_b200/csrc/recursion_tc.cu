@@ -614,7 +614,12 @@ __global__ void __launch_bounds__(192, 1)
 tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_constant__ CUtensorMap mapXf1,
                     const __grid_constant__ CUtensorMap mapXb0, const __grid_constant__ CUtensorMap mapXb1,
                     const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df, TcDir db,
-                    TcEmis em, int64_t B, int64_t T, int N, int mtiles, int ndir, uint32_t *done) {
+                    TcEmis em, int64_t B, int64_t T, int N, int mtiles, int ndir, uint32_t *done, long long *trace) {
+#define RC_TRACE(ev)                                                                                   \
+    do {                                                                                               \
+        if (trace && blockIdx.x == 0 && step >= 8 && step < 12 && (threadIdx.x & 31) == 0)              \
+            trace[((step - 8) * 2 + (ln >= (int)gridDim.x ? 1 : 0)) * 16 + (ev)] = clock64();            \
+    } while (0)
     constexpr int BN = 256;
     constexpr int STAGE_BYTES = TC_TILE_BYTES + BN * TC_BK * 4;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -657,7 +662,9 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
                     int m0, n0, dir, chain;
                     decode(ln, m0, n0, dir, chain);
                     // inputs: W_{step-1} of this chain = all its column-tile jobs of the previous step
+                    RC_TRACE(0);
                     wait_chain(done + chain, (uint32_t)(ntile_n * (step - 1)));
+                    RC_TRACE(1);
                     asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes -> TMA reads
                     const CUtensorMap *mapX = dir ? (src ? &mapXb1 : &mapXb0) : (src ? &mapXf1 : &mapXf0);
                     const CUtensorMap *mapM = dir ? &mapMb : &mapMf;
@@ -680,8 +687,10 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
                 for (int ln = blockIdx.x; ln < nlanes; ln += gridDim.x, nj++) {
                     const int a = nj & 1;
                     mbar_wait(&bars->tmem_empty[a], ((nj >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+                    RC_TRACE(4);
                     tc_fence_after();
                     for (int kb = 0; kb < nkb; kb++, it++) {
+                        if (kb == 1) RC_TRACE(5);
                         int s = it % TC_STAGES;
                         uint32_t ph = (it / TC_STAGES) & 1;
                         mbar_wait(&bars->full[s], ph);
@@ -696,6 +705,7 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
                         tc_commit(&bars->empty[s]);
                     }
                     tc_commit(&bars->tmem_full[a]);
+                    RC_TRACE(6);
                 }
         }
     } else {
@@ -718,6 +728,7 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
                     }
                 }
                 // the previous step's row sums of this chain come from other CTAs: acquire them
+                if (warp == 0) RC_TRACE(8);
                 wait_chain(done + chain, (uint32_t)(ntile_n * (step - 1)));
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int64_t b = m0 + warp * 32 + lane;
@@ -739,7 +750,9 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
                         brow = em.p0 + (int64_t)sym * N + n0;
                     }
                 }
+                if (warp == 0) RC_TRACE(9);
                 mbar_wait(&bars->tmem_full[a], (nj >> 1) & 1);
+                if (warp == 0) RC_TRACE(10);
                 tc_fence_after();
                 float rowsum = 0.f;
                 float *out = d.W + (b * 2 + dst) * N + n0;
@@ -783,6 +796,7 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done + chain) : "memory");
+                if (warp == 0) RC_TRACE(11);
             }
         }
     }
@@ -864,6 +878,8 @@ static size_t tc_workspace_floats(int64_t B, int N) {
     // + per-chain completion counters of the whole-recursion kernel (2 directions x row tiles)
     return (size_t)2 * ((size_t)Bp * 2 * N + (size_t)Bp * 2 * NT + (size_t)Bp * 2) + (size_t)2 * N * N + 2 * (size_t)(Bp / TC_BM) + 64;
 }
+
+static long long *g_rc_trace = nullptr;
 
 template <bool GAUSS>
 static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, const float *AT, TcEmis em, void *ws,
@@ -968,7 +984,7 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
         int Ni = N, mt = mtiles, nd = ndir;
         int64_t Bv = B, Tv = T;
         void *args[] = {&mapX[0][0], &mapX[0][1], &mapX[1][0], &mapX[1][1], &mapM[0], &mapM[1], &d[0], &d[1], &em,
-                        &Bv, &Tv, &Ni, &mt, &nd, &done};
+                        &Bv, &Tv, &Ni, &mt, &nd, &done, &g_rc_trace};
         KHMM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(192), args, smem, st));
     } else if (KHMM_TC_PERSIST && BN == 256) {
         const int mtiles = (int)(Bp / TC_BM);
@@ -1036,6 +1052,11 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
 using namespace khmm;
 
 extern "C" {
+
+int khmm_debug_rc_trace(int64_t *dev_buf) {
+    g_rc_trace = (long long *)dev_buf;
+    return KHMM_OK;
+}
 
 size_t khmm_fwdbwd_loglik_tc_workspace_bytes(int64_t B, int N) {
     if (N < TC_BN || N % TC_BN != 0) return 0;
