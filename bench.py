@@ -322,11 +322,11 @@ def run_ours(args):
         def e2e_step(i):
             return model.log_likelihood_batch(host_sets[0], tensor_cores="bf16" if c5_prec else True)[0]
 
-        launches_per_step = 5      # 2 x tc_round_matrix, tc_init, tc_recursion (all T-1 steps), tc_final
+        launches_per_step = 5      # 2 x matrix conversion, tc_init, tc_recursion2 (all T-1 steps), tc_final
         algo_bytes = None
         h2d, d2h = B * T * 4, 2 * B * 8
-        dominant = "tc_recursion_kernel (tcgen05 kind::%s, one cooperative launch for all steps)" % (
-            "f16 bf16 operands" if c5_prec else "tf32")
+        dominant = "tc_recursion2%s_kernel (tcgen05 kind::%s, one cooperative launch for all steps)" % (
+            "" if c5_prec else "_pair", "f16 bf16 operands" if c5_prec else "tf32, cta_group::2")
         l2_note = "W ping-pong rows + A/AT stay L2 resident by design"
         dtype = ("bf16" if c5_prec else "tf32") + " multiply / f32 accumulate"
 

@@ -22,6 +22,7 @@
 // which is why the float32 SIMT kernels remain the parity path for alpha/beta outputs.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "tcgen05.cuh"
 
@@ -805,6 +806,372 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
     if (warp == 5) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Whole-recursion kernel, second generation.  The clock64 timeline of tc_recursion_kernel (tools/dbg_rc_trace.py)
+// showed a job's MMAs taking 8.7k cycles (bf16) while its epilogue took 19k -- 9.5k of exposed L2 latency before the
+// accumulator is even needed (serial row-sum loads, emission constants, a CTA barrier) and 9.4k of TMEM reads,
+// emission evaluation and thread-per-row stores -- with ONE epilogue warpgroup serialising both; and 108 of the 148
+// CTAs owned two lanes while 40 owned one.  Changes:
+//   * two epilogue warpgroups (warps 0-3 / 4-7), one per TMEM accumulator: the epilogues of consecutive jobs overlap;
+//   * a job's global order is g = (step-1)*nlanes + lane and walker w runs g = w, w+W, w+2W, ... across step
+//     boundaries, so every walker gets the same number of jobs (chains drift apart freely, as before);
+//   * lanes are chain-major (the column tiles of one chain are neighbours), which puts nlanes - ntile_n + 1 jobs
+//     between a chain's step and its next step instead of nlanes - 3*mtiles: more slack for the dependency;
+//   * Gaussian constants of all N states computed once per CTA; observation prefetched before the dependency
+//     wait; the previous step's partial row sums fetched with independent vector loads; TMEM loads of the next
+//     32-column chunk issued under the arithmetic of the current one; W_t staged in shared memory and written by TMA tensor stores;
+//   * PAIR: a cluster of two CTAs (tcgen05 cta_group::2) runs a 256-sequence x 256-state job: each CTA stages its
+//     own 128 W rows and HALF of the matrix tile, 512 KB instead of 768 KB of L2 -> SM traffic per 128 x 256 x 1024
+//     job.  At c5 the single-CTA kernel asks the L2 for 256 x 1023 x 768 KB = 201 GB per call; the L2 delivers
+//     ~6.3 KB/clk chip-wide, i.e. >= 16.8 ms, above the 10.9 ms the tensor pipe needs (bf16).
+template <bool PAIR>
+struct __align__(8) TcRBars {
+    static constexpr int STAGES = PAIR ? 5 : 3;       // 160 KB / 144 KB of operand ring; 32 KB of output staging
+    uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+#ifndef KHMM_RC2
+#define KHMM_RC2 1
+#endif
+#ifndef KHMM_RC2_PAIR
+#define KHMM_RC2_PAIR 1
+#endif
+#ifndef KHMM_RC2_ORDER
+#define KHMM_RC2_ORDER 0      /* 0: chain-major lanes, 1: row tile fastest (neighbouring walkers share a matrix tile) */
+#endif
+
+struct RcWalk {               // (step, lane) of the jobs w, w + stride, w + 2 stride, ... of the global order
+    int64_t step;
+    int ln, nlanes;
+    __device__ __forceinline__ RcWalk(int start, int nl) : step(1), ln(start), nlanes(nl) { norm(); }
+    __device__ __forceinline__ void norm() { while (ln >= nlanes) { ln -= nlanes; step++; } }
+    __device__ __forceinline__ void advance(int by) { ln += by; norm(); }
+};
+
+__device__ __forceinline__ void mma2_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
+}
+
+template <bool GAUSS, bool BF16, bool PAIR>
+__device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, const CUtensorMap &mapXf1, const CUtensorMap &mapXb0,
+                                                   const CUtensorMap &mapXb1, const CUtensorMap &mapMf, const CUtensorMap &mapMb,
+                                                   TcDir df, TcDir db, TcEmis em, int64_t B, int64_t T, int N, int mtiles,
+                                                   int ndir, uint32_t *done, long long *trace) {
+#define RC2_TRACE(ev, njv)                                                                              \
+    do {                                                                                                \
+        if (trace && blockIdx.x == 0 && (njv) >= 16 && (njv) < 24 && (threadIdx.x & 31) == 0)            \
+            trace[((njv) - 16) * 16 + (ev)] = clock64();                                                 \
+    } while (0)
+    constexpr int BN = 256;
+    constexpr int STAGES = TcRBars<PAIR>::STAGES;
+    constexpr int MROWS = PAIR ? 128 : BN;                          // matrix-tile rows staged by this CTA
+    constexpr int STAGE_BYTES = TC_TILE_BYTES + MROWS * 128;        // k-block rows are 128 bytes in both precisions
+    constexpr int BKE = BF16 ? 64 : TC_BK;                          // elements per 128-byte k-block row
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *stage_out = tiles + STAGES * STAGE_BYTES;        // [2 warpgroups][128 rows][128 B], 128-byte swizzle
+    TcRBars<PAIR> *bars = (TcRBars<PAIR> *)(stage_out + 2 * TC_TILE_BYTES);
+    float *sp = (float *)(((uintptr_t)(bars + 1) + 15) & ~(uintptr_t)15);   // [3][N] Gaussian constants of all states
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+    const int w = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // walker index
+    const int nwalk = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int nkb = N / BKE, NT = N / 128, ntile_n = N / BN;
+    const int mjobs = PAIR ? mtiles / 2 : mtiles;
+    const int nlanes = mjobs * ntile_n * ndir;
+    const int64_t njobs_total = (int64_t)nlanes * (T - 1);
+    const uint32_t per_step = 2u * (uint32_t)ntile_n;                        // half-tile completions per chain and step
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], PAIR ? 16 : 8); }
+        fence_barrier_init();
+    }
+    if (GAUSS) {
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            float sd = em.p1[j];
+            sp[j] = -em.p0[j];
+            sp[N + j] = -0.5f * 1.4426950408889634f / (sd * sd);
+            sp[2 * N + j] = -log2f(sd * 2.5066282746310002f);
+        }
+    }
+    if (warp == 9) { if (PAIR) tmem_alloc2(&bars->tmem_base, 512); else tmem_alloc(&bars->tmem_base, 512); }
+    tc_fence_before();
+    __syncthreads();
+    if (PAIR) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    auto decode = [&](int ln, int &m0, int &n0, int &dir, int &chain) {
+        int mtp, nt;
+        if (KHMM_RC2_ORDER == 0) {
+            nt = ln % ntile_n;
+            const int cp = ln / ntile_n;
+            dir = cp / mjobs;
+            mtp = cp % mjobs;
+        } else {
+            mtp = ln % mjobs;
+            const int rest = ln / mjobs;
+            nt = rest % ntile_n;
+            dir = rest / ntile_n;
+        }
+        const int mt = PAIR ? mtp * 2 + (int)rank : mtp;
+        m0 = mt * TC_BM;
+        n0 = nt * BN;
+        chain = dir * mtiles + mt;
+    };
+    const int64_t myjobs = njobs_total > w ? (njobs_total - w + nwalk - 1) / nwalk : 0;   // jobs of this walker
+
+    if (warp == 8) {
+        if (elect_one()) {
+            tma_prefetch_desc(&mapXf0); tma_prefetch_desc(&mapXf1); tma_prefetch_desc(&mapMf);
+            if (ndir > 1) { tma_prefetch_desc(&mapXb0); tma_prefetch_desc(&mapXb1); tma_prefetch_desc(&mapMb); }
+            uint32_t it = 0;
+            RcWalk jw(w, nlanes);
+            for (int64_t nj = 0; nj < myjobs; nj++, jw.advance(nwalk)) {
+                int m0, n0, dir, chain;
+                decode(jw.ln, m0, n0, dir, chain);
+                const int src = (int)((jw.step - 1) & 1);
+                RC2_TRACE(0, nj);
+                const CUtensorMap *mapX = dir ? (src ? &mapXb1 : &mapXb0) : (src ? &mapXf1 : &mapXf0);
+                const CUtensorMap *mapM = dir ? &mapMb : &mapMf;
+                // k-block kb: arm the stage and fetch the matrix tile (it does not depend on the chain) / fetch the W tile
+                auto load_m = [&](int kb, uint32_t itk) {
+                    const int s = itk % STAGES;
+                    mbar_wait(&bars->empty[s], ((itk / STAGES) & 1) ^ 1);
+                    if (PAIR) {
+                        // the leader alone arrives, expecting both CTAs' bytes; the peer's loads complete_tx on the leader's barrier
+                        if (rank == 0) mbar_arrive_expect_tx(&bars->full[s], 2 * STAGE_BYTES);
+                        tma_load_2d_pair(tiles + s * STAGE_BYTES + TC_TILE_BYTES, mapM, mapa_u32(smem_u32(&bars->full[s]), 0), kb * BKE,
+                                         n0 + (int)rank * 128);
+                    } else {
+                        mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
+                        tma_load_2d(tiles + s * STAGE_BYTES + TC_TILE_BYTES, mapM, &bars->full[s], kb * BKE, n0);
+                    }
+                };
+                auto load_x = [&](int kb, uint32_t itk) {
+                    const int s = itk % STAGES;
+                    if (PAIR) tma_load_2d_pair(tiles + s * STAGE_BYTES, mapX, mapa_u32(smem_u32(&bars->full[s]), 0), kb * BKE, m0);
+                    else tma_load_2d(tiles + s * STAGE_BYTES, mapX, &bars->full[s], kb * BKE, m0);
+                };
+                // the matrix tiles of the first STAGES k-blocks are requested BEFORE the dependency wait
+                const int npre = nkb < STAGES ? nkb : STAGES;
+                for (int kb = 0; kb < npre; kb++) load_m(kb, it + kb);
+                // inputs: W_{step-1} of this CTA's chain = all its column-tile jobs of the previous step
+                wait_chain(done + chain, per_step * (uint32_t)(jw.step - 1));
+                RC2_TRACE(1, nj);
+                asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy acquire -> TMA reads
+                for (int kb = 0; kb < npre; kb++) load_x(kb, it + kb);
+                for (int kb = npre; kb < nkb; kb++) { load_m(kb, it + kb); load_x(kb, it + kb); }
+                it += nkb;
+            }
+        }
+    } else if (warp == 9) {
+        if (rank == 0 && elect_one()) {
+            const uint32_t idesc = BF16 ? make_idesc_bf16(PAIR ? 256 : TC_BM, BN) : make_idesc_tf32(PAIR ? 256 : TC_BM, BN);
+            uint32_t it = 0;
+            for (int64_t nj = 0; nj < myjobs; nj++) {
+                const int a = (int)(nj & 1);
+                mbar_wait(&bars->tmem_empty[a], (uint32_t)((nj >> 1) & 1) ^ 1);   // the epilogue(s) drained this accumulator
+                RC2_TRACE(4, nj);
+                tc_fence_after();
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    if (kb == 1) RC2_TRACE(5, nj);
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&bars->full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = make_kmajor_sw128_desc(tiles + s * STAGE_BYTES);
+                    const uint64_t dbb = make_kmajor_sw128_desc(tiles + s * STAGE_BYTES + TC_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {      // 32 bytes of K per MMA: 8 tf32 or 16 bf16 elements
+                        const uint64_t ak = desc_advance(da, k * 32), bk = desc_advance(dbb, k * 32);
+                        const bool accum = (kb | k) != 0;
+                        if (PAIR) { if (BF16) mma2_bf16_ss(tmem + a * BN, ak, bk, idesc, accum); else mma2_tf32_ss(tmem + a * BN, ak, bk, idesc, accum); }
+                        else { if (BF16) mma_bf16_ss(tmem + a * BN, ak, bk, idesc, accum); else mma_tf32_ss(tmem + a * BN, ak, bk, idesc, accum); }
+                    }
+                    if (PAIR) tc_commit2(&bars->empty[s], 3); else tc_commit(&bars->empty[s]);
+                }
+                if (PAIR) tc_commit2(&bars->tmem_full[a], 3); else tc_commit(&bars->tmem_full[a]);
+                RC2_TRACE(6, nj);
+            }
+        }
+    } else {
+        // epilogue: all eight warps work on EVERY job -- warp (wq, h) owns TMEM lanes 32 wq .. 32 wq + 31 (= sequences) and the
+        // 128-column half h of the tile, so a job's epilogue latency (which sits on the chain's critical path) is four
+        // 32-column chunks instead of eight.  Arithmetic is packed (FADD2/FMUL2/FFMA2): two states per instruction.
+        const int h = warp >> 2, wq = warp & 3;
+        RcWalk jw(w, nlanes);
+        for (int64_t nj = 0; nj < myjobs; nj++, jw.advance(nwalk)) {
+            const int a = (int)(nj & 1);
+            int m0, n0, dir, chain;
+            decode(jw.ln, m0, n0, dir, chain);
+            const TcDir d = dir ? db : df;
+            const int src = (int)((jw.step - 1) & 1), dst = (int)(jw.step & 1);
+            const int64_t b = m0 + wq * 32 + lane;
+            const bool live = b < B;
+            const int64_t t = dir ? (T - 1 - jw.step) : jw.step;
+            float r = 0.f, x = 0.f;
+            const float *brow = nullptr;
+            if (live) {       // nothing here depends on the previous step
+                if (GAUSS) {
+                    x = load_real<float>(em.obs, em.obs_dtype, b * T + t);
+                } else {
+                    int sym = load_symbol(em.obs, em.obs_dtype, b * T + t);
+                    sym = sym < 0 ? 0 : (sym >= em.M ? em.M - 1 : sym);
+                    brow = em.p0 + (int64_t)sym * N + n0;
+                }
+            }
+            if (warp == 0) RC2_TRACE(8, nj);
+            // the previous step's row sums of this chain come from other CTAs: acquire them
+            wait_chain(done + chain, per_step * (uint32_t)(jw.step - 1));
+            if (live) {
+                const float2 *ps = reinterpret_cast<const float2 *>(d.psum + (b * 2 + src) * NT);
+                float2 p2[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) p2[k] = (2 * k < NT) ? __ldcg(ps + k) : make_float2(0.f, 0.f);   // N <= 1024: NT <= 8
+                const float c = ((p2[0].x + p2[0].y) + (p2[1].x + p2[1].y)) + ((p2[2].x + p2[2].y) + (p2[3].x + p2[3].y));
+                r = 1.0f / c;
+                if (n0 == 0 && h == 0) __stcg(d.logacc + b, __ldcg(d.logacc + b) + log((double)c));
+            }
+            if (warp == 0) RC2_TRACE(9, nj);
+            mbar_wait(&bars->tmem_full[a], (uint32_t)((nj >> 1) & 1));
+            if (warp == 0) RC2_TRACE(10, nj);
+            tc_fence_after();
+            const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + a * BN + h * 128;
+            // W_t leaves through shared memory: thread = row writes its 16-byte pieces into a [128 rows][128 B] box with the
+            // TMA 128-byte swizzle (piece p of row r at p ^ (r & 7): conflict-free), one thread stores the box with a tensor
+            // store -- full 128-byte lines to L2 instead of 16-byte pieces of 32 different lines per warp instruction.
+            unsigned char *obuf = stage_out + h * TC_TILE_BYTES;
+            const int orow = wq * 32 + lane;
+            unsigned char *orowp = obuf + orow * 128;
+            const CUtensorMap *mapO = dir ? (dst ? &mapXb1 : &mapXb0) : (dst ? &mapXf1 : &mapXf0);
+            constexpr int BOXC = BF16 ? 64 : 32;                   // columns per 128-byte box row
+            const float2 rr = make_float2(r, r), xx = make_float2(x, x);
+            float2 rs0 = make_float2(0.f, 0.f), rs1 = make_float2(0.f, 0.f);
+            auto process = [&](const uint32_t (&acc)[32], int c0) {       // c0: column inside this warp's 128-column half
+                float2 v[16];
+                if (!live) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) v[q] = make_float2(0.f, 0.f);
+                } else if (GAUSS) {
+                    const float4 *nm4 = reinterpret_cast<const float4 *>(sp + n0 + h * 128 + c0);
+                    const float4 *k4 = reinterpret_cast<const float4 *>(sp + N + n0 + h * 128 + c0);
+                    const float4 *l4 = reinterpret_cast<const float4 *>(sp + 2 * N + n0 + h * 128 + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 nm = nm4[q], kk = k4[q], ll = l4[q];
+                        const float2 d0 = __fadd2_rn(xx, make_float2(nm.x, nm.y)), d1 = __fadd2_rn(xx, make_float2(nm.z, nm.w));
+                        const float2 a0 = __ffma2_rn(__fmul2_rn(d0, d0), make_float2(kk.x, kk.y), make_float2(ll.x, ll.y));
+                        const float2 a1 = __ffma2_rn(__fmul2_rn(d1, d1), make_float2(kk.z, kk.w), make_float2(ll.z, ll.w));
+                        float e0, e1, e2, e3;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0.x));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a0.y));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(a1.x));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(a1.y));
+                        v[2 * q] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])), rr), make_float2(e0, e1));
+                        v[2 * q + 1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), rr), make_float2(e2, e3));
+                    }
+                } else {
+                    const float4 *b4 = reinterpret_cast<const float4 *>(brow + h * 128 + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 e = __ldg(b4 + q);
+                        v[2 * q] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])), rr), make_float2(e.x, e.y));
+                        v[2 * q + 1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), rr), make_float2(e.z, e.w));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) { rs0 = __fadd2_rn(rs0, v[2 * q]); rs1 = __fadd2_rn(rs1, v[2 * q + 1]); }
+                if ((c0 % BOXC) == 0) {
+                    // the box of the previous group must have been read out by its tensor store
+                    if (threadIdx.x == h * 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+                }
+                if (BF16) {
+                    const int p0 = (c0 & 32) ? 4 : 0;               // second 32-column half of the 64-column box
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        *reinterpret_cast<uint4 *>(orowp + (((p0 + q) ^ (orow & 7)) << 4)) =
+                            make_uint4(pack_bf16(v[4 * q].x, v[4 * q].y), pack_bf16(v[4 * q + 1].x, v[4 * q + 1].y),
+                                       pack_bf16(v[4 * q + 2].x, v[4 * q + 2].y), pack_bf16(v[4 * q + 3].x, v[4 * q + 3].y));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        *reinterpret_cast<float4 *>(orowp + ((q ^ (orow & 7)) << 4)) =
+                            make_float4(round_tf32(v[2 * q].x), round_tf32(v[2 * q].y), round_tf32(v[2 * q + 1].x), round_tf32(v[2 * q + 1].y));
+                }
+                if (((c0 + 32) % BOXC) == 0) {
+                    fence_proxy_async();                             // generic-proxy smem writes -> async-proxy (TMA) reads
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+                    if (threadIdx.x == h * 128) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(mapO), "r"(smem_u32(obuf)), "r"(n0 + h * 128 + c0 + 32 - BOXC), "r"(m0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            };
+            uint32_t accA[32], accB[32];
+            tmem_ld_32x32(tbase, accA);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 64) {
+                tmem_ld_wait();
+                if (c0 == 0 && warp == 0) RC2_TRACE(12, nj);
+                tmem_ld_32x32(tbase + c0 + 32, accB);          // in flight under the arithmetic on accA
+                process(accA, c0);
+                if (c0 == 0 && warp == 0) RC2_TRACE(13, nj);
+                tmem_ld_wait();
+                if (c0 + 64 < 128) tmem_ld_32x32(tbase + c0 + 64, accA);
+                process(accB, c0 + 32);
+            }
+            if (warp == 0) RC2_TRACE(14, nj);
+            if (live) d.psum[(b * 2 + dst) * NT + (n0 >> 7) + h] = (rs0.x + rs0.y) + (rs1.x + rs1.y);
+            // accumulator a may be overwritten: one arrival per epilogue warp, on the LEADER's barrier
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[a]), 0));
+                else mbar_arrive(&bars->tmem_empty[a]);
+            }
+            // publish this half of the job: the barrier orders the 128 threads' row-sum / log-accumulator stores before
+            // the elected thread, whose gpu-scope release is cumulative over them (the pattern of a grid barrier); its
+            // own tensor stores are complete (wait_group) first
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+            if (warp == 0) RC2_TRACE(15, nj);
+            if (threadIdx.x == h * 128) {
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // complete = visible to the generic proxy (implicit proxy fence)
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done + chain) : "memory");
+            }
+            if (warp == 0) RC2_TRACE(11, nj);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer may still signal our barriers / use the paired TMEM
+    if (warp == 9) { if (PAIR) tmem_dealloc2(tmem, 512); else tmem_dealloc(tmem, 512); }
+#undef RC2_TRACE
+}
+
+template <bool GAUSS, bool BF16>
+__global__ void __launch_bounds__(320, 1)
+tc_recursion2_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_constant__ CUtensorMap mapXf1,
+                     const __grid_constant__ CUtensorMap mapXb0, const __grid_constant__ CUtensorMap mapXb1,
+                     const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df, TcDir db,
+                     TcEmis em, int64_t B, int64_t T, int N, int mtiles, int ndir, uint32_t *done, long long *trace) {
+    tc_recursion2_body<GAUSS, BF16, false>(mapXf0, mapXf1, mapXb0, mapXb1, mapMf, mapMb, df, db, em, B, T, N, mtiles, ndir, done, trace);
+}
+template <bool GAUSS, bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+tc_recursion2_pair_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_constant__ CUtensorMap mapXf1,
+                          const __grid_constant__ CUtensorMap mapXb0, const __grid_constant__ CUtensorMap mapXb1,
+                          const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df, TcDir db,
+                          TcEmis em, int64_t B, int64_t T, int N, int mtiles, int ndir, uint32_t *done, long long *trace) {
+    tc_recursion2_body<GAUSS, BF16, true>(mapXf0, mapXf1, mapXb0, mapXb1, mapMf, mapMb, df, db, em, B, T, N, mtiles, ndir, done, trace);
+}
+
 // step 0: W_0 = start . b(o_first): start = pi (forward, t = 0) or ones (backward, t = T-1)
 template <bool GAUSS, bool BF16 = false>
 __global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__restrict__ pi, int64_t B, int64_t T, int N) {
@@ -972,7 +1339,56 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     }
-    if (coop) {
+    // KHMM_RC_MODE (development switch): 1 = first-generation whole-recursion kernel, 2 = second generation on
+    // single CTAs, 3 = second generation on CTA pairs (default when the row-tile count is even)
+    // measured at c5 (B = 4096, T = 1024, N = 1024): bf16 17.5 ms single / 17.9 ms pairs; tf32 ~29 ms single / 25.8 ms pairs
+    int rc_mode = KHMM_RC2 ? ((KHMM_RC2_PAIR && !bf16) ? 3 : 2) : 1;
+    if (const char *e = getenv("KHMM_RC_MODE")) rc_mode = atoi(e);
+    if (coop && rc_mode >= 2) {
+        const int mtiles = (int)(Bp / TC_BM);
+        bool rpair = rc_mode == 3 && mtiles % 2 == 0;
+        CUtensorMap mapH[2];
+        if (rpair && (bf16 ? (make_tmap_bf16_rowmajor(&mapH[0], ATr, N, N, 128) || make_tmap_bf16_rowmajor(&mapH[1], Ar, N, N, 128))
+                           : (make_tmap_f32_rowmajor(&mapH[0], ATr, N, N, 128) || make_tmap_f32_rowmajor(&mapH[1], Ar, N, N, 128)))) {
+            set_error("tensor map creation for the transition matrix failed");
+            return KHMM_ERR_CUDA;
+        }
+        const size_t smem = (rpair ? (size_t)TcRBars<true>::STAGES * (TC_TILE_BYTES + 128 * 128) : (size_t)TcRBars<false>::STAGES * (TC_TILE_BYTES + 256 * 128)) +
+                            2 * (size_t)TC_TILE_BYTES + sizeof(TcRBars<true>) + 16 + 3 * (size_t)N * sizeof(float) + 1024;
+        void *kern = rpair ? (bf16 ? (void *)tc_recursion2_pair_kernel<GAUSS, true> : (void *)tc_recursion2_pair_kernel<GAUSS, false>)
+                           : (bf16 ? (void *)tc_recursion2_kernel<GAUSS, true> : (void *)tc_recursion2_kernel<GAUSS, false>);
+        KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int nlanes = (rpair ? mtiles / 2 : mtiles) * (N / 256) * ndir;
+        int walkers = rpair ? sm_count() / 2 : sm_count();
+        if (rpair) {
+            // every CTA pair must be resident at once: ask how many clusters of two the device can hold
+            cudaLaunchConfig_t qc = {};
+            qc.gridDim = dim3(2 * walkers);
+            qc.blockDim = dim3(320);
+            qc.dynamicSmemBytes = smem;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &qc) != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                nclusters = walkers;
+            }
+            if (nclusters < walkers) walkers = nclusters;
+        }
+        if (nlanes < walkers) walkers = nlanes;
+        const int grid = rpair ? 2 * walkers : walkers;
+        KHMM_CUDA_CHECK(cudaMemsetAsync(done, 0, 2 * (size_t)mtiles * sizeof(uint32_t), st));
+        int Ni = N, mt = mtiles, nd = ndir;
+        int64_t Bv = B, Tv = T;
+        void *args[] = {&mapX[0][0], &mapX[0][1], &mapX[1][0], &mapX[1][1], rpair ? &mapH[0] : &mapM[0], rpair ? &mapH[1] : &mapM[1],
+                        &d[0], &d[1], &em, &Bv, &Tv, &Ni, &mt, &nd, &done, &g_rc_trace};
+        cudaError_t le = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(320), args, smem, st);
+        if (le != cudaSuccess && rpair) {
+            // cooperative launch of a cluster kernel refused: the grid is sized to the resident-cluster count, so a plain
+            // launch still has every CTA resident once the preceding kernels of this stream have drained
+            cudaGetLastError();
+            le = cudaLaunchKernel(kern, dim3(grid), dim3(320), args, smem, st);
+        }
+        KHMM_CUDA_CHECK(le);
+    } else if (coop) {
         // one cooperative launch for all T-1 steps
         const int mtiles = (int)(Bp / TC_BM);
         const int nlanes = mtiles * (N / 256) * ndir;

@@ -19,10 +19,9 @@ _lib.call("khmm_debug_rc_trace", tr.data_ptr())
 h.log_likelihood_batch(xd, tensor_cores=mode if mode == "bf16" else True)
 torch.cuda.synchronize()
 _lib.call("khmm_debug_rc_trace", None)
-a = tr.cpu().numpy().reshape(4, 2, 16)
-names = {0: "tma:job", 1: "tma:deps ok", 4: "mma:acc free", 5: "mma:kb1", 6: "mma:issued", 8: "epi:job", 9: "epi:deps ok", 10: "epi:acc full", 11: "epi:published"}
-base = a[0, 0, 0]
-for s in range(4):
-    for l in range(2):
-        ev = sorted((int(a[s, l, k] - base), names[k]) for k in names if a[s, l, k])
-        print("step", s + 8, "lane", l, " | ".join("%s @%d" % (n, c) for c, n in ev))
+a = tr.cpu().numpy().reshape(8, 16)
+names = {0: "tma:job", 1: "tma:deps ok", 4: "mma:acc free", 5: "mma:kb1", 6: "mma:issued", 8: "epi:job", 9: "epi:deps ok", 10: "epi:acc full", 11: "epi:published", 12: "epi:ld0", 13: "epi:chunk0", 14: "epi:loop end", 15: "epi:fenced"}
+base = a[0, 0]
+for j in range(8):
+    ev = sorted((int(a[j, k] - base), names[k]) for k in names if a[j, k])
+    print("job", j + 16, " | ".join("%s @%d" % (n, c) for c, n in ev))
