@@ -824,9 +824,11 @@ tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_con
 //     own 128 W rows and HALF of the matrix tile, 512 KB instead of 768 KB of L2 -> SM traffic per 128 x 256 x 1024
 //     job.  At c5 the single-CTA kernel asks the L2 for 256 x 1023 x 768 KB = 201 GB per call; the L2 delivers
 //     ~6.3 KB/clk chip-wide, i.e. >= 16.8 ms, above the 10.9 ms the tensor pipe needs (bf16).
-template <bool PAIR>
+template <bool PAIR, int BN>
 struct __align__(8) TcRBars {
-    static constexpr int STAGES = PAIR ? 5 : 3;       // 160 KB / 144 KB of operand ring; 32 KB of output staging
+    // operand ring: 16 KB W tile + (BN or BN/2) x 128 B matrix tile per stage; 144-160 KB, next to 32 KB of output staging
+    // and the 12 KB constant table
+    static constexpr int STAGES = PAIR ? 5 : (BN == 256 ? 3 : 5);
     uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
@@ -856,7 +858,7 @@ __device__ __forceinline__ void mma2_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
 }
 
-template <bool GAUSS, bool BF16, bool PAIR>
+template <bool GAUSS, bool BF16, bool PAIR, int BN>
 __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, const CUtensorMap &mapXf1, const CUtensorMap &mapXb0,
                                                    const CUtensorMap &mapXb1, const CUtensorMap &mapMf, const CUtensorMap &mapMb,
                                                    TcDir df, TcDir db, TcEmis em, int64_t B, int64_t T, int N, int mtiles,
@@ -866,21 +868,22 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
         if (trace && blockIdx.x == 0 && (njv) >= 16 && (njv) < 24 && (threadIdx.x & 31) == 0)            \
             trace[((njv) - 16) * 16 + (ev)] = clock64();                                                 \
     } while (0)
-    constexpr int BN = 256;
-    constexpr int STAGES = TcRBars<PAIR>::STAGES;
-    constexpr int MROWS = PAIR ? 128 : BN;                          // matrix-tile rows staged by this CTA
+    static_assert(BN == 256 || (BN == 128 && !PAIR), "column tiles: 256 (single CTAs or pairs) or 128 (single CTAs)");
+    constexpr int STAGES = TcRBars<PAIR, BN>::STAGES;
+    constexpr int MROWS = PAIR ? BN / 2 : BN;                       // matrix-tile rows staged by this CTA
+    constexpr int HALF = BN / 2;                                    // columns per epilogue warp (column half h)
     constexpr int STAGE_BYTES = TC_TILE_BYTES + MROWS * 128;        // k-block rows are 128 bytes in both precisions
     constexpr int BKE = BF16 ? 64 : TC_BK;                          // elements per 128-byte k-block row
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *stage_out = tiles + STAGES * STAGE_BYTES;        // [2 warpgroups][128 rows][128 B], 128-byte swizzle
-    TcRBars<PAIR> *bars = (TcRBars<PAIR> *)(stage_out + 2 * TC_TILE_BYTES);
+    TcRBars<PAIR, BN> *bars = (TcRBars<PAIR, BN> *)(stage_out + 2 * TC_TILE_BYTES);
     float *sp = (float *)(((uintptr_t)(bars + 1) + 15) & ~(uintptr_t)15);   // [3][N] Gaussian constants of all states
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0;
     const int w = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // walker index
     const int nwalk = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int nkb = N / BKE, NT = N / 128, ntile_n = N / BN;
+    const int nkb = N / BKE, NTq = N / 64, ntile_n = N / BN;        // row sums are kept per 64 columns: [b][slot][N/64]
     const int mjobs = PAIR ? mtiles / 2 : mtiles;
     const int nlanes = mjobs * ntile_n * ndir;
     const int64_t njobs_total = (int64_t)nlanes * (T - 1);
@@ -946,7 +949,7 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
                         // the leader alone arrives, expecting both CTAs' bytes; the peer's loads complete_tx on the leader's barrier
                         if (rank == 0) mbar_arrive_expect_tx(&bars->full[s], 2 * STAGE_BYTES);
                         tma_load_2d_pair(tiles + s * STAGE_BYTES + TC_TILE_BYTES, mapM, mapa_u32(smem_u32(&bars->full[s]), 0), kb * BKE,
-                                         n0 + (int)rank * 128);
+                                         n0 + (int)rank * MROWS);
                     } else {
                         mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
                         tma_load_2d(tiles + s * STAGE_BYTES + TC_TILE_BYTES, mapM, &bars->full[s], kb * BKE, n0);
@@ -1001,8 +1004,8 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
         }
     } else {
         // epilogue: all eight warps work on EVERY job -- warp (wq, h) owns TMEM lanes 32 wq .. 32 wq + 31 (= sequences) and the
-        // 128-column half h of the tile, so a job's epilogue latency (which sits on the chain's critical path) is four
-        // 32-column chunks instead of eight.  Arithmetic is packed (FADD2/FMUL2/FFMA2): two states per instruction.
+        // column half h of the tile, so a job's epilogue latency (which sits on the chain's critical path) is BN/64
+        // 32-column chunks instead of BN/32.  Arithmetic is packed (FADD2/FMUL2/FFMA2): two states per instruction.
         const int h = warp >> 2, wq = warp & 3;
         RcWalk jw(w, nlanes);
         for (int64_t nj = 0; nj < myjobs; nj++, jw.advance(nwalk)) {
@@ -1029,11 +1032,12 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
             // the previous step's row sums of this chain come from other CTAs: acquire them
             wait_chain(done + chain, per_step * (uint32_t)(jw.step - 1));
             if (live) {
-                const float2 *ps = reinterpret_cast<const float2 *>(d.psum + (b * 2 + src) * NT);
-                float2 p2[4];
+                const float2 *ps = reinterpret_cast<const float2 *>(d.psum + (b * 2 + src) * NTq);
+                float2 p2[8];
 #pragma unroll
-                for (int k = 0; k < 4; k++) p2[k] = (2 * k < NT) ? __ldcg(ps + k) : make_float2(0.f, 0.f);   // N <= 1024: NT <= 8
-                const float c = ((p2[0].x + p2[0].y) + (p2[1].x + p2[1].y)) + ((p2[2].x + p2[2].y) + (p2[3].x + p2[3].y));
+                for (int k = 0; k < 8; k++) p2[k] = (2 * k < NTq) ? __ldcg(ps + k) : make_float2(0.f, 0.f);   // N <= 1024: NTq <= 16
+                const float c = (((p2[0].x + p2[0].y) + (p2[1].x + p2[1].y)) + ((p2[2].x + p2[2].y) + (p2[3].x + p2[3].y))) +
+                                (((p2[4].x + p2[4].y) + (p2[5].x + p2[5].y)) + ((p2[6].x + p2[6].y) + (p2[7].x + p2[7].y)));
                 r = 1.0f / c;
                 if (n0 == 0 && h == 0) __stcg(d.logacc + b, __ldcg(d.logacc + b) + log((double)c));
             }
@@ -1041,7 +1045,8 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
             mbar_wait(&bars->tmem_full[a], (uint32_t)((nj >> 1) & 1));
             if (warp == 0) RC2_TRACE(10, nj);
             tc_fence_after();
-            const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + a * BN + h * 128;
+            const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + a * BN + h * HALF;
+            const int nh = n0 + h * HALF;                           // first column of this warp's half
             // W_t leaves through shared memory: thread = row writes its 16-byte pieces into a [128 rows][128 B] box with the
             // TMA 128-byte swizzle (piece p of row r at p ^ (r & 7): conflict-free), one thread stores the box with a tensor
             // store -- full 128-byte lines to L2 instead of 16-byte pieces of 32 different lines per warp instruction.
@@ -1052,15 +1057,15 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
             constexpr int BOXC = BF16 ? 64 : 32;                   // columns per 128-byte box row
             const float2 rr = make_float2(r, r), xx = make_float2(x, x);
             float2 rs0 = make_float2(0.f, 0.f), rs1 = make_float2(0.f, 0.f);
-            auto process = [&](const uint32_t (&acc)[32], int c0) {       // c0: column inside this warp's 128-column half
+            auto process = [&](const uint32_t (&acc)[32], int c0) {       // c0: column inside this warp's half
                 float2 v[16];
                 if (!live) {
 #pragma unroll
                     for (int q = 0; q < 16; q++) v[q] = make_float2(0.f, 0.f);
                 } else if (GAUSS) {
-                    const float4 *nm4 = reinterpret_cast<const float4 *>(sp + n0 + h * 128 + c0);
-                    const float4 *k4 = reinterpret_cast<const float4 *>(sp + N + n0 + h * 128 + c0);
-                    const float4 *l4 = reinterpret_cast<const float4 *>(sp + 2 * N + n0 + h * 128 + c0);
+                    const float4 *nm4 = reinterpret_cast<const float4 *>(sp + nh + c0);
+                    const float4 *k4 = reinterpret_cast<const float4 *>(sp + N + nh + c0);
+                    const float4 *l4 = reinterpret_cast<const float4 *>(sp + 2 * N + nh + c0);
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         const float4 nm = nm4[q], kk = k4[q], ll = l4[q];
@@ -1076,13 +1081,18 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
                         v[2 * q + 1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), rr), make_float2(e2, e3));
                     }
                 } else {
-                    const float4 *b4 = reinterpret_cast<const float4 *>(brow + h * 128 + c0);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(brow + h * HALF + c0);
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         const float4 e = __ldg(b4 + q);
                         v[2 * q] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])), rr), make_float2(e.x, e.y));
                         v[2 * q + 1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), rr), make_float2(e.z, e.w));
                     }
+                }
+                if (c0 == 64) {       // (BN = 256) the first 64 columns of this half are one row-sum slot
+                    if (live) d.psum[(b * 2 + dst) * NTq + (nh >> 6)] = (rs0.x + rs0.y) + (rs1.x + rs1.y);
+                    rs0 = make_float2(0.f, 0.f);
+                    rs1 = make_float2(0.f, 0.f);
                 }
 #pragma unroll
                 for (int q = 0; q < 8; q++) { rs0 = __fadd2_rn(rs0, v[2 * q]); rs1 = __fadd2_rn(rs1, v[2 * q + 1]); }
@@ -1109,7 +1119,7 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
                     if (threadIdx.x == h * 128) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     ::"l"(mapO), "r"(smem_u32(obuf)), "r"(n0 + h * 128 + c0 + 32 - BOXC), "r"(m0) : "memory");
+                                     ::"l"(mapO), "r"(smem_u32(obuf)), "r"(nh + c0 + 32 - BOXC), "r"(m0) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -1117,18 +1127,18 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
             uint32_t accA[32], accB[32];
             tmem_ld_32x32(tbase, accA);
 #pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 64) {
+            for (int c0 = 0; c0 < HALF; c0 += 64) {
                 tmem_ld_wait();
                 if (c0 == 0 && warp == 0) RC2_TRACE(12, nj);
                 tmem_ld_32x32(tbase + c0 + 32, accB);          // in flight under the arithmetic on accA
                 process(accA, c0);
                 if (c0 == 0 && warp == 0) RC2_TRACE(13, nj);
                 tmem_ld_wait();
-                if (c0 + 64 < 128) tmem_ld_32x32(tbase + c0 + 64, accA);
+                if (c0 + 64 < HALF) tmem_ld_32x32(tbase + c0 + 64, accA);
                 process(accB, c0 + 32);
             }
             if (warp == 0) RC2_TRACE(14, nj);
-            if (live) d.psum[(b * 2 + dst) * NT + (n0 >> 7) + h] = (rs0.x + rs0.y) + (rs1.x + rs1.y);
+            if (live) d.psum[(b * 2 + dst) * NTq + ((nh + HALF - 64) >> 6)] = (rs0.x + rs0.y) + (rs1.x + rs1.y);
             // accumulator a may be overwritten: one arrival per epilogue warp, on the LEADER's barrier
             tc_fence_before();
             __syncwarp();
@@ -1155,13 +1165,13 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
 #undef RC2_TRACE
 }
 
-template <bool GAUSS, bool BF16>
+template <bool GAUSS, bool BF16, int BN>
 __global__ void __launch_bounds__(320, 1)
 tc_recursion2_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_constant__ CUtensorMap mapXf1,
                      const __grid_constant__ CUtensorMap mapXb0, const __grid_constant__ CUtensorMap mapXb1,
                      const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df, TcDir db,
                      TcEmis em, int64_t B, int64_t T, int N, int mtiles, int ndir, uint32_t *done, long long *trace) {
-    tc_recursion2_body<GAUSS, BF16, false>(mapXf0, mapXf1, mapXb0, mapXb1, mapMf, mapMb, df, db, em, B, T, N, mtiles, ndir, done, trace);
+    tc_recursion2_body<GAUSS, BF16, false, BN>(mapXf0, mapXf1, mapXb0, mapXb1, mapMf, mapMb, df, db, em, B, T, N, mtiles, ndir, done, trace);
 }
 template <bool GAUSS, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
@@ -1169,12 +1179,13 @@ tc_recursion2_pair_kernel(const __grid_constant__ CUtensorMap mapXf0, const __gr
                           const __grid_constant__ CUtensorMap mapXb0, const __grid_constant__ CUtensorMap mapXb1,
                           const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df, TcDir db,
                           TcEmis em, int64_t B, int64_t T, int N, int mtiles, int ndir, uint32_t *done, long long *trace) {
-    tc_recursion2_body<GAUSS, BF16, true>(mapXf0, mapXf1, mapXb0, mapXb1, mapMf, mapMb, df, db, em, B, T, N, mtiles, ndir, done, trace);
+    tc_recursion2_body<GAUSS, BF16, true, 256>(mapXf0, mapXf1, mapXb0, mapXb1, mapMf, mapMb, df, db, em, B, T, N, mtiles, ndir, done, trace);
 }
 
 // step 0: W_0 = start . b(o_first): start = pi (forward, t = 0) or ones (backward, t = T-1)
 template <bool GAUSS, bool BF16 = false>
-__global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__restrict__ pi, int64_t B, int64_t T, int N) {
+__global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__restrict__ pi, int64_t B, int64_t T, int N, int psg) {
+    // psg: columns per partial-row-sum slot (128 for the per-step kernels, 64 for the whole-recursion kernel)
     const int dir = blockIdx.y;
     const TcDir d = dir ? db : df;
     const int64_t b = blockIdx.x;
@@ -1206,7 +1217,14 @@ __global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__res
         __syncthreads();
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
         __syncthreads();
-        if (threadIdx.x == 0) d.psum[(b * 2 + 0) * NT + nt] = red[0] + red[1] + red[2] + red[3];
+        if (threadIdx.x == 0) {
+            if (psg == 64) {
+                d.psum[(b * 2 + 0) * (2 * NT) + 2 * nt] = red[0] + red[1];
+                d.psum[(b * 2 + 0) * (2 * NT) + 2 * nt + 1] = red[2] + red[3];
+            } else {
+                d.psum[(b * 2 + 0) * NT + nt] = red[0] + red[1] + red[2] + red[3];
+            }
+        }
     }
     if (threadIdx.x == 0) d.logacc[b] = 0.0;
 }
@@ -1243,7 +1261,8 @@ static size_t tc_workspace_floats(int64_t B, int N) {
     int64_t Bp = (B + TC_BM - 1) / TC_BM * TC_BM;
     // per direction: W [Bp][2][N], psum [Bp][2][NT], logacc [Bp] doubles (2 floats each)
     // + per-chain completion counters of the whole-recursion kernel (2 directions x row tiles)
-    return (size_t)2 * ((size_t)Bp * 2 * N + (size_t)Bp * 2 * NT + (size_t)Bp * 2) + (size_t)2 * N * N + 2 * (size_t)(Bp / TC_BM) + 64;
+    // (row sums per 64 columns in the whole-recursion kernel: 2 NT slots)
+    return (size_t)2 * ((size_t)Bp * 2 * N + (size_t)Bp * 2 * 2 * NT + (size_t)Bp * 2) + (size_t)2 * N * N + 2 * (size_t)(Bp / TC_BM) + 64;
 }
 
 static long long *g_rc_trace = nullptr;
@@ -1268,28 +1287,37 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
     TcDir d[2];
     for (int k = 0; k < 2; k++) {
         d[k].W = p;      p += (size_t)Bp * 2 * N;
-        d[k].psum = p;   p += (size_t)Bp * 2 * NT;
+        d[k].psum = p;   p += (size_t)Bp * 2 * 2 * NT;
         d[k].logacc = (double *)p; p += (size_t)Bp * 2;
     }
     float *Ar = p;  p += (size_t)N * N;     // tf32-rounded copies of A and AT
     float *ATr = p; p += (size_t)N * N;
     uint32_t *done = (uint32_t *)p; p += 2 * (size_t)(Bp / TC_BM);
     const int ndir = loglik_bwd ? 2 : 1;
-    if (bf16) {
-        int dev = 0, coop = 0;
+    int coop = 0;
+    {
+        int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        if (!(N % 256 == 0 && coop && (Bp / TC_BM) * (N / 256) * ndir >= sm_count())) {
-            set_error("fwdbwd_loglik_tc: bf16 operands need N %% 256 == 0 and at least one job per SM");
+    }
+    // KHMM_RC_MODE (development switch): 1 = first-generation kernels, 2 = whole-recursion kernel, second generation, on
+    // single CTAs, 3 = on CTA pairs where the shape allows.  Measured at c5 (B = 4096, T = 1024, N = 1024): bf16 17.5 ms
+    // single / 17.9 ms pairs; tf32 ~29 ms single / 25.8 ms pairs
+    int rc_mode = KHMM_RC2 ? ((KHMM_RC2_PAIR && !bf16) ? 3 : 2) : 1;
+    if (const char *e = getenv("KHMM_RC_MODE")) rc_mode = atoi(e);
+    const bool use_rc2 = coop && rc_mode >= 2;         // any N % 128 == 0, any batch: one launch for all T-1 steps
+    if (bf16) {
+        if (!use_rc2 && !(N % 256 == 0 && coop && (Bp / TC_BM) * (N / 256) * ndir >= sm_count())) {
+            set_error("fwdbwd_loglik_tc: bf16 operands need a device with cooperative launch");
             return KHMM_ERR_UNSUPPORTED;
         }
         tc_to_bf16_kernel<<<64, 256, 0, st>>>(A, (__nv_bfloat16 *)Ar, N * N);
         tc_to_bf16_kernel<<<64, 256, 0, st>>>(AT, (__nv_bfloat16 *)ATr, N * N);
-        tc_init_kernel<GAUSS, true><<<dim3((unsigned)B, ndir), 128, 0, st>>>(d[0], d[1], em, pi, B, T, N);
+        tc_init_kernel<GAUSS, true><<<dim3((unsigned)B, ndir), 128, 0, st>>>(d[0], d[1], em, pi, B, T, N, use_rc2 ? 64 : 128);
     } else {
         tc_round_matrix_kernel<<<64, 256, 0, st>>>(A, Ar, N * N);
         tc_round_matrix_kernel<<<64, 256, 0, st>>>(AT, ATr, N * N);
-        tc_init_kernel<GAUSS, false><<<dim3((unsigned)B, ndir), 128, 0, st>>>(d[0], d[1], em, pi, B, T, N);
+        tc_init_kernel<GAUSS, false><<<dim3((unsigned)B, ndir), 128, 0, st>>>(d[0], d[1], em, pi, B, T, N, use_rc2 ? 64 : 128);
     }
     KHMM_LAUNCH_CHECK("tc_init_kernel");
     // tensor maps: the W buffer [Bp][2][N] is addressed as a 2-D matrix whose row b is (b, slot):
@@ -1333,32 +1361,24 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
         return KHMM_ERR_CUDA;
     }
     const bool pair = KHMM_TC_PAIR && BN == 256 && ((Bp / TC_BM) % 2 == 0);
-    int coop = 0;
-    if ((KHMM_TC_WHOLE || bf16) && BN == 256) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    }
-    // KHMM_RC_MODE (development switch): 1 = first-generation whole-recursion kernel, 2 = second generation on
-    // single CTAs, 3 = second generation on CTA pairs (default when the row-tile count is even)
-    // measured at c5 (B = 4096, T = 1024, N = 1024): bf16 17.5 ms single / 17.9 ms pairs; tf32 ~29 ms single / 25.8 ms pairs
-    int rc_mode = KHMM_RC2 ? ((KHMM_RC2_PAIR && !bf16) ? 3 : 2) : 1;
-    if (const char *e = getenv("KHMM_RC_MODE")) rc_mode = atoi(e);
-    if (coop && rc_mode >= 2) {
+    if (use_rc2) {
         const int mtiles = (int)(Bp / TC_BM);
-        bool rpair = rc_mode == 3 && mtiles % 2 == 0;
+        const bool rpair = rc_mode == 3 && BN == 256 && mtiles % 2 == 0;
         CUtensorMap mapH[2];
         if (rpair && (bf16 ? (make_tmap_bf16_rowmajor(&mapH[0], ATr, N, N, 128) || make_tmap_bf16_rowmajor(&mapH[1], Ar, N, N, 128))
                            : (make_tmap_f32_rowmajor(&mapH[0], ATr, N, N, 128) || make_tmap_f32_rowmajor(&mapH[1], Ar, N, N, 128)))) {
             set_error("tensor map creation for the transition matrix failed");
             return KHMM_ERR_CUDA;
         }
-        const size_t smem = (rpair ? (size_t)TcRBars<true>::STAGES * (TC_TILE_BYTES + 128 * 128) : (size_t)TcRBars<false>::STAGES * (TC_TILE_BYTES + 256 * 128)) +
-                            2 * (size_t)TC_TILE_BYTES + sizeof(TcRBars<true>) + 16 + 3 * (size_t)N * sizeof(float) + 1024;
+        const size_t ring = rpair ? (size_t)TcRBars<true, 256>::STAGES * (TC_TILE_BYTES + 128 * 128)
+                                  : (BN == 256 ? (size_t)TcRBars<false, 256>::STAGES * (TC_TILE_BYTES + 256 * 128)
+                                               : (size_t)TcRBars<false, 128>::STAGES * (TC_TILE_BYTES + 128 * 128));
+        const size_t smem = ring + 2 * (size_t)TC_TILE_BYTES + sizeof(TcRBars<true, 256>) + 16 + 3 * (size_t)N * sizeof(float) + 1024;
         void *kern = rpair ? (bf16 ? (void *)tc_recursion2_pair_kernel<GAUSS, true> : (void *)tc_recursion2_pair_kernel<GAUSS, false>)
-                           : (bf16 ? (void *)tc_recursion2_kernel<GAUSS, true> : (void *)tc_recursion2_kernel<GAUSS, false>);
+                   : BN == 256 ? (bf16 ? (void *)tc_recursion2_kernel<GAUSS, true, 256> : (void *)tc_recursion2_kernel<GAUSS, false, 256>)
+                               : (bf16 ? (void *)tc_recursion2_kernel<GAUSS, true, 128> : (void *)tc_recursion2_kernel<GAUSS, false, 128>);
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int nlanes = (rpair ? mtiles / 2 : mtiles) * (N / 256) * ndir;
+        const int nlanes = (rpair ? mtiles / 2 : mtiles) * (N / BN) * ndir;
         int walkers = rpair ? sm_count() / 2 : sm_count();
         if (rpair) {
             // every CTA pair must be resident at once: ask how many clusters of two the device can hold
@@ -1388,7 +1408,7 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
             le = cudaLaunchKernel(kern, dim3(grid), dim3(320), args, smem, st);
         }
         KHMM_CUDA_CHECK(le);
-    } else if (coop) {
+    } else if (coop && (KHMM_TC_WHOLE || bf16) && BN == 256) {
         // one cooperative launch for all T-1 steps
         const int mtiles = (int)(Bp / TC_BM);
         const int nlanes = mtiles * (N / 256) * ndir;

@@ -589,5 +589,25 @@ def test_tensor_core_loglik_bf16_operands(K):
     np.testing.assert_allclose(llb.cpu().numpy()[:256], ref, rtol=1e-4)
     ll_tf, _ = h.log_likelihood_batch(torch.from_numpy(x).cuda())
     assert not np.array_equal(ll.cpu().numpy(), ll_tf.cpu().numpy())          # it really is another arithmetic
-    small, _ = h.log_likelihood_batch(torch.from_numpy(x[:256]).cuda(), tensor_cores="bf16")   # too few jobs -> tf32
-    np.testing.assert_allclose(small.cpu().numpy(), ref, rtol=2e-5)
+    small, _ = h.log_likelihood_batch(torch.from_numpy(x[:256]).cuda(), tensor_cores="bf16")   # few jobs: 128-wide tiles
+    np.testing.assert_allclose(small.cpu().numpy(), ref, rtol=1e-4)
+    np.testing.assert_array_equal(small.cpu().numpy(), ll.cpu().numpy()[:256])  # a row does not depend on the batch shape
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,B,T", [(128, 200, 12), (384, 200, 12), (1024, 512, 8), (256, 70, 9)])
+@pytest.mark.parametrize("mode", [True, "bf16"])
+def test_tensor_core_loglik_small_batches(K, N, B, T, mode):
+    """Whole-recursion kernel on shapes with fewer jobs than SMs (a strong-scaling shard of config 5 is B = 512),
+    N not a multiple of 256 (128-wide column tiles) and ragged last row tiles, against the float64 oracle."""
+    import torch
+    np.random.seed(101 + N)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(102 + B)
+    x = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T))).astype(np.float32)
+    ll, llb = h.log_likelihood_batch(torch.from_numpy(x).cuda(), tensor_cores=mode)
+    ref = O.loglik(O.forward(pi, A, O.emissions_gaussian_1d(mean, sd, x.astype(np.float64)))[1])
+    tol = 2e-4 if mode == "bf16" else 5e-5
+    np.testing.assert_allclose(ll.cpu().numpy(), ref, rtol=tol)
+    np.testing.assert_allclose(llb.cpu().numpy(), ref, rtol=tol)
