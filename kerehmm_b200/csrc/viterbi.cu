@@ -13,6 +13,7 @@
 // memory when it fits, else through L1/L2.  Backpointers go to HBM as uint8 (N <= 256) or uint16,
 // one coalesced N-byte row per (sequence, step).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace khmm {
 
@@ -266,6 +267,272 @@ static int launch_viterbi_tile(int64_t B, int64_t T, int M, const double *logpi,
     return KHMM_OK;
 }
 
+// ------------------------------------------------------------------ float32-screened kernel (N = 32, 64)
+// The register-tile kernel spends five instructions per transition (DADD, DSETP, two FSEL, SEL) on the half-rate
+// FP64 / ALU pipes.  Almost all of that work decides something a float32 comparison already decides: which source
+// state wins.  This kernel finds the winner in float32 and evaluates ONLY the winner in float64:
+//
+//   x_i  = delta[i] - R,  R = fl32(max_i delta[i])   (float64 subtraction, once per source and step; <= 2^-24 |R|)
+//   s_ij = fl32( fl32(x_i) + fl32(logA[i][j]) ) (screen value of the candidate  v_ij = fl64(delta[i] + logA[i][j]))
+//   p_gj = max of s_ij over the four sources of group g,  m_j = max_g p_gj
+//                                               (packed FADD2 + 5/8 max instruction per transition)
+//   the GROUPS with  p_gj > m_j - D_j  are counted and their indices summed with two FMA-pipe instructions per
+//   group ( c = fma.sat(p, 2^100, -thr 2^100) in {0, 1};  acc += c (g + 256) ).
+//
+// |s_ij - (v_ij - max delta)| <= 2^-23 (|s_ij| + 2 max(0, max logA)) (1 + 2^-22) + 2^-52 (|max delta| + |v_ij|): three
+// float32 roundings of quantities bounded by |x_i| + |logA_ij|, plus the float64 roundings of x_i and v_ij.  With
+// D_j = 2^-20 (|m_j| + 2 max(0, max logA)) + 2^-48 |max delta| + 2^-60 -- four times the sum of the two error bounds --
+// every source that attains the float64 maximum passes the filter, and so does its group.  If exactly ONE group
+// passes, all maximisers are among its four sources: those four are evaluated in float64 in index order with the
+// reference's strict compare, so delta_t[j] and psi_t[j] are bit-identical to abstract_hmm.py:227-230.  Otherwise
+// (a near-tie between groups, -inf rows, a threshold too close to zero) the lane runs the reference's float64
+// loop over all sources with the first-index rule.  A warp that needed the float64 loop three steps
+// in a row stops screening and re-probes after 16 steps, so tie-heavy models (left-to-right, uniform rows) cost
+// ~6 % extra instead of a wasted screen per step.
+//
+// Mapping: one WARP per sequence (no CTA barriers in the time loop), 16 warps per CTA, lane l owns targets l, l+32;
+// fl32(logA) in shared memory grouped by four sources (one conflict-free LDS.128 per group and target), the float64
+// logA and the delta rows in shared memory for the exact evaluations.
+#ifndef KHMM_VIT_AREG
+#define KHMM_VIT_AREG 1       /* 1: fl32(logA) in registers, 8 warps per CTA; 0: in shared memory, 16 warps (measured 221 vs 209 ms at c3) */
+#endif
+constexpr bool kVitAReg = KHMM_VIT_AREG != 0;
+#ifndef KHMM_VIT_WARPS
+#define KHMM_VIT_WARPS 8       /* 9+ warps leave 168 registers per thread (three warps on one scheduler): 320-390 ms instead of 187 ms */
+#endif
+constexpr int kVitScreenWarps = kVitAReg ? KHMM_VIT_WARPS : 16;
+template <int NN, typename PSI>
+__global__ void __launch_bounds__(32 * kVitScreenWarps, 1)
+viterbi_screen_kernel(int64_t B, int64_t T, int M, const double *__restrict__ logpi, const double *__restrict__ logA,
+                      const double *__restrict__ logBsm, const void *__restrict__ obs, int obs_dtype,
+                      const int32_t *__restrict__ lengths, PSI *__restrict__ psi, int32_t *__restrict__ last_state,
+                      double *__restrict__ logp) {
+    constexpr int JT = NN / 32, WARPS = kVitScreenWarps;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *A64 = reinterpret_cast<double *>(smem_raw);                 // [NN][NN]
+    double *drow = A64 + NN * NN;                                       // [WARPS][NN]  delta_{t-1}, float64
+    float *dlrow = reinterpret_cast<float *>(drow + WARPS * NN);        // [WARPS][NN]  fl32(delta - R)
+    float4 *A32g = reinterpret_cast<float4 *>(dlrow + WARPS * NN);      // [NN/4][NN]   fl32(logA[4g .. 4g+3][j])
+    __shared__ float apos_red[WARPS];
+    float ap = 0.f;                                                     // max(0, largest finite logA), rounded up
+    for (int k = threadIdx.x; k < NN * NN; k += blockDim.x) {
+        const double v = logA[k];
+        A64[k] = v;
+        if (v > 0.0 && v < 1e300) ap = fmaxf(ap, __double2float_ru(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ap = fmaxf(ap, __shfl_xor_sync(0xffffffffu, ap, o));
+    if ((threadIdx.x & 31) == 0) apos_red[threadIdx.x >> 5] = ap;
+    __syncthreads();
+    ap = apos_red[0];
+#pragma unroll
+    for (int k = 1; k < WARPS; k++) ap = fmaxf(ap, apos_red[k]);
+    const float apos2 = 2.f * ap;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    float4 a4r[kVitAReg ? JT : 1][kVitAReg ? NN / 4 : 1];      // register copy: a4r[q][g] = fl32(logA[4g .. 4g+3][l + 32 q])
+    if (kVitAReg) {
+#pragma unroll
+        for (int q = 0; q < JT; q++)
+#pragma unroll
+            for (int g = 0; g < NN / 4; g++) {
+                const int j = l + 32 * q;
+                a4r[kVitAReg ? q : 0][kVitAReg ? g : 0] = make_float4((float)A64[(4 * g) * NN + j], (float)A64[(4 * g + 1) * NN + j],
+                                                                      (float)A64[(4 * g + 2) * NN + j], (float)A64[(4 * g + 3) * NN + j]);
+            }
+    } else {
+        for (int k = threadIdx.x; k < (NN / 4) * NN; k += blockDim.x) {
+            const int g = k / NN, j = k % NN;
+            A32g[k] = make_float4((float)A64[(4 * g) * NN + j], (float)A64[(4 * g + 1) * NN + j], (float)A64[(4 * g + 2) * NN + j],
+                                  (float)A64[(4 * g + 3) * NN + j]);
+        }
+        __syncthreads();
+    }
+    double lp[JT];
+#pragma unroll
+    for (int q = 0; q < JT; q++) lp[q] = logpi[l + 32 * q];
+    double *dw = drow + w * NN;
+    float *dlw = dlrow + w * NN;
+    const float BIG = 0x1p100f;
+    const float FINF = __int_as_float(0x7f800000);
+
+    for (int64_t b = (int64_t)blockIdx.x * WARPS + w; b < B; b += (int64_t)gridDim.x * WARPS) {
+        const int len = lengths ? lengths[b] : (int)T;
+        if (len <= 0) continue;
+        double d[JT];
+        {
+            int sym = load_symbol(obs, obs_dtype, b * T);
+            sym = sym < 0 ? 0 : (sym >= M ? M - 1 : sym);
+#pragma unroll
+            for (int q = 0; q < JT; q++) d[q] = lp[q] + __ldg(logBsm + (int64_t)sym * NN + l + 32 * q);
+        }
+        int exact_until = 0, streak = 0;       // steps < exact_until skip the screen
+        // the symbol of step t+2 and the emission row of step t+1 are requested during step t (both are L2 latencies)
+        auto symbol_at = [&](int tt) {
+            int sy = load_symbol(obs, obs_dtype, b * T + (tt < len ? tt : len - 1));
+            return sy < 0 ? 0 : (sy >= M ? M - 1 : sy);
+        };
+        double e_next[JT];
+        {
+            const int s1 = symbol_at(1);
+#pragma unroll
+            for (int q = 0; q < JT; q++) e_next[q] = __ldg(logBsm + (int64_t)s1 * NN + l + 32 * q);
+        }
+        int sym_next = symbol_at(2);
+        for (int t = 1; t < len; t++) {
+            double e[JT];
+#pragma unroll
+            for (int q = 0; q < JT; q++) {
+                e[q] = e_next[q];
+                e_next[q] = __ldg(logBsm + (int64_t)sym_next * NN + l + 32 * q);
+            }
+            sym_next = symbol_at(t + 2);
+            // reference level R = fl32(max of the previous row): one integer warp reduction on the order-preserving
+            // integer image of the float32 values (the screen only needs delta - R to be small near the top)
+            float lf = (float)d[0];
+#pragma unroll
+            for (int q = 1; q < JT; q++) lf = fmaxf(lf, (float)d[q]);
+            int key = __float_as_int(lf);
+            key = key >= 0 ? key : key ^ 0x7fffffff;
+            key = __reduce_max_sync(0xffffffffu, key);
+            key = key >= 0 ? key : key ^ 0x7fffffff;
+            const float Rf = __int_as_float(key);
+            const double dmax = (double)Rf;
+            const bool screen = t >= exact_until && Rf > -FINF && Rf < FINF;
+            __syncwarp();                      // the previous step's readers are done with dw / dlw
+#pragma unroll
+            for (int q = 0; q < JT; q++) {
+                dw[l + 32 * q] = d[q];
+                if (screen) dlw[l + 32 * q] = (float)(d[q] - dmax);
+            }
+            __syncwarp();
+            double best[JT];
+            int arg[JT];
+            bool done_q[JT];
+#pragma unroll
+            for (int q = 0; q < JT; q++) { done_q[q] = false; best[q] = 0.0; arg[q] = 0; }
+            if (screen) {
+                // max delta - R <= 2^-24 |R|: the x_i may be that much above zero, which adds twice that to the bound on
+                // |x_i| + |logA_ij| in terms of |s_ij| (see the header)
+                const float apx = fmaf(fabsf(Rf), 0x1p-22f, apos2);
+                const float dmx_term = fmaf(fabsf(Rf), 0x1p-48f, 0x1p-60f) * 1.0000002f;
+#pragma unroll
+                for (int q = 0; q < JT; q++) {
+                    // group maxima p[g] = max of the four screen values of sources 4g .. 4g+3 (two packed adds, two max
+                    // instructions per group); only the groups are thresholded, the winning group is resolved in float64
+                    float p[NN / 4];
+                    float m0 = -FINF, m1 = m0;
+#pragma unroll
+                    for (int g = 0; g < NN / 4; g++) {
+                        const float4 x4 = *reinterpret_cast<const float4 *>(dlw + 4 * g);
+                        const float4 a4 = kVitAReg ? a4r[kVitAReg ? q : 0][kVitAReg ? g : 0] : A32g[g * NN + l + 32 * q];
+                        const float2 s01 = __fadd2_rn(make_float2(x4.x, x4.y), make_float2(a4.x, a4.y));
+                        const float2 s23 = __fadd2_rn(make_float2(x4.z, x4.w), make_float2(a4.z, a4.w));
+                        float pg = s01.x;
+                        asm("max.f32 %0, %0, %1, %2;" : "+f"(pg) : "f"(s01.y), "f"(s23.x));
+                        p[g] = fmaxf(pg, s23.y);
+                    }
+#pragma unroll
+                    for (int g = 0; g < NN / 4; g += 4) {
+                        asm("max.f32 %0, %0, %1, %2;" : "+f"(m0) : "f"(p[g]), "f"(p[g + 1]));
+                        asm("max.f32 %0, %0, %1, %2;" : "+f"(m1) : "f"(p[g + 2]), "f"(p[g + 3]));
+                    }
+                    const float m = fmaxf(m0, m1);
+                    const float dlt = fmaf(fabsf(m) + apx, 0x1p-20f, dmx_term);
+                    const float thr = m - dlt;
+                    const float nthrB = -thr * BIG;
+                    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                    for (int g = 0; g < NN / 4; g += 2) {
+                        float c0, c1;
+                        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(c0) : "f"(p[g]), "f"(BIG), "f"(nthrB));
+                        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(c1) : "f"(p[g + 1]), "f"(BIG), "f"(nthrB));
+                        acc0 = fmaf(c0, (float)(g + 256), acc0);
+                        acc1 = fmaf(c1, (float)(g + 257), acc1);
+                    }
+                    const float acc = acc0 + acc1;
+                    // exactly one group above the threshold (and a threshold far enough from zero for c to be 0 or 1):
+                    // every source that attains the float64 maximum is in that group -- evaluate its four sources exactly
+                    if (acc >= 256.f && acc < 512.f && fabsf(thr) >= 0x1p-60f) {
+                        const int k = ((int)acc - 256) * 4;
+                        const int j = l + 32 * q;
+                        double bb = dw[k] + A64[k * NN + j];
+                        int ba = k;
+#pragma unroll
+                        for (int e2 = 1; e2 < 4; e2++) {
+                            const double v = dw[k + e2] + A64[(k + e2) * NN + j];
+                            if (v > bb) { bb = v; ba = k + e2; }
+                        }
+                        arg[q] = ba;
+                        best[q] = bb;
+                        done_q[q] = true;
+                    }
+                }
+            }
+            bool all_done = true;
+#pragma unroll
+            for (int q = 0; q < JT; q++) all_done = all_done && done_q[q];
+            if (!__all_sync(0xffffffffu, all_done)) {
+                // the reference's loop, float64, first index wins ties (abstract_hmm.py:227-230)
+#pragma unroll
+                for (int q = 0; q < JT; q++) {
+                    if (!done_q[q]) {
+                        double bb = dw[0] + A64[l + 32 * q];
+                        int ba = 0;
+#pragma unroll 4
+                        for (int i = 1; i < NN; i++) {
+                            const double v = dw[i] + A64[i * NN + l + 32 * q];
+                            if (v > bb) { bb = v; ba = i; }
+                        }
+                        best[q] = bb;
+                        arg[q] = ba;
+                    }
+                }
+                // three steps in a row needed the float64 loop: stop screening for 16 steps
+                if (screen && ++streak >= 3) { exact_until = t + 16; streak = 0; }
+            } else {
+                streak = 0;
+            }
+#pragma unroll
+            for (int q = 0; q < JT; q++) {
+                psi[(b * T + t) * NN + l + 32 * q] = (PSI)arg[q];
+                d[q] = best[q] + e[q];
+            }
+        }
+        // termination: first-index argmax over the final row (abstract_hmm.py:233,235)
+        double m = d[0];
+        int am = l;
+#pragma unroll
+        for (int q = 1; q < JT; q++)
+            if (d[q] > m) { m = d[q]; am = l + 32 * q; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double om = __shfl_xor_sync(0xffffffffu, m, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+            if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+        }
+        if (l == 0) {
+            last_state[b] = am;
+            logp[b] = m;
+        }
+    }
+}
+
+template <int NN, typename PSI>
+static int launch_viterbi_screen(int64_t B, int64_t T, int M, const double *logpi, const double *logA, const double *logBsm,
+                                 const void *obs, int obs_dtype, const int32_t *lengths, PSI *psi, int32_t *last,
+                                 double *logp, cudaStream_t st) {
+    auto kern = viterbi_screen_kernel<NN, PSI>;
+    const size_t smem = sizeof(double) * (NN * NN + kVitScreenWarps * NN) + sizeof(float) * kVitScreenWarps * NN + sizeof(float) * NN * NN;
+    if (smem > 48 * 1024) KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    KHMM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * kVitScreenWarps, smem));
+    if (occ < 1) occ = 1;
+    const int64_t nblk = (B + kVitScreenWarps - 1) / kVitScreenWarps, cap = (int64_t)sm_count() * occ;   // persistent: one resident wave of warps
+    kern<<<(int)(nblk < cap ? nblk : cap), 32 * kVitScreenWarps, smem, st>>>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp);
+    KHMM_LAUNCH_CHECK("viterbi_screen_kernel");
+    return KHMM_OK;
+}
+
 // One thread per sequence chases the backpointers: path[t] = psi[t+1][path[t+1]] (:236-237).
 template <typename PSI, typename OUT>
 __global__ void viterbi_backtrace_kernel(int64_t B, int64_t T, int N, const int32_t *__restrict__ lengths,
@@ -299,7 +566,12 @@ static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, 
     size_t off = (((size_t)B * sizeof(int32_t)) + 255) / 256 * 256;
     PSI *psi = reinterpret_cast<PSI *>(reinterpret_cast<unsigned char *>(backptr) + off);
     int rc_tile = -1;
-    if (sizeof(PSI) == 1 && B >= 64) {   // register-tile kernels (small batches stay on the generic kernel)
+    static const bool use_screen = !(getenv("KHMM_VIT_SCREEN") && atoi(getenv("KHMM_VIT_SCREEN")) == 0);   // development switch
+    if (sizeof(PSI) == 1 && B >= 64 && use_screen && (N == 32 || N == 64)) {
+        // float32-screened warp-per-sequence kernel
+        if (N == 32) rc_tile = launch_viterbi_screen<32, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+        else rc_tile = launch_viterbi_screen<64, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+    } else if (sizeof(PSI) == 1 && B >= 64) {   // register-tile kernels (small batches stay on the generic kernel)
         if (N == 32) rc_tile = launch_viterbi_tile<32, 4, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
         else if (N == 64) rc_tile = launch_viterbi_tile<64, 4, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
         else if (N == 128) rc_tile = launch_viterbi_tile<128, 2, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);

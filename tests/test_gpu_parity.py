@@ -216,6 +216,53 @@ def test_viterbi_register_tile_kernels_ragged(K, N):
             assert logp[b] == rl
 
 
+@pytest.mark.parametrize("kind", ["near_ties", "uniform", "left_to_right", "long", "unnormalised", "banded"])
+@pytest.mark.parametrize("N", [32, 64])
+def test_viterbi_screened_kernel_adversarial(K, N, kind):
+    """The float32-screened kernel (N in {32, 64}, B >= 64) must stay bit-exact where float32 cannot decide:
+    transition rows that differ in the 9th digit only, exact ties everywhere, -inf rows and columns, |delta| ~ 1e4
+    (long sequences), log A > 0 (unnormalised rows) and banded matrices (most candidates -inf)."""
+    M, B, T = 16, 70, 60
+    rng = np.random.default_rng(1000 + N)
+    A = rng.random((N, N)) + 0.1
+    A /= A.sum(axis=1, keepdims=True)
+    Bm = rng.random((N, M)) + 0.05
+    Bm /= Bm.sum(axis=1, keepdims=True)
+    pi = rng.random(N)
+    pi /= pi.sum()
+    if kind == "near_ties":
+        base = rng.random(N) + 0.5
+        A = np.tile(base / base.sum(), (N, 1)) * (1.0 + 1e-9 * rng.standard_normal((N, N)))   # float32-identical columns
+        Bm = np.tile(Bm[0], (N, 1)) * (1.0 + 1e-10 * rng.standard_normal((N, M)))
+    elif kind == "uniform":
+        A = np.full((N, N), 1.0 / N)
+        Bm = np.full((N, M), 1.0 / M)
+        pi = np.full(N, 1.0 / N)
+    elif kind == "left_to_right":
+        A = np.zeros((N, N))
+        for i in range(N):
+            A[i, i] = 0.5
+            A[i, min(i + 1, N - 1)] += 0.5
+        pi = np.zeros(N)
+        pi[0] = 1.0
+    elif kind == "long":
+        T = 3000
+        B = 64
+    elif kind == "unnormalised":
+        A = A * 50.0                                             # log A > 0 for many entries
+    elif kind == "banded":
+        mask = np.abs(np.subtract.outer(np.arange(N), np.arange(N))) <= 2
+        A = np.where(mask, A, 0.0)
+        A /= A.sum(axis=1, keepdims=True)
+    h = discrete_model(K, pi, A, Bm)
+    obs = rng.integers(0, M, size=(B, T)).astype(np.uint8)
+    path, logp = h.viterbi_batch(obs)
+    with np.errstate(divide="ignore"):
+        rp, rl = O.viterbi(pi, A, Bm, obs.astype(np.int64))
+    assert np.array_equal(path, rp)
+    assert np.array_equal(logp, rl)
+
+
 def test_viterbi_with_zero_probabilities(K):
     """log(0) = -inf entries; -inf columns resolve to index 0."""
     N, M = 5, 4
