@@ -256,7 +256,7 @@ def run_ours(args):
         launches_per_step = 2
         algo_bytes = B * T * (1 + N + 1 + 1)         # obs + N backpointer bytes written + 1 read + path byte
         h2d, d2h = B * T, B * T + B * 8
-        dominant = "viterbi_generic_kernel<uint8>"
+        dominant = "viterbi_screen_kernel<64, uint8> (float32 screen, float64 resolve) + viterbi_backtrace_kernel"
         l2_note = "backpointer workspace 17 GB per step (>> L2)"
         dtype = "f64"
     elif kind == "c4":
@@ -418,12 +418,18 @@ def run_ours(args):
             "clocks": clocks,
         }
         if kind == "c3":
-            # 2 FP64-pipe instructions (DADD + DSETP) per transition; measured DADD rate 18.4e12/s (profiles/r1_microbench_pipes.json)
-            out["roofline"]["fp64_pipe"] = {"achieved_transitions_per_s": transitions / world / (ms_per_step * 1e-3),
-                                            "pipe_bound_transitions_per_s": 18.4e12 / 2,
-                                            "frac": transitions / world / (ms_per_step * 1e-3) / (18.4e12 / 2),
-                                            "note": "bit-exact float64 max-plus: FP64/ALU-issue bound, not HBM bound; "
-                                                    "the backpointer stream is 0.8 % of HBM (DESIGN.md 3.2)"}
+            # float32-screened kernel: 403 warp instructions per (sequence, step) = 3.15 per 32 transitions
+            # (ncu smsp__inst_executed, profiles/r1_ncu_c3_viterbi_screen_summary.csv); a scheduler issues one warp
+            # instruction per clock, 4 schedulers per SM.  The float64 register-tile kernel it replaces needs 2 FP64-pipe
+            # instructions per transition (measured DADD rate 18.4e12/s -> 9.2e12 transitions/s, profiles/r1_microbench_pipes.json).
+            ach = transitions / world / (ms_per_step * 1e-3)
+            issue_bound = 148 * 4 * 1.965e9 * 32 / 3.15
+            out["roofline"]["issue_slots"] = {"achieved_transitions_per_s": ach, "issue_bound_transitions_per_s": issue_bound,
+                                              "frac": ach / issue_bound, "warp_instructions_per_32_transitions": 3.15,
+                                              "fp64_pipe_bound_of_the_unscreened_kernel": 18.4e12 / 2,
+                                              "note": "bit-exact float64 Viterbi with a float32 screen: instruction-issue "
+                                                      "bound (2 warps per scheduler, 221 registers), not HBM bound; the "
+                                                      "backpointer stream is 1.4 % of HBM (DESIGN.md 3.2)"}
         if kind in ("c2",):
             flops = transitions / world * 4.0          # 2 (forward) + 2 (backward) flop per transition
             out["roofline"]["fp32_simt"] = {"achieved_tflops": flops / (ms_per_step * 1e-3) / 1e12,
