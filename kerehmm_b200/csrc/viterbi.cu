@@ -293,21 +293,30 @@ static int launch_viterbi_tile(int64_t B, int64_t T, int M, const double *logpi,
 // Mapping: one WARP per sequence (no CTA barriers in the time loop), 16 warps per CTA, lane l owns targets l, l+32;
 // fl32(logA) in shared memory grouped by four sources (one conflict-free LDS.128 per group and target), the float64
 // logA and the delta rows in shared memory for the exact evaluations.
-#ifndef KHMM_VIT_AREG
-#define KHMM_VIT_AREG 1       /* 1: fl32(logA) in registers, 8 warps per CTA; 0: in shared memory, 16 warps (measured 221 vs 209 ms at c3) */
+// fl32(logA) lives in REGISTERS for N <= 64 (8 warps per CTA; 9+ warps leave 168 registers per thread and spill:
+// 320-390 ms instead of 187 ms at c3) and in shared memory, grouped by four sources, for N = 128 (the same layout at
+// N = 64 measured 224-230 ms against 187 ms for the register copy and 349 ms for the float64 kernel).  8 warps per
+// CTA in both cases: at N = 128 sixteen warps leave 128 registers and spill (48.9 ms at B = 16384, T = 512, no
+// better than the float64 register-tile kernel's 47.7 ms); eight warps with 255 registers run 24.6 ms.
+#ifndef KHMM_VIT_AREG_MAX
+#define KHMM_VIT_AREG_MAX 64
 #endif
-constexpr bool kVitAReg = KHMM_VIT_AREG != 0;
-#ifndef KHMM_VIT_WARPS
-#define KHMM_VIT_WARPS 8       /* 9+ warps leave 168 registers per thread (three warps on one scheduler): 320-390 ms instead of 187 ms */
-#endif
-constexpr int kVitScreenWarps = kVitAReg ? KHMM_VIT_WARPS : 16;
+template <int NN>
+struct VitScreen {
+    static constexpr bool AREG = NN <= KHMM_VIT_AREG_MAX;
+    static constexpr int WARPS = 8;
+    static constexpr size_t smem_bytes() {
+        return sizeof(double) * (NN * NN + WARPS * NN) + sizeof(float) * WARPS * NN + (AREG ? 0 : sizeof(float) * NN * NN);
+    }
+};
 template <int NN, typename PSI>
-__global__ void __launch_bounds__(32 * kVitScreenWarps, 1)
+__global__ void __launch_bounds__(32 * VitScreen<NN>::WARPS, 1)
 viterbi_screen_kernel(int64_t B, int64_t T, int M, const double *__restrict__ logpi, const double *__restrict__ logA,
                       const double *__restrict__ logBsm, const void *__restrict__ obs, int obs_dtype,
                       const int32_t *__restrict__ lengths, PSI *__restrict__ psi, int32_t *__restrict__ last_state,
                       double *__restrict__ logp) {
-    constexpr int JT = NN / 32, WARPS = kVitScreenWarps;
+    constexpr int JT = NN / 32, WARPS = VitScreen<NN>::WARPS;
+    constexpr bool kVitAReg = VitScreen<NN>::AREG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *A64 = reinterpret_cast<double *>(smem_raw);                 // [NN][NN]
     double *drow = A64 + NN * NN;                                       // [WARPS][NN]  delta_{t-1}, float64
@@ -522,7 +531,8 @@ static int launch_viterbi_screen(int64_t B, int64_t T, int M, const double *logp
                                  const void *obs, int obs_dtype, const int32_t *lengths, PSI *psi, int32_t *last,
                                  double *logp, cudaStream_t st) {
     auto kern = viterbi_screen_kernel<NN, PSI>;
-    const size_t smem = sizeof(double) * (NN * NN + kVitScreenWarps * NN) + sizeof(float) * kVitScreenWarps * NN + sizeof(float) * NN * NN;
+    constexpr int kVitScreenWarps = VitScreen<NN>::WARPS;
+    const size_t smem = VitScreen<NN>::smem_bytes();
     if (smem > 48 * 1024) KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     KHMM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * kVitScreenWarps, smem));
@@ -567,10 +577,11 @@ static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, 
     PSI *psi = reinterpret_cast<PSI *>(reinterpret_cast<unsigned char *>(backptr) + off);
     int rc_tile = -1;
     static const bool use_screen = !(getenv("KHMM_VIT_SCREEN") && atoi(getenv("KHMM_VIT_SCREEN")) == 0);   // development switch
-    if (sizeof(PSI) == 1 && B >= 64 && use_screen && (N == 32 || N == 64)) {
+    if (sizeof(PSI) == 1 && B >= 64 && use_screen && (N == 32 || N == 64 || N == 128)) {
         // float32-screened warp-per-sequence kernel
         if (N == 32) rc_tile = launch_viterbi_screen<32, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
-        else rc_tile = launch_viterbi_screen<64, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+        else if (N == 64) rc_tile = launch_viterbi_screen<64, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+        else rc_tile = launch_viterbi_screen<128, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
     } else if (sizeof(PSI) == 1 && B >= 64) {   // register-tile kernels (small batches stay on the generic kernel)
         if (N == 32) rc_tile = launch_viterbi_tile<32, 4, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
         else if (N == 64) rc_tile = launch_viterbi_tile<64, 4, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
