@@ -829,7 +829,7 @@ struct __align__(8) TcRBars {
     // operand ring: 16 KB W tile + (BN or BN/2) x 128 B matrix tile per stage; 144-160 KB, next to 32 KB of output staging
     // and the 12 KB constant table
     static constexpr int STAGES = PAIR ? 5 : (BN == 256 ? 3 : 5);
-    uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    uint64_t full[STAGES], empty[STAGES], tmem_full[4], tmem_empty[4];
     uint32_t tmem_base;
 };
 #ifndef KHMM_RC2
@@ -872,6 +872,7 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
     constexpr int STAGES = TcRBars<PAIR, BN>::STAGES;
     constexpr int MROWS = PAIR ? BN / 2 : BN;                       // matrix-tile rows staged by this CTA
     constexpr int HALF = BN / 2;                                    // columns per epilogue warp (column half h)
+    constexpr int NACC = 512 / BN;                                  // accumulators in TMEM: the MMA thread may run NACC-1 jobs ahead
     constexpr int STAGE_BYTES = TC_TILE_BYTES + MROWS * 128;        // k-block rows are 128 bytes in both precisions
     constexpr int BKE = BF16 ? 64 : TC_BK;                          // elements per 128-byte k-block row
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -891,7 +892,7 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], PAIR ? 16 : 8); }
+        for (int a = 0; a < NACC; a++) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], PAIR ? 16 : 8); }
         fence_barrier_init();
     }
     if (GAUSS) {
@@ -977,8 +978,8 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
             const uint32_t idesc = BF16 ? make_idesc_bf16(PAIR ? 256 : TC_BM, BN) : make_idesc_tf32(PAIR ? 256 : TC_BM, BN);
             uint32_t it = 0;
             for (int64_t nj = 0; nj < myjobs; nj++) {
-                const int a = (int)(nj & 1);
-                mbar_wait(&bars->tmem_empty[a], (uint32_t)((nj >> 1) & 1) ^ 1);   // the epilogue(s) drained this accumulator
+                const int a = (int)(nj % NACC);
+                mbar_wait(&bars->tmem_empty[a], (uint32_t)((nj / NACC) & 1) ^ 1);   // the epilogue(s) drained this accumulator
                 RC2_TRACE(4, nj);
                 tc_fence_after();
                 for (int kb = 0; kb < nkb; kb++, it++) {
@@ -1009,7 +1010,7 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
         const int h = warp >> 2, wq = warp & 3;
         RcWalk jw(w, nlanes);
         for (int64_t nj = 0; nj < myjobs; nj++, jw.advance(nwalk)) {
-            const int a = (int)(nj & 1);
+            const int a = (int)(nj % NACC);
             int m0, n0, dir, chain;
             decode(jw.ln, m0, n0, dir, chain);
             const TcDir d = dir ? db : df;
@@ -1042,7 +1043,7 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
                 if (n0 == 0 && h == 0) __stcg(d.logacc + b, __ldcg(d.logacc + b) + log((double)c));
             }
             if (warp == 0) RC2_TRACE(9, nj);
-            mbar_wait(&bars->tmem_full[a], (uint32_t)((nj >> 1) & 1));
+            mbar_wait(&bars->tmem_full[a], (uint32_t)((nj / NACC) & 1));
             if (warp == 0) RC2_TRACE(10, nj);
             tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + a * BN + h * HALF;
@@ -1352,7 +1353,8 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
         }
     // 256-wide column tiles when N allows: 25 % less L2 operand traffic per MAC and half the CTAs
     // (small batches -- e.g. a strong-scaling shard -- keep 128-wide tiles so that more SMs get a CTA)
-    const int BN = (N % 256 == 0 && (Bp / TC_BM) * (N / 256) * ndir >= sm_count()) ? 256 : 128;
+    int BN = (N % 256 == 0 && (Bp / TC_BM) * (N / 256) * ndir >= sm_count()) ? 256 : 128;
+    if (const char *e = getenv("KHMM_RC_BN")) { if (atoi(e) == 128) BN = 128; }      // development switch
     // forward: out[j] = sum_i W[i] A[i][j]  -> B-operand rows j, K index i: AT[j][i]
     // backward: out[i] = sum_j A[i][j] w[j] -> B-operand rows i, K index j: A[i][j]
     if (bf16 ? (make_tmap_bf16_rowmajor(&mapM[0], ATr, N, N, BN) || make_tmap_bf16_rowmajor(&mapM[1], Ar, N, N, BN))
