@@ -576,7 +576,8 @@ static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, 
     size_t off = (((size_t)B * sizeof(int32_t)) + 255) / 256 * 256;
     PSI *psi = reinterpret_cast<PSI *>(reinterpret_cast<unsigned char *>(backptr) + off);
     int rc_tile = -1;
-    static const bool use_screen = !(getenv("KHMM_VIT_SCREEN") && atoi(getenv("KHMM_VIT_SCREEN")) == 0);   // development switch
+    const char *vs_env = getenv("KHMM_VIT_SCREEN");      // development / cross-check switch, read on every call
+    const bool use_screen = !(vs_env && atoi(vs_env) == 0);
     if (sizeof(PSI) == 1 && B >= 64 && use_screen && (N == 32 || N == 64 || N == 128)) {
         // float32-screened warp-per-sequence kernel
         if (N == 32) rc_tile = launch_viterbi_screen<32, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);

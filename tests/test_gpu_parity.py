@@ -566,6 +566,53 @@ def test_viterbi_config3_shape_properties(K):
     assert np.array_equal(p[:8], rp) and np.array_equal(logp[:8], rl)
 
 
+def test_viterbi_config3_full_size_two_kernels_agree(K):
+    """BASELINE config 3 at FULL size (65,536 sequences x 4,096 steps, N = 64, M = 256): the float32-screened kernel
+    and the plain float64 register-tile kernel -- two independent implementations of abstract_hmm.py:203-239 -- must
+    return the same paths and the same float64 log-probabilities, bit for bit; the oracle agrees on a sub-sample."""
+    import os
+    import torch
+    N, M, B, T = 64, 256, 65536, 4096
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=3)
+    obs = torch.from_numpy(np.random.default_rng(1003).integers(0, M, size=(B, T)).astype(np.uint8)).cuda()
+    old = os.environ.get("KHMM_VIT_SCREEN")
+    try:
+        os.environ["KHMM_VIT_SCREEN"] = "1"
+        p1, l1 = h.viterbi_batch(obs, path_dtype=torch.uint8)
+        os.environ["KHMM_VIT_SCREEN"] = "0"
+        p0, l0 = h.viterbi_batch(obs, path_dtype=torch.uint8)
+    finally:
+        if old is None:
+            os.environ.pop("KHMM_VIT_SCREEN", None)
+        else:
+            os.environ["KHMM_VIT_SCREEN"] = old
+    assert torch.equal(p1, p0) and torch.equal(l1, l0)
+    with np.errstate(divide="ignore"):
+        rp, rl = O.viterbi(pi, A, Bm, obs[:4].cpu().numpy().astype(np.int64))
+    assert np.array_equal(p1[:4].cpu().numpy(), rp) and np.array_equal(l1[:4].cpu().numpy(), rl)
+
+
+@pytest.mark.parametrize("mode,tol", [(True, 5e-6), ("bf16", 4e-5)])
+def test_fwdbwd_config5_full_size_properties(K, mode, tol):
+    """BASELINE config 5 at FULL size (GaussianHMM N = 1024, B = 4096, T = 1024) on the whole-recursion tensor-core
+    kernel: the forward and the (independent, self-scaled) backward recursion must give the same log-likelihood for
+    every sequence, and the float64 oracle agrees on a sub-sample (stated bounds: tf32 5e-6, bf16 4e-5 relative)."""
+    import torch
+    N, B, T = 1024, 4096, 1024
+    np.random.seed(5)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(1005)
+    x = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T))).astype(np.float32)
+    ll, llb = h.log_likelihood_batch(torch.from_numpy(x).cuda(), tensor_cores=mode)
+    ll, llb = ll.cpu().numpy(), llb.cpu().numpy()
+    assert np.isfinite(ll).all() and np.isfinite(llb).all()
+    np.testing.assert_allclose(ll, llb, rtol=tol)
+    ref = O.loglik(O.forward(pi, A, O.emissions_gaussian_1d(mean, sd, x[:8].astype(np.float64)))[1])
+    np.testing.assert_allclose(ll[:8], ref, rtol=tol)
+    np.testing.assert_allclose(llb[:8], ref, rtol=tol)
+
+
 def test_fwdbwd_config2_shape_properties(K):
     """N=8 Gaussian, T=2048 at a reduced batch: forward and backward likelihoods agree, and the
     oracle agrees on a sub-sample."""
