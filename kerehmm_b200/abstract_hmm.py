@@ -342,8 +342,9 @@ class AbstractHMM(object):
         """log P(O_b | model) for every sequence -> `(loglik, loglik_from_backward | None)`.
         float32, N <= 16: the fused forward+backward register kernel.  float32, N a multiple of 128
         (<= 1024), equal lengths and `tensor_cores=True`: the tcgen05 (tf32) recursion, forward and
-        backward together; `tensor_cores="bf16"` uses bf16 operands (twice the MMA rate; N % 256 == 0 and
-        large batches, else tf32).  Otherwise the generic forward kernel (second value None)."""
+        backward together in one cooperative launch; `tensor_cores="bf16"` uses bf16 operands (twice the MMA
+        rate, looser bound on short sequences -- DESIGN.md 3.4).  Otherwise the generic forward kernel (second
+        value None)."""
         real, p = self._real(dtype), self._params()
         t = engine.torch()
         if (real == t.float32 and lengths is None and p.N <= _lib.SMALL_N_MAX and p.kind in ("discrete", "gauss")):

@@ -613,6 +613,28 @@ def test_fwdbwd_config5_full_size_properties(K, mode, tol):
     np.testing.assert_allclose(llb[:8], ref, rtol=tol)
 
 
+def test_baumwelch_config4_full_size_properties(K):
+    """BASELINE config 4 at its FULL per-GPU size (DiscreteHMM N = 128, M = 1024, 131,072 sequences x 512 steps):
+    three independent implementations of the scaled forward recursion -- the fused tensor-core E-step, the
+    whole-recursion tensor-core log-likelihood kernel and the float32 SIMT forward kernel -- must agree on the
+    log-likelihood; the E-step's counts satisfy the identities of its definition."""
+    N, M, B, T = 128, 1024, 131072, 512
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=4)
+    obs = np.random.default_rng(1004).integers(0, M, size=(B, T)).astype(np.uint16)
+    c = h.estep_batch(obs, tensor_cores=True).host()
+    assert c["nseq"] == B and c["flags"] == 0
+    np.testing.assert_allclose(c["pi"].sum(), B, rtol=1e-5)                        # every smooth1d(gamma_0) sums to 1
+    np.testing.assert_allclose(c["emis_num"].sum(axis=1), c["emis_den"], rtol=1e-6)
+    assert (c["xi_raw"] >= 0).all() and np.isfinite(c["xi_raw"]).all()
+    ll_simt, _ = h.log_likelihood_batch(obs, tensor_cores=False)
+    ll_tc, llb_tc = h.log_likelihood_batch(obs, tensor_cores=True)
+    np.testing.assert_allclose(ll_tc, ll_simt, rtol=5e-5)
+    np.testing.assert_allclose(llb_tc, ll_simt, rtol=5e-5)
+    np.testing.assert_allclose(c["loglik"], ll_simt.sum(), rtol=2e-5)
+    ref = O.loglik(O.forward(pi, A, O.emissions_discrete(Bm, obs[:4].astype(np.int64)))[1])
+    np.testing.assert_allclose(ll_simt[:4], ref, rtol=F32_RTOL)
+
+
 def test_fwdbwd_config2_shape_properties(K):
     """N=8 Gaussian, T=2048 at a reduced batch: forward and backward likelihoods agree, and the
     oracle agrees on a sub-sample."""
