@@ -33,12 +33,14 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (description, N, M, B per GPU, T)
+    "c1": ("DiscreteHMM N=3 M=4, forward + backward + Viterbi of ONE sequence, T=1000 (the reference's CPU-runnable case; "
+           "latency, not throughput)", 3, 4, 1, 1000),
     "c2": ("GaussianHMM N=8 D=1 forward-backward log-likelihood, B=16384 T=2048 per GPU", 8, 0, 16384, 2048),
     "c3": ("DiscreteHMM N=64 M=256 Viterbi, B=65536 T=4096", 64, 256, 65536, 4096),
     "c4": ("DiscreteHMM N=128 M=1024 Baum-Welch iteration, B=131072 T=512 per GPU", 128, 1024, 131072, 512),
     "c5": ("GaussianHMM N=1024 D=1 forward-backward, B=4096 T=1024", 1024, 0, 4096, 1024),
 }
-CFG_INDEX = {"c2": 2, "c3": 3, "c4": 4, "c5": 5}
+CFG_INDEX = {"c1": 1, "c2": 2, "c3": 3, "c4": 4, "c5": 5}
 
 
 def peaks():
@@ -84,6 +86,15 @@ def _cpu_chunk(args):
         pi, A, mean, sd = params
         E = O.emissions_gaussian_1d(mean, sd, obs.astype(np.float64))
         O.fwdbwd_loglik_batch(pi, A, E)
+    elif kind == "c1":
+        pi, A, Bm = params
+        o = obs.astype(np.int64)
+        E = O.emissions_discrete(Bm, o)
+        for b in range(o.shape[0]):
+            alpha, scale = O.forward(pi, A, E[b])
+            O.backward(A, E[b], scale)
+        with np.errstate(divide="ignore"):
+            O.viterbi(pi, A, Bm, o)
     elif kind == "c3":
         pi, A, Bm = params
         with np.errstate(divide="ignore"):
@@ -95,7 +106,7 @@ def _cpu_chunk(args):
 
 
 # bounded samples: a few seconds of wall time of the NumPy port on the GPU box's 16+ host cores each
-CPU_SAMPLE = {"c2": (16384, 2048), "c3": (8192, 1024), "c4": (8192, 512), "c5": (32, 32)}
+CPU_SAMPLE = {"c1": (1, 1000), "c2": (16384, 2048), "c3": (8192, 1024), "c4": (8192, 512), "c5": (32, 32)}
 
 
 def cpu_params(kind, model):
@@ -241,6 +252,28 @@ def run_ours(args):
         ncu_traffic = 180.484352e6 + 4.261632e6
         l2_note = "two alternating 134 MB observation sets (268 MB > 126 MB L2)"
         dtype = "f32"
+    elif kind == "c1":
+        model, obs_h = make_discrete(N, M, B, T, seed)
+        p = model._params()
+        ob = engine.prepare_obs(torch.from_numpy(obs_h.astype(np.int64)).to(dev), symbols=True)
+
+        def step(i):          # the three single-sequence calls of the reference's tests, inputs resident on the device
+            _, scale, _ = engine.forward(p, ob, torch.float64)
+            engine.backward(p, ob, torch.float64, scale)
+            engine.viterbi(p, ob)
+
+        def e2e_step(i):      # ... and through the reference-named methods, NumPy in / NumPy out
+            o = obs_h[0].astype(np.int64)
+            _, scale = model.forward(o)
+            model.backward(o, scale)
+            return model.viterbi_path(o)[1]
+
+        launches_per_step = 4      # forward, backward, Viterbi DP, backtrace
+        algo_bytes = B * T * (8 + 3 * N * 8 + N + 8)     # symbols, alpha/scale/beta rows out, backpointers, path
+        h2d, d2h = 3 * B * T * 8, B * T * (2 * N * 8 + 8 + 8)
+        dominant = "forward/backward/viterbi generic kernels, one CTA: a 1000-step dependency chain (latency, no roofline claim)"
+        l2_note = "9e3 transitions per step: everything is cache resident; the step is 4 launches of ~1000 dependent steps"
+        dtype = "f64"
     elif kind == "c3":
         model, obs_h = make_discrete(N, M, B, T, seed)
         host_sets = [torch.from_numpy(obs_h).pin_memory()]
@@ -380,7 +413,9 @@ def run_ours(args):
             bf = args.operands == "bf16"
             peak = 1621.0 if bf else 1621.0 / 2
             roof = {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
-                    "frac": tflops / peak, "traffic": None, "kernel": dominant,
+                    "frac": tflops / peak, "traffic": 43.3344e6 if bf else None, "kernel": dominant,
+                    "traffic_note": "dram__bytes_read+write of one launch (profiles/r1_ncu_c5_tc_recursion2_bf16_summary.csv): "
+                                    "W ping-pong rows and A stay in L2; L2->SM operand traffic is 201 GB per launch",
                     "peak_source": "measured bf16 burst peak (MEASURED_PEAKS.json)" if bf else
                     "half of the measured bf16 burst peak (MEASURED_PEAKS.json): tf32 runs at half the bf16 rate",
                     "accuracy": "log-likelihood vs float64 oracle at this T: max rel 6.8e-6 (bf16) / 9.2e-7 (tf32), measured"}
