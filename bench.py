@@ -290,6 +290,9 @@ def run_ours(args):
         algo_bytes = B * T * (1 + N + 1 + 1)         # obs + N backpointer bytes written + 1 read + path byte
         h2d, d2h = B * T, B * T + B * 8
         dominant = "viterbi_screen_kernel<64, uint8> (float32 screen, float64 resolve) + viterbi_backtrace_kernel"
+        # dram__bytes_read.sum + dram__bytes_write.sum of the DP kernel at full size, ncu --set full
+        # (profiles/r1_ncu_c3_viterbi_screen_fullsize_summary.csv): 17.18 GB of backpointers written once, observations read once
+        ncu_traffic = 0.309431808e9 + 17.133593e9
         l2_note = "backpointer workspace 17 GB per step (>> L2)"
         dtype = "f64"
     elif kind == "c4":
