@@ -78,6 +78,18 @@ int khmm_viterbi_discrete_f64(int64_t B, int64_t T, int N, int M,
                               void *path, int path_dtype, double *logp,
                               khmm_stream_t stream);
 
+/* EXTENSION: the same DP for 1-D Gaussian emissions.  The reference's viterbi_path fails on
+ * float observations (abstract_hmm.py:234-237), so there is no reference output to match; the definition
+ * is log b_j(x) = (-0.5 z) z + logc_j with z = (x - mean_j) / sd_j, one IEEE rounding per operation in that order, and
+ * logc_j = -log(sd_j) - log(sqrt(2 pi)) computed on the HOST.  mean_sd_logc is [3][N] float64: mean, sd, logc.
+ * obs: [B][T] f32 or f64.  Bit-exact against oracle/hmm_oracle.py::viterbi_gaussian_1d ("parity unpinned" beyond it). */
+int khmm_viterbi_gauss_f64(int64_t B, int64_t T, int N,
+                           const double *logpi, const double *logA, const double *mean_sd_logc,
+                           const void *obs, int obs_dtype, const int32_t *lengths,
+                           void *backptr, size_t backptr_bytes,
+                           void *path, int path_dtype, double *logp,
+                           khmm_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Scaled forward -- AbstractHMM.forward (abstract_hmm.py:250-285) with the emission
  * evaluation (abstract_hmm.py:353-367 -> distribution.py:35-36 / :151-155) fused in.

@@ -160,8 +160,14 @@ class AbstractHMM(object):
         obs_arr = np.asarray(observations)
         if obs_arr.ndim != 1:
             raise ValueError("viterbi_path takes one sequence; use viterbi_batch for a batch")
+        p = self._params()
+        if p.kind != "discrete":
+            # the reference indexes psi with float observations here and fails (abstract_hmm.py:234-237);
+            # Gaussian decoding exists as the batched extension viterbi_batch only
+            raise IndexError("viterbi_path needs integer observations (discrete emissions); "
+                             "the reference fails on float observations too (abstract_hmm.py:234-237)")
         ob = self._prep(obs_arr, single=True)
-        path, logp = engine.viterbi(self._params(), ob)
+        path, logp = engine.viterbi(p, ob)
         out = np.empty_like(obs_arr)
         out[:] = path[0].cpu().numpy()
         return out, float(logp[0].item())
@@ -365,7 +371,9 @@ class AbstractHMM(object):
 
     def viterbi_batch(self, observations, lengths=None, path_dtype=None):
         """Batched bit-exact Viterbi -> `(path[B,T], log_prob[B])`; entries past a sequence's length
-        are 0.  `path_dtype` defaults to int64."""
+        are 0.  `path_dtype` defaults to int64.  EXTENSION: a GaussianHMM with 1-D emissions decodes real
+        observations with log b_j(x) = (-0.5 z) z - log(sd_j) - log sqrt(2 pi) (the reference's own viterbi_path
+        fails on float observations); bit-exact against oracle.viterbi_gaussian_1d."""
         t = engine.require_cuda()
         ob = self._prep(observations, lengths)
         if path_dtype is not None and not isinstance(path_dtype, t.dtype):

@@ -37,6 +37,10 @@ viterbi_generic_kernel(int64_t B, int64_t T, int N, int M, const double *__restr
     }
     const bool active = j < N;
     const double lpj = active ? logpi[j] : 0.0;
+    // M == 0: 1-D Gaussian emissions (extension, khmm_viterbi_gauss_f64); logBsm is then [3][N] = mean, sd, log-constant
+    const bool gauss = M == 0;
+    const double g_mean = (gauss && active) ? logBsm[j] : 0.0, g_sd = (gauss && active) ? logBsm[N + j] : 1.0,
+                 g_logc = (gauss && active) ? logBsm[2 * N + j] : 0.0;
     const int64_t ngroups = (B + S - 1) / S;
     __syncthreads();
 
@@ -50,12 +54,32 @@ viterbi_generic_kernel(int64_t B, int64_t T, int N, int M, const double *__restr
             len[s] = b < B ? (lengths ? lengths[b] : (int)T) : 0;
             tmax = max(tmax, len[s]);
         }
+        // log b_j(o_t) is requested one step ahead (symbol -> table row: two dependent global loads)
+        auto log_emission = [&](int s, int tt) -> double {
+            if (!(active && tt < len[s])) return 0.0;
+            if (gauss) {
+                // z = (x - mean)/sd; log pdf = (-0.5 z) z + (-log sd - log sqrt(2 pi)): one rounding per operation, in the
+                // order the oracle's NumPy expression evaluates (no contraction into an FMA)
+                const double x = load_real<double>(obs, obs_dtype, (b0 + s) * T + tt);
+                const double z = __ddiv_rn(__dsub_rn(x, g_mean), g_sd);
+                return __dadd_rn(__dmul_rn(__dmul_rn(-0.5, z), z), g_logc);
+            }
+            int sym = load_symbol(obs, obs_dtype, (b0 + s) * T + tt);
+            sym = sym < 0 ? 0 : (sym >= M ? M - 1 : sym);
+            return __ldg(logBsm + (int64_t)sym * N + j);
+        };
+        double e_cur[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) e_cur[s] = log_emission(s, 0);
         int cur = 0;
         for (int t = 0; t < tmax; t++) {
             const double *prev = rows + cur * NT * S;
             double *next = rows + (cur ^ 1) * NT * S;
             double best[S];
             int arg[S];
+            double e_nxt[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) e_nxt[s] = log_emission(s, t + 1);
             if (t == 0) {
 #pragma unroll
                 for (int s = 0; s < S; s++) { best[s] = lpj; arg[s] = 0; }
@@ -84,12 +108,11 @@ viterbi_generic_kernel(int64_t B, int64_t T, int N, int M, const double *__restr
                 double d = 0.0;
                 if (active && t < len[s]) {
                     int64_t b = b0 + s;
-                    int sym = load_symbol(obs, obs_dtype, b * T + t);
-                    sym = sym < 0 ? 0 : (sym >= M ? M - 1 : sym);
-                    d = best[s] + __ldg(logBsm + (int64_t)sym * N + j);
+                    d = best[s] + e_cur[s];
                     if (t > 0) psi[(b * T + t) * N + j] = (PSI)arg[s];
                 }
                 next[j * S + s] = d;
+                e_cur[s] = e_nxt[s];
             }
             __syncthreads();
             // termination for sequences that end at this step: first-index argmax (abstract_hmm.py:233,235)
@@ -578,12 +601,12 @@ static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, 
     int rc_tile = -1;
     const char *vs_env = getenv("KHMM_VIT_SCREEN");      // development / cross-check switch, read on every call
     const bool use_screen = !(vs_env && atoi(vs_env) == 0);
-    if (sizeof(PSI) == 1 && B >= 64 && use_screen && (N == 32 || N == 64 || N == 128)) {
+    if (M > 0 && sizeof(PSI) == 1 && B >= 64 && use_screen && (N == 32 || N == 64 || N == 128)) {
         // float32-screened warp-per-sequence kernel
         if (N == 32) rc_tile = launch_viterbi_screen<32, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
         else if (N == 64) rc_tile = launch_viterbi_screen<64, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
         else rc_tile = launch_viterbi_screen<128, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
-    } else if (sizeof(PSI) == 1 && B >= 64) {   // register-tile kernels (small batches stay on the generic kernel)
+    } else if (M > 0 && sizeof(PSI) == 1 && B >= 64) {   // register-tile kernels (small batches stay on the generic kernel)
         if (N == 32) rc_tile = launch_viterbi_tile<32, 4, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
         else if (N == 64) rc_tile = launch_viterbi_tile<64, 4, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
         else if (N == 128) rc_tile = launch_viterbi_tile<128, 2, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
@@ -649,6 +672,31 @@ int khmm_viterbi_discrete_f64(int64_t B, int64_t T, int N, int M, const double *
         return run_viterbi<uint8_t>(B, T, N, M, logpi, logA, logBsm, obs, obs_dtype, lengths, backptr, path,
                                     path_dtype, logp, st);
     return run_viterbi<uint16_t>(B, T, N, M, logpi, logA, logBsm, obs, obs_dtype, lengths, backptr, path, path_dtype,
+                                 logp, st);
+}
+
+int khmm_viterbi_gauss_f64(int64_t B, int64_t T, int N, const double *logpi, const double *logA,
+                           const double *mean_sd_logc, const void *obs, int obs_dtype, const int32_t *lengths,
+                           void *backptr, size_t backptr_bytes, void *path, int path_dtype, double *logp,
+                           khmm_stream_t stream) {
+    KHMM_REQUIRE(B >= 0 && T >= 1 && N >= 1, "viterbi_gauss: bad shape B=%lld T=%lld N=%d", (long long)B, (long long)T, N);
+    if (N > 1024) {
+        set_error("N=%d > 1024 is not supported", N);
+        return KHMM_ERR_UNSUPPORTED;
+    }
+    if (B == 0) return KHMM_OK;
+    KHMM_REQUIRE(logpi && logA && mean_sd_logc && obs && path && logp && backptr, "viterbi_gauss: NULL pointer argument");
+    KHMM_REQUIRE(obs_dtype == KHMM_F32 || obs_dtype == KHMM_F64, "viterbi_gauss: obs dtype code %d is not f32/f64", obs_dtype);
+    KHMM_REQUIRE(path_dtype >= KHMM_U8 && path_dtype <= KHMM_I64, "viterbi_gauss: path dtype code %d is not an integer type",
+                 path_dtype);
+    KHMM_REQUIRE(backptr_bytes >= khmm_viterbi_workspace_bytes(B, T, N), "viterbi_gauss: workspace too small (%zu < %zu)",
+                 backptr_bytes, khmm_viterbi_workspace_bytes(B, T, N));
+    cudaStream_t st = (cudaStream_t)stream;
+    // M = 0 selects the Gaussian emission evaluation of the generic kernel
+    if (N <= 256)
+        return run_viterbi<uint8_t>(B, T, N, 0, logpi, logA, mean_sd_logc, obs, obs_dtype, lengths, backptr, path, path_dtype,
+                                    logp, st);
+    return run_viterbi<uint16_t>(B, T, N, 0, logpi, logA, mean_sd_logc, obs, obs_dtype, lengths, backptr, path, path_dtype,
                                  logp, st);
 }
 

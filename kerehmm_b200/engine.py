@@ -87,9 +87,11 @@ class DeviceModel:
         self.suffix = "f32" if real == t.float32 else "f64"
         self.pi = _dev(p.pi, real)
         self.A = _dev(p.A, real)
-        self.AT = _dev(p.A.T, real)
+        # transposes are taken on the device: a strided host copy of a 1024 x 1024 float64 matrix plus a second
+        # upload cost ~3 ms per call at config 5
+        self.AT = self.A.t().contiguous()
         if p.kind == "discrete":
-            self.Bsm = _dev(p.B.T, real)          # symbol-major [M][N]
+            self.Bsm = _dev(p.B, real).t().contiguous()          # symbol-major [M][N]
         elif p.kind == "gauss":
             self.mean = _dev(p.mean, real)
             self.sd = _dev(p.sd, real)
@@ -173,10 +175,30 @@ def prepare_obs(obs, symbols: bool, lengths=None, feature_dims: int = 0, u16_bit
     return Obs(tensor=x, code=code, B=B, T=T, on_host=on_host, lengths=L, h2d_bytes=h2d)
 
 
+_PINNED_RESULT_MIN_BYTES = 1 << 20
+
+
+def _to_host(x):
+    """Device tensor -> NumPy.  Large results (a config-3 path array is 268 MB) land in page-locked memory from
+    torch's caching host allocator and the returned array keeps that block alive: a pageable `.cpu()` copy of that
+    size costs ~100 ms of page faults and staging, the pinned copy ~5 ms at PCIe rate; the block goes back to the
+    allocator's cache when the caller drops the array."""
+    t = torch()
+    if x.numel() * x.element_size() < _PINNED_RESULT_MIN_BYTES:
+        return x.cpu().numpy()
+    try:
+        host = t.empty(x.shape, dtype=x.dtype, pin_memory=True)
+    except RuntimeError:          # page-locked memory exhausted: fall back to a pageable copy
+        return x.cpu().numpy()
+    host.copy_(x, non_blocking=True)
+    t.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
 def finish(ob: Obs, *tensors):
     """Return results on the side the observations came from."""
     if ob.on_host:
-        out = tuple(None if x is None else x.cpu().numpy() for x in tensors)
+        out = tuple(None if x is None else _to_host(x) for x in tensors)
     else:
         out = tensors
     return out if len(out) != 1 else out[0]
@@ -379,20 +401,32 @@ def viterbi(p: ModelParams, ob: Obs, path_dtype=None):
     """Bit-exact float64 Viterbi -> (path[B][T], logp[B]) device tensors.  The log tables are
     taken on the HOST with np.log, exactly what abstract_hmm.py:218,227,229 evaluates."""
     t = require_cuda()
-    if p.kind != "discrete":
-        raise IndexError("viterbi_path needs integer observations (discrete emissions); "
-                         "the reference fails on float observations too (abstract_hmm.py:234-237)")
-    N, M, dev = p.N, p.M, device()
+    if p.kind not in ("discrete", "gauss"):
+        raise IndexError("viterbi needs integer observations (discrete emissions) or 1-D Gaussian emissions "
+                         "(batched extension); the reference fails on float observations (abstract_hmm.py:234-237)")
+    N, dev = p.N, device()
     with np.errstate(divide="ignore"):
-        logpi, logA, logBsm = np.log(p.pi), np.log(p.A), np.log(p.B.T)
-    d_logpi, d_logA, d_logBsm = _dev(logpi, t.float64), _dev(logA, t.float64), _dev(logBsm, t.float64)
+        logpi, logA = np.log(p.pi), np.log(p.A)
+    d_logpi, d_logA = _dev(logpi, t.float64), _dev(logA, t.float64)
     path_dtype = path_dtype or t.int64
     pname = str(path_dtype).replace("torch.", "")
     path = t.zeros((ob.B, ob.T), dtype=path_dtype, device=dev)
     logp = t.empty((ob.B,), dtype=t.float64, device=dev)
     ws_bytes = _lib.lib().khmm_viterbi_workspace_bytes(ob.B, ob.T, N)
     ws, wsp = workspace(ws_bytes, 256)      # cached: the backpointer workspace is 17 GB at config 3
-    _lib.call("khmm_viterbi_discrete_f64", ob.B, ob.T, N, M, ptr(d_logpi), ptr(d_logA), ptr(d_logBsm),
+    if p.kind == "gauss":
+        # EXTENSION (include/khmm.h): log-density constants on the host, exactly as oracle.log_gaussian_pdf_1d forms them
+        mean, sd = np.asarray(p.mean, dtype=np.float64), np.asarray(p.sd, dtype=np.float64)
+        with np.errstate(divide="ignore"):
+            logc = -np.log(sd) - np.log(np.sqrt(2.0 * np.pi))
+        d_tab = _dev(np.stack([mean, sd, logc]), t.float64)
+        _lib.call("khmm_viterbi_gauss_f64", ob.B, ob.T, N, ptr(d_logpi), ptr(d_logA), ptr(d_tab), ptr(ob.tensor), ob.code,
+                  ptr(ob.lengths), wsp, ws_bytes, ptr(path), _PATH_CODES[pname], ptr(logp), stream_ptr())
+        return path, logp
+    with np.errstate(divide="ignore"):
+        logBsm = np.log(p.B.T)
+    d_logBsm = _dev(logBsm, t.float64)
+    _lib.call("khmm_viterbi_discrete_f64", ob.B, ob.T, N, p.M, ptr(d_logpi), ptr(d_logA), ptr(d_logBsm),
               ptr(ob.tensor), ob.code, ptr(ob.lengths), wsp, ws_bytes, ptr(path), _PATH_CODES[pname],
               ptr(logp), stream_ptr())
     return path, logp

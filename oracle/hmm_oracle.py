@@ -226,6 +226,45 @@ def viterbi(pi: np.ndarray, A: np.ndarray, Bm: np.ndarray, obs: np.ndarray):
     return path, logp
 
 
+def log_gaussian_pdf_1d(x, mean, sd):
+    """log of distribution.py:151-155 for D = 1 as an explicit float64 expression: z = (x - mean)/sd,
+    (-0.5 z) z + (-log sd - log sqrt(2 pi)); x (..., T) -> (..., T, N).  EXTENSION: the reference never takes this
+    logarithm for Gaussians (its viterbi_path fails on float observations, abstract_hmm.py:234-237)."""
+    x = np.asarray(x, dtype=np.float64)[..., None]
+    z = (x - mean) / sd
+    logc = -np.log(sd) - np.log(np.sqrt(2.0 * np.pi))
+    return -0.5 * z * z + logc
+
+
+def viterbi_gaussian_1d(pi, A, mean, sd, x):
+    """The max-plus DP of abstract_hmm.py:203-239 on 1-D Gaussian log-densities (EXTENSION, parity unpinned: the
+    reference raises on float observations).  Same association order as `viterbi`: delta[t-1] + log A, max /
+    first-index argmax, + log b.  x is (T,) or (B, T) real.  Returns (path int64, logp)."""
+    x = np.asarray(x)
+    single = x.ndim == 1
+    xb = x[None] if single else x
+    Bn, T = xb.shape
+    N = A.shape[0]
+    with np.errstate(divide="ignore"):
+        logpi, logA = np.log(pi), np.log(A)
+    logE = log_gaussian_pdf_1d(xb, np.asarray(mean, dtype=np.float64), np.asarray(sd, dtype=np.float64))   # (B, T, N)
+    psi = np.zeros((Bn, T, N), dtype=np.int32)
+    delta = logpi[None, :] + logE[:, 0, :]
+    for t in range(1, T):
+        tr = delta[:, :, None] + logA[None, :, :]
+        psi[:, t, :] = tr.argmax(axis=1)
+        delta = tr.max(axis=1) + logE[:, t, :]
+    path = np.empty((Bn, T), dtype=np.int64)
+    path[:, -1] = delta.argmax(axis=1)
+    logp = delta.max(axis=1)
+    rows = np.arange(Bn)
+    for t in range(T - 2, -1, -1):
+        path[:, t] = psi[rows, t + 1, path[:, t + 1]]
+    if single:
+        return path[0], logp[0]
+    return path, logp
+
+
 # -------------------------------------------------------------------- Baum-Welch
 def sequence_stats_discrete(pi, A, Bm, obs):
     """Sufficient statistics of ONE sequence exactly as `DiscreteHMM.do_pass` forms them

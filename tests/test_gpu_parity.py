@@ -263,6 +263,30 @@ def test_viterbi_screened_kernel_adversarial(K, N, kind):
     assert np.array_equal(logp, rl)
 
 
+@pytest.mark.parametrize("N,B,T,dtype", [(3, 5, 40, np.float64), (8, 70, 100, np.float32), (64, 66, 30, np.float32),
+                                          (300, 4, 25, np.float64)])
+def test_viterbi_batch_gaussian_extension(K, N, B, T, dtype):
+    """EXTENSION: batched Viterbi for 1-D Gaussian emissions, bit-exact against the oracle's
+    statement of the same definition (ragged lengths included); the single-sequence reference method keeps failing
+    on float observations like the reference (Q10)."""
+    np.random.seed(300 + N)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    sd = sd * (0.5 + np.random.random(N))                       # the reference initialises every sd to 1
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(301 + N)
+    x = (mean[rng.integers(0, N, size=(B, T))] + 2.0 * rng.standard_normal((B, T))).astype(dtype)
+    lengths = rng.integers(1, T + 1, size=B)
+    path, logp = h.viterbi_batch(x, lengths=lengths)
+    for b in range(B):
+        L = lengths[b]
+        rp, rl = O.viterbi_gaussian_1d(pi, A, mean, sd, x[b, :L])
+        assert np.array_equal(path[b, :L], rp), b
+        assert logp[b] == rl
+        assert not path[b, L:].any()
+    with pytest.raises(IndexError):
+        h.viterbi_path(x[0])
+
+
 def test_viterbi_with_zero_probabilities(K):
     """log(0) = -inf entries; -inf columns resolve to index 0."""
     N, M = 5, 4

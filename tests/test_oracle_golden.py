@@ -232,3 +232,29 @@ def test_simulate_restatement_matches_reference_golden(name):
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "simulate_golden.npz"))
     s, e = O.simulate_from_uniforms(g[name + "_pi"], g[name + "_A"], g[name + "_uniforms"], Bm=g[name + "_B"])
     assert np.array_equal(s, g[name + "_states"]) and np.array_equal(e, g[name + "_emissions"])
+
+
+def test_gaussian_viterbi_extension_is_the_best_path():
+    """EXTENSION, parity unpinned (the reference's viterbi_path fails on float observations, Q10): the oracle's
+    Gaussian Viterbi must return the maximum over ALL state paths of log pi + sum log A + sum log N(x; mean, sd),
+    with SciPy's logpdf as the independent statement of the density."""
+    import itertools
+    from scipy.stats import norm
+    rng = np.random.default_rng(77)
+    N, T = 3, 6
+    np.random.seed(78)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    sd = sd * (0.5 + rng.random(N))
+    x = mean[rng.integers(0, N, size=T)] + rng.standard_normal(T)
+    path, logp = O.viterbi_gaussian_1d(pi, A, mean, sd, x)
+    logE = np.stack([norm(mean[j], sd[j]).logpdf(x) for j in range(N)], axis=1)
+    np.testing.assert_allclose(O.log_gaussian_pdf_1d(x, mean, sd), logE, rtol=1e-12, atol=1e-12)
+    best, best_path = -np.inf, None
+    for cand in itertools.product(range(N), repeat=T):
+        s = np.log(pi[cand[0]]) + logE[0, cand[0]]
+        for t in range(1, T):
+            s += np.log(A[cand[t - 1], cand[t]]) + logE[t, cand[t]]
+        if s > best:
+            best, best_path = s, cand
+    assert tuple(path) == best_path
+    np.testing.assert_allclose(logp, best, rtol=1e-12)
