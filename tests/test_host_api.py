@@ -164,3 +164,27 @@ def test_no_cpu_fallback():
                  lambda: h.log_likelihood_batch(np.zeros((2, 3), dtype=np.int64))):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             call()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) must print ONE JSON line with
+    the contract's keys; the smallest workload keeps this a sub-second CPU test."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "transitions/s" and d["higher_is_better"] is True
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data",
+                "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["value"] > 0 and d["steps"] == 2 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
