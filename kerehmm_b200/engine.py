@@ -327,9 +327,8 @@ def fwdbwd_loglik_small_host(p: ModelParams, obs, both=True, nchunks=4, min_byte
     main = t.cuda.current_stream()
     side = t.cuda.Stream(device=dev)
     xd = t.empty((B, T), dtype=x.dtype, device=dev)
-    ll = t.empty((B,), dtype=t.float64, device=dev)
-    llb = t.empty((B,), dtype=t.float64, device=dev) if both else None
-    dm = DeviceModel(p, t.float32)
+    res = t.empty((2 if both else 1, B), dtype=t.float64, device=dev)      # one device->host copy for both results
+    ll, llb = res[0], (res[1] if both else None)
     bounds = [(B * k) // nchunks for k in range(nchunks + 1)]
     side.wait_stream(main)
     events = []
@@ -341,6 +340,8 @@ def fwdbwd_loglik_small_host(p: ModelParams, obs, both=True, nchunks=4, min_byte
             ev = t.cuda.Event()
             ev.record(side)
             events.append(ev)
+    # the (small, blocking) parameter uploads go behind the first block's copy instead of in front of it
+    dm = DeviceModel(p, t.float32)
     for k in range(nchunks):
         b0, b1 = bounds[k], bounds[k + 1]
         if b1 <= b0:
@@ -354,7 +355,8 @@ def fwdbwd_loglik_small_host(p: ModelParams, obs, both=True, nchunks=4, min_byte
             _lib.call("khmm_fwdbwd_loglik_discrete_f32", b1 - b0, T, p.N, p.M, ptr(dm.pi), ptr(dm.A), ptr(dm.Bsm),
                       ptr(xd[b0:b1]), code, None, ptr(lk), ptr(lbk), main.cuda_stream)
     xd.record_stream(main)
-    return ll.cpu().numpy(), (llb.cpu().numpy() if both else None)
+    host = res.cpu().numpy()
+    return host[0], (host[1] if both else None)
 
 
 def tc_supported(p: ModelParams, ob: Obs) -> bool:
