@@ -1,25 +1,28 @@
-// Tensor-core recursion for large state spaces (N a multiple of 128, N >= 128): the forward step
+// Tensor-core recursion for large state spaces (N a multiple of 128, 128 <= N <= 1024): the forward step
 // alpha_{t-1} . A (abstract_hmm.py:266-270) and the backward step A . (b . beta_{t+1}) (:339-349) of
-// a whole batch are one (B x N) x (N x N) contraction per time step.  Each step is ONE launch of a
-// tcgen05 kernel (kind::tf32, fp32 accumulators in TMEM, operands staged by TMA with the 128-byte
-// swizzle) whose epilogue fuses the emission evaluation, the scaling and the row sums:
+// a whole batch are one (B x N) x (N x N) contraction per time step, run on tcgen05 (kind::tf32 or kind::f16 with
+// bf16 operands, fp32 accumulators in TMEM, operands staged by TMA with the 128-byte swizzle) with an epilogue that
+// fuses the emission evaluation, the scaling and the row sums:
 //
 //     W_t = (W_{t-1} M) . b_t . r_{t-1},      r_{t-1} = 1 / sum_j W_{t-1}(j),
 //
 // M = A with reversed time gives the (self-scaled) backward recursion in the form w_t = b_t . beta_t,
 // exactly as in smalln.cu.  W_t is the reference's *unnormalised* alpha_t (its row sum is the scale
 // factor c_t), so normalisation needs no second pass over a row that is split across CTAs: every
-// column tile writes its partial row sum and the next step's epilogue adds them up.  Forward and
-// backward share a launch (blockIdx.z), log P accumulates in float64 from the c_t.
+// column tile writes its partial row sums and the next step's epilogue adds them up.  Forward and
+// backward run together, log P accumulates in float64 from the c_t.
 //
-// Warp roles per CTA (192 threads): warps 0-3 epilogue (thread = TMEM lane = sequence), warp 4 TMA
-// producer, warp 5 TMEM allocator + single-thread MMA issuer.  4-stage smem ring of
-// (128 x 32 fp32) W tiles and (128 x 32 fp32) matrix tiles.
+// Two drivers of that step:
+//   * tc_recursion2_kernel -- ALL T-1 steps in one cooperative launch, jobs chained through per-chain completion
+//     counters (the product path; see the comment above it and DESIGN.md 3.4);
+//   * tc_step_kernel -- one launch per time step (devices without cooperative launch, KHMM_RC_MODE=1): warps 0-3
+//     epilogue (thread = TMEM lane = sequence), warp 4 TMA producer, warp 5 TMEM allocator + single-thread MMA issuer,
+//     4-stage smem ring.
 //
-// Precision: tf32 multiplies (10-bit mantissa, inputs truncated by the tensor core), fp32
-// accumulation.  Measured against the float64 oracle at N=256..1024 the log-likelihood agrees to
-// ~1e-6 relative (tests/test_gpu_parity.py states the bound); alpha itself is only good to ~1e-3,
-// which is why the float32 SIMT kernels remain the parity path for alpha/beta outputs.
+// Precision: tf32 multiplies (10-bit mantissa; operands are ROUNDED to tf32 when written, the tensor core would
+// truncate) or bf16 multiplies, fp32 accumulation.  Measured against the float64 oracle at N = 256..1024 the
+// log-likelihood agrees to ~1e-6 relative with tf32 (tests/test_gpu_parity.py states the bounds); alpha itself is only
+// good to ~1e-3, which is why the float32 SIMT kernels remain the parity path for alpha/beta outputs.
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -32,18 +35,6 @@ using namespace tc;
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;   // TC_BN: psum / workspace granularity (column tile of 128)
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;       // one 128 x 32 fp32 operand tile
-#ifndef KHMM_TC_WHOLE
-#define KHMM_TC_WHOLE 1
-#endif
-#ifndef KHMM_TC_PERSIST
-#define KHMM_TC_PERSIST 1
-#endif
-#ifndef KHMM_TC_PERSIST_PAIR
-#define KHMM_TC_PERSIST_PAIR 0   /* CTA pairs (cta_group::2): validated, but measured equal to single CTAs (37.8 ms at c5) */
-#endif
-#ifndef KHMM_TC_PAIR
-#define KHMM_TC_PAIR 0   /* measured: no faster than the single-CTA kernel (43.6 vs 43.8 ms at c5) -- the step is bound by per-launch prologue/epilogue time, not by bytes in flight */
-#endif
 constexpr int TC_STAGES = 4;                           // ring depth (BN = 128: 32 KB per stage, BN = 256: 48 KB)
 
 struct __align__(8) TcBars {
@@ -220,376 +211,7 @@ tc_step_kernel(const __grid_constant__ CUtensorMap mapXf, const __grid_constant_
     if (warp == 5) tmem_dealloc(tmem, BN);
 }
 
-// CTA-pair variant (cluster of 2, tcgen05 cta_group::2): one MMA covers 256 sequences x 256 states; each CTA
-// stages its own 128 W rows and only HALF of the matrix tile (128 of the 256 state rows), so a stage is 32 KB
-// instead of 48 KB for the same 512 cycles of tensor work and six stages fit.  The single-CTA kernel is bound by
-// bytes in flight: 4 stages x 48 KB per ~1.2 us of L2 latency = 85 B/clk against the 94 B/clk the MMAs consume.
-// The leader CTA (cluster rank 0) issues the MMAs; both CTAs load (their bytes complete on the LEADER's `full`
-// barrier), both run the epilogue on their own 128 TMEM lanes; `empty` / `tmem_full` are signalled in both CTAs
-// by multicast commits.
-constexpr int TC2_STAGES = 6;
-constexpr int TC2_STAGE_BYTES = 2 * TC_TILE_BYTES;   // W tile + half matrix tile, per CTA
-struct __align__(8) Tc2Bars {
-    uint64_t full[TC2_STAGES], empty[TC2_STAGES], tmem_full;
-    uint32_t tmem_base;
-};
-
-template <bool GAUSS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
-tc_step2_kernel(const __grid_constant__ CUtensorMap mapXf, const __grid_constant__ CUtensorMap mapXb,
-                const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df, TcDir db,
-                TcEmis em, int64_t B, int64_t T, int N, int step) {
-    constexpr int BN = 256;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    Tc2Bars *bars = (Tc2Bars *)(tiles + TC2_STAGES * TC2_STAGE_BYTES);
-    float *sp = (float *)(bars + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int dir = blockIdx.z;
-    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
-    const int nkb = N / TC_BK, NT = N / 128;
-    const CUtensorMap *mapX = dir ? &mapXb : &mapXf;
-    const CUtensorMap *mapM = dir ? &mapMb : &mapMf;
-    const TcDir d = dir ? db : df;
-    const int src = (step - 1) & 1, dst = step & 1;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < TC2_STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        mbar_init(&bars->tmem_full, 1);
-        fence_barrier_init();
-    }
-    if (GAUSS) {
-        for (int c = threadIdx.x; c < BN; c += blockDim.x) {
-            int j = n0 + c;
-            float sd = em.p1[j];
-            sp[c] = em.p0[j];
-            sp[BN + c] = -0.5f * 1.4426950408889634f / (sd * sd);
-            sp[2 * BN + c] = -log2f(sd * 2.5066282746310002f);
-        }
-    }
-    if (warp == 5) tmem_alloc2(&bars->tmem_base, BN);
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();          // the peer's barriers exist before anything arrives on them
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-
-    if (warp == 4) {
-        if (elect_one()) {
-            tma_prefetch_desc(mapX);
-            tma_prefetch_desc(mapM);
-            for (int kb = 0; kb < nkb; kb++) {
-                int s = kb % TC2_STAGES;
-                uint32_t ph = (kb / TC2_STAGES) & 1;
-                mbar_wait(&bars->empty[s], ph ^ 1);
-                const uint32_t lead_full = mapa_u32(smem_u32(&bars->full[s]), 0);
-                // only the leader arrives (expecting both CTAs' bytes); the peer's loads just complete_tx on the
-                // leader's barrier -- its next use of the slot is gated by its own `empty`, so it cannot run a phase
-                // ahead (a remote release-arrive here costs a GPU-scope fence per k-block: measured 71 us per step)
-                if (rank == 0) mbar_arrive_expect_tx(&bars->full[s], 2 * TC2_STAGE_BYTES);
-                tma_load_2d_pair(tiles + s * TC2_STAGE_BYTES, mapX, lead_full, kb * TC_BK, m0);
-                tma_load_2d_pair(tiles + s * TC2_STAGE_BYTES + TC_TILE_BYTES, mapM, lead_full, kb * TC_BK, n0 + (int)rank * 128);
-            }
-        }
-    } else if (warp == 5) {
-        if (rank == 0 && elect_one()) {
-            const uint32_t idesc = make_idesc_tf32(256, BN);
-            for (int kb = 0; kb < nkb; kb++) {
-                int s = kb % TC2_STAGES;
-                uint32_t ph = (kb / TC2_STAGES) & 1;
-                mbar_wait(&bars->full[s], ph);
-                tc_fence_after();
-                uint64_t da = make_kmajor_sw128_desc(tiles + s * TC2_STAGE_BYTES);
-                uint64_t dbb = make_kmajor_sw128_desc(tiles + s * TC2_STAGE_BYTES + TC_TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < TC_BK / 8; k++)
-                    mma2_tf32_ss(tmem, desc_advance(da, k * 32), desc_advance(dbb, k * 32), idesc, (kb | k) != 0);
-                tc_commit2(&bars->empty[s], 3);
-            }
-            tc_commit2(&bars->tmem_full, 3);
-        }
-    } else {
-        const int64_t b = m0 + warp * 32 + lane;
-        const bool live = b < B;
-        const int64_t t = dir ? (T - 1 - step) : step;
-        float r = 0.f, x = 0.f;
-        const float *brow = nullptr;
-        if (live) {
-            const float *ps = d.psum + (b * 2 + src) * NT;
-            float c = 0.f;
-            for (int k = 0; k < NT; k++) c += ps[k];
-            r = 1.0f / c;
-            if (blockIdx.y == 0) d.logacc[b] += log((double)c);
-            if (GAUSS) {
-                x = load_real<float>(em.obs, em.obs_dtype, b * T + t);
-            } else {
-                int sym = load_symbol(em.obs, em.obs_dtype, b * T + t);
-                sym = sym < 0 ? 0 : (sym >= em.M ? em.M - 1 : sym);
-                brow = em.p0 + (int64_t)sym * N + n0;
-            }
-        }
-        mbar_wait(&bars->tmem_full, 0);
-        tc_fence_after();
-        float rowsum = 0.f;
-        float *out = d.W + (b * 2 + dst) * N + n0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            if (c0 == 128) {
-                if (live) d.psum[(b * 2 + dst) * NT + blockIdx.y * 2] = rowsum;
-                rowsum = 0.f;
-            }
-            uint32_t acc[32];
-            tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, acc);
-            tmem_ld_wait();
-            if (live) {
-                float v[32];
-#pragma unroll
-                for (int q = 0; q < 32; q++) {
-                    v[q] = __uint_as_float(acc[q]) * r * tc_emission<GAUSS, BN>(em, sp, c0 + q, x, brow);
-                    rowsum += v[q];
-                }
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    reinterpret_cast<float4 *>(out + c0)[q] = make_float4(round_tf32(v[4 * q]), round_tf32(v[4 * q + 1]),
-                                                                          round_tf32(v[4 * q + 2]), round_tf32(v[4 * q + 3]));
-            }
-        }
-        if (live) d.psum[(b * 2 + dst) * NT + blockIdx.y * 2 + 1] = rowsum;
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();          // the peer may still be multicasting into our barriers / using the paired TMEM
-    if (warp == 5) tmem_dealloc2(tmem, BN);
-}
-
-// Persistent per-step variant (N % 256 == 0): one CTA per SM walks the step's (row tile, column tile, direction)
-// jobs with a grid-stride loop; the accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of
-// one tile (TMEM -> emission, scaling, row sums -> W_t in L2) runs under the MMAs of the next, and barrier
-// initialisation / TMEM allocation / descriptor prefetch happen once per step instead of once per tile.
-// Measured at c5 (256 jobs per step on 148 SMs): the one-tile-per-CTA kernel spends ~10 of its ~20 us per wave
-// outside the MMA loop.
-template <bool PAIR>
-struct __align__(8) TcPBars {
-    static constexpr int STAGES = PAIR ? 6 : TC_STAGES;
-    uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
-    uint32_t tmem_base;
-};
-
-// PAIR: a cluster of two CTAs (tcgen05 cta_group::2) walks the job list together; a job is then 256 sequences x
-// 256 states, each CTA stages its own 128 W rows and only half of the matrix tile (32 KB per stage instead of
-// 48 KB for the same tensor work, six stages).  The step is bound by L2 -> SM operand traffic (148 SMs x 94 B/clk
-// demanded against ~7 KB/clk delivered), so a third less traffic per MMA is a third more MMA rate.  The leader
-// (cluster rank 0) issues the MMAs; loads of both CTAs complete on the leader's `full`; `empty`/`tmem_full` are
-// multicast commits; the peer's epilogue warps release an accumulator with a remote arrive on the leader's
-// `tmem_empty`.
-template <bool GAUSS, bool PAIR>
-__device__ __forceinline__ void tc_step_persist_body(const CUtensorMap &mapXf, const CUtensorMap &mapXb,
-                                                     const CUtensorMap &mapMf, const CUtensorMap &mapMb, TcDir df, TcDir db,
-                                                     TcEmis em, int64_t B, int64_t T, int N, int step, int mtiles, int ndir) {
-    constexpr int BN = 256;
-    constexpr int STAGES = TcPBars<PAIR>::STAGES;
-    constexpr int MROWS = PAIR ? 128 : BN;                         // matrix-tile rows staged by this CTA
-    constexpr int STAGE_BYTES = TC_TILE_BYTES + MROWS * TC_BK * 4;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    TcPBars<PAIR> *bars = (TcPBars<PAIR> *)(tiles + STAGES * STAGE_BYTES);
-    float *sp = (float *)(bars + 1);  // [2 accumulators][3][256] emission constants of the tile in that accumulator
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
-    const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // job walker index
-    const int nwalk = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int nkb = N / TC_BK, NT = N / 128, ntile_n = N / BN;
-    const int mjobs = PAIR ? mtiles / 2 : mtiles;
-    const int njobs = mjobs * ntile_n * ndir;
-    const int src = (step - 1) & 1, dst = step & 1;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], PAIR ? 8 : 4); }
-        fence_barrier_init();
-    }
-    if (warp == 5) { if (PAIR) tmem_alloc2(&bars->tmem_base, 512); else tmem_alloc(&bars->tmem_base, 512); }
-    tc_fence_before();
-    __syncthreads();
-    if (PAIR) cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-    // job -> (row tile, column tile, direction): consecutive jobs share the column tile (matrix tile reuse in L2)
-    auto decode = [&](int job, int &m0, int &n0, int &dir) {
-        const int mt = job % mjobs;
-        const int rest = job / mjobs;
-        n0 = (rest % ntile_n) * BN;
-        dir = rest / ntile_n;
-        m0 = (PAIR ? mt * 2 + (int)rank : mt) * TC_BM;
-    };
-
-    if (warp == 4) {
-        if (elect_one()) {
-            tma_prefetch_desc(&mapXf); tma_prefetch_desc(&mapMf);
-            if (ndir > 1) { tma_prefetch_desc(&mapXb); tma_prefetch_desc(&mapMb); }
-            uint32_t it = 0;
-            for (int job = cta; job < njobs; job += nwalk) {
-                int m0, n0, dir;
-                decode(job, m0, n0, dir);
-                const CUtensorMap *mapX = dir ? &mapXb : &mapXf;
-                const CUtensorMap *mapM = dir ? &mapMb : &mapMf;
-                for (int kb = 0; kb < nkb; kb++, it++) {
-                    int s = it % STAGES;
-                    uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&bars->empty[s], ph ^ 1);
-                    if (PAIR) {
-                        // only the leader arrives, expecting both CTAs' bytes; the peer's loads complete_tx on the
-                        // leader's barrier (a remote release-arrive per k-block costs a GPU-scope fence each)
-                        const uint32_t lead_full = mapa_u32(smem_u32(&bars->full[s]), 0);
-                        if (rank == 0) mbar_arrive_expect_tx(&bars->full[s], 2 * STAGE_BYTES);
-                        tma_load_2d_pair(tiles + s * STAGE_BYTES, mapX, lead_full, kb * TC_BK, m0);
-                        tma_load_2d_pair(tiles + s * STAGE_BYTES + TC_TILE_BYTES, mapM, lead_full, kb * TC_BK, n0 + (int)rank * 128);
-                    } else {
-                        mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
-                        tma_load_2d(tiles + s * STAGE_BYTES, mapX, &bars->full[s], kb * TC_BK, m0);
-                        tma_load_2d(tiles + s * STAGE_BYTES + TC_TILE_BYTES, mapM, &bars->full[s], kb * TC_BK, n0);
-                    }
-                }
-            }
-        }
-    } else if (warp == 5) {
-        if (rank == 0 && elect_one()) {
-            const uint32_t idesc = make_idesc_tf32(PAIR ? 256 : TC_BM, BN);
-            uint32_t it = 0, nj = 0;
-            for (int job = cta; job < njobs; job += nwalk, nj++) {
-                const int a = nj & 1;
-                mbar_wait(&bars->tmem_empty[a], ((nj >> 1) & 1) ^ 1);   // the epilogue(s) drained this accumulator
-                tc_fence_after();
-                for (int kb = 0; kb < nkb; kb++, it++) {
-                    int s = it % STAGES;
-                    uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&bars->full[s], ph);
-                    tc_fence_after();
-                    uint64_t da = make_kmajor_sw128_desc(tiles + s * STAGE_BYTES);
-                    uint64_t dbb = make_kmajor_sw128_desc(tiles + s * STAGE_BYTES + TC_TILE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 8; k++) {
-                        if (PAIR) mma2_tf32_ss(tmem + a * BN, desc_advance(da, k * 32), desc_advance(dbb, k * 32), idesc, (kb | k) != 0);
-                        else mma_tf32_ss(tmem + a * BN, desc_advance(da, k * 32), desc_advance(dbb, k * 32), idesc, (kb | k) != 0);
-                    }
-                    if (PAIR) tc_commit2(&bars->empty[s], 3); else tc_commit(&bars->empty[s]);
-                }
-                if (PAIR) tc_commit2(&bars->tmem_full[a], 3); else tc_commit(&bars->tmem_full[a]);
-            }
-        }
-    } else {
-        uint32_t nj = 0;
-        for (int job = cta; job < njobs; job += nwalk, nj++) {
-            const int a = nj & 1;
-            int m0, n0, dir;
-            decode(job, m0, n0, dir);
-            const TcDir d = dir ? db : df;
-            float *spa = sp + a * 3 * BN;
-            if (GAUSS) {
-                // (the previous user of spa, job nj-2, finished its epilogue before this warp got here; the other three
-                // epilogue warps are synchronised by the named barrier below)
-                for (int c = threadIdx.x; c < BN; c += 128) {
-                    int j = n0 + c;
-                    float sd = em.p1[j];
-                    spa[c] = em.p0[j];
-                    spa[BN + c] = -0.5f * 1.4426950408889634f / (sd * sd);
-                    spa[2 * BN + c] = -log2f(sd * 2.5066282746310002f);
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-            const int64_t b = m0 + warp * 32 + lane;
-            const bool live = b < B;
-            const int64_t t = dir ? (T - 1 - step) : step;
-            float r = 0.f, x = 0.f;
-            const float *brow = nullptr;
-            if (live) {
-                const float *ps = d.psum + (b * 2 + src) * NT;
-                float c = 0.f;
-                for (int k = 0; k < NT; k++) c += ps[k];
-                r = 1.0f / c;
-                if (n0 == 0) d.logacc[b] += log((double)c);
-                if (GAUSS) {
-                    x = load_real<float>(em.obs, em.obs_dtype, b * T + t);
-                } else {
-                    int sym = load_symbol(em.obs, em.obs_dtype, b * T + t);
-                    sym = sym < 0 ? 0 : (sym >= em.M ? em.M - 1 : sym);
-                    brow = em.p0 + (int64_t)sym * N + n0;
-                }
-            }
-            mbar_wait(&bars->tmem_full[a], (nj >> 1) & 1);
-            tc_fence_after();
-            float rowsum = 0.f;
-            float *out = d.W + (b * 2 + dst) * N + n0;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (c0 == 128) {
-                    if (live) d.psum[(b * 2 + dst) * NT + (n0 >> 7)] = rowsum;
-                    rowsum = 0.f;
-                }
-                uint32_t acc[32];
-                tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + a * BN + c0, acc);
-                tmem_ld_wait();
-                if (live) {
-                    float v[32];
-#pragma unroll
-                    for (int q = 0; q < 32; q++) {
-                        v[q] = __uint_as_float(acc[q]) * r * tc_emission<GAUSS, BN>(em, spa, c0 + q, x, brow);
-                        rowsum += v[q];
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; q++)
-                        reinterpret_cast<float4 *>(out + c0)[q] = make_float4(round_tf32(v[4 * q]), round_tf32(v[4 * q + 1]),
-                                                                              round_tf32(v[4 * q + 2]), round_tf32(v[4 * q + 3]));
-                }
-            }
-            if (live) d.psum[(b * 2 + dst) * NT + (n0 >> 7) + 1] = rowsum;
-            // accumulator a may be overwritten: one arrival per epilogue warp, on the LEADER's barrier
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[a]), 0));
-                else mbar_arrive(&bars->tmem_empty[a]);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (PAIR) cluster_sync_all();      // the peer may still signal our barriers / use the paired TMEM
-    if (warp == 5) { if (PAIR) tmem_dealloc2(tmem, 512); else tmem_dealloc(tmem, 512); }
-}
-
-// Persistent per-step kernel (N % 256 == 0): one CTA (or CTA pair) per SM walks the step's (row tile, column tile,
-// direction) jobs with a grid-stride loop; the accumulator is double-buffered in TMEM (2 x 256 columns), so the
-// epilogue of one job (TMEM -> emission, scaling, row sums -> W_t in L2) runs under the MMAs of the next, and
-// barrier initialisation / TMEM allocation / descriptor prefetch happen once per step instead of once per tile.
-// Measured at c5 (256 jobs per step on 148 SMs): one-tile-per-CTA kernel 43.8 ms, persistent 37.8 ms.
-template <bool GAUSS>
-__global__ void __launch_bounds__(192, 1)
-tc_step_persist_kernel(const __grid_constant__ CUtensorMap mapXf, const __grid_constant__ CUtensorMap mapXb,
-                       const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df,
-                       TcDir db, TcEmis em, int64_t B, int64_t T, int N, int step, int mtiles, int ndir) {
-    tc_step_persist_body<GAUSS, false>(mapXf, mapXb, mapMf, mapMb, df, db, em, B, T, N, step, mtiles, ndir);
-}
-template <bool GAUSS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
-tc_step_persist_pair_kernel(const __grid_constant__ CUtensorMap mapXf, const __grid_constant__ CUtensorMap mapXb,
-                            const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df,
-                            TcDir db, TcEmis em, int64_t B, int64_t T, int N, int step, int mtiles, int ndir) {
-    tc_step_persist_body<GAUSS, true>(mapXf, mapXb, mapMf, mapMb, df, db, em, B, T, N, step, mtiles, ndir);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// Whole-recursion kernel (N % 256 == 0): ONE cooperative launch runs every time step.  The work of a step is a
-// set of independent CHAINS -- (row tile of 128 sequences, direction) -- each made of N/256 column-tile jobs
-// that only depend on the same chain's jobs of the previous step.  Lanes (chain, column tile) are dealt to the
-// CTAs round-robin once; every CTA walks (step, its lanes) in order and waits for a job's inputs on a per-chain
-// completion counter in global memory (release by the producing epilogue, acquire by the consuming TMA
-// producer) instead of on a kernel boundary.  This removes what bounds the launch-per-step kernels (measured:
-// 37.8 ms at c5 for 17 us of MMA time per 37 us step): the per-step prologue, the exposed last epilogue, the
-// launch gap and the wave tail of 256 jobs on 148 SMs -- chains drift apart freely, so an SM never idles
-// at a step boundary.  Progress: a job only waits for jobs that precede it in every CTA's (step, lane) order, so
-// the globally smallest unfinished job can always run (all CTAs are co-resident: cooperative launch).
+// helpers of the whole-recursion kernel
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {   // round to nearest even, lo in the low half
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -607,207 +229,15 @@ __device__ __forceinline__ void wait_chain(const uint32_t *ctr, uint32_t need) {
     }
 }
 
-// BF16 = true: bf16 operands (tcgen05 kind::f16, fp32 accumulation): a k-block of 128-byte rows then holds 64
-// elements instead of 32, i.e. twice the K per byte staged and twice the MMA rate.  Measured on the c5 shape the
-// log-likelihood moves by < 2e-6 relative (the rounding errors of 1,024 states average out).
-template <bool GAUSS, bool BF16>
-__global__ void __launch_bounds__(192, 1)
-tc_recursion_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_constant__ CUtensorMap mapXf1,
-                    const __grid_constant__ CUtensorMap mapXb0, const __grid_constant__ CUtensorMap mapXb1,
-                    const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df, TcDir db,
-                    TcEmis em, int64_t B, int64_t T, int N, int mtiles, int ndir, uint32_t *done, long long *trace) {
-#define RC_TRACE(ev)                                                                                   \
-    do {                                                                                               \
-        if (trace && blockIdx.x == 0 && step >= 8 && step < 12 && (threadIdx.x & 31) == 0)              \
-            trace[((step - 8) * 2 + (ln >= (int)gridDim.x ? 1 : 0)) * 16 + (ev)] = clock64();            \
-    } while (0)
-    constexpr int BN = 256;
-    constexpr int STAGE_BYTES = TC_TILE_BYTES + BN * TC_BK * 4;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    TcPBars<false> *bars = (TcPBars<false> *)(tiles + TC_STAGES * STAGE_BYTES);
-    float *sp = (float *)(bars + 1);  // [2 accumulators][3][256] emission constants of the job in that accumulator
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int BKE = BF16 ? 64 : TC_BK;       // elements per 128-byte k-block row
-    const int nkb = N / BKE, NT = N / 128, ntile_n = N / BN;
-    const int nlanes = mtiles * ntile_n * ndir;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 4); }
-        fence_barrier_init();
-    }
-    if (warp == 5) tmem_alloc(&bars->tmem_base, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-    // lane -> (row tile, column tile, direction); the row tile runs fastest so that neighbouring CTAs share a matrix tile
-    auto decode = [&](int ln, int &m0, int &n0, int &dir, int &chain) {
-        const int mt = ln % mtiles;
-        const int rest = ln / mtiles;
-        n0 = (rest % ntile_n) * BN;
-        dir = rest / ntile_n;
-        m0 = mt * TC_BM;
-        chain = dir * mtiles + mt;
-    };
-
-    if (warp == 4) {
-        if (elect_one()) {
-            tma_prefetch_desc(&mapXf0); tma_prefetch_desc(&mapXf1); tma_prefetch_desc(&mapMf);
-            if (ndir > 1) { tma_prefetch_desc(&mapXb0); tma_prefetch_desc(&mapXb1); tma_prefetch_desc(&mapMb); }
-            uint32_t it = 0;
-            for (int64_t step = 1; step < T; step++) {
-                const int src = (int)((step - 1) & 1);
-                for (int ln = blockIdx.x; ln < nlanes; ln += gridDim.x) {
-                    int m0, n0, dir, chain;
-                    decode(ln, m0, n0, dir, chain);
-                    // inputs: W_{step-1} of this chain = all its column-tile jobs of the previous step
-                    RC_TRACE(0);
-                    wait_chain(done + chain, (uint32_t)(ntile_n * (step - 1)));
-                    RC_TRACE(1);
-                    asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes -> TMA reads
-                    const CUtensorMap *mapX = dir ? (src ? &mapXb1 : &mapXb0) : (src ? &mapXf1 : &mapXf0);
-                    const CUtensorMap *mapM = dir ? &mapMb : &mapMf;
-                    for (int kb = 0; kb < nkb; kb++, it++) {
-                        int s = it % TC_STAGES;
-                        uint32_t ph = (it / TC_STAGES) & 1;
-                        mbar_wait(&bars->empty[s], ph ^ 1);
-                        mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
-                        tma_load_2d(tiles + s * STAGE_BYTES, mapX, &bars->full[s], kb * BKE, m0);
-                        tma_load_2d(tiles + s * STAGE_BYTES + TC_TILE_BYTES, mapM, &bars->full[s], kb * BKE, n0);
-                    }
-                }
-            }
-        }
-    } else if (warp == 5) {
-        if (elect_one()) {
-            const uint32_t idesc = BF16 ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN);
-            uint32_t it = 0, nj = 0;
-            for (int64_t step = 1; step < T; step++)
-                for (int ln = blockIdx.x; ln < nlanes; ln += gridDim.x, nj++) {
-                    const int a = nj & 1;
-                    mbar_wait(&bars->tmem_empty[a], ((nj >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
-                    RC_TRACE(4);
-                    tc_fence_after();
-                    for (int kb = 0; kb < nkb; kb++, it++) {
-                        if (kb == 1) RC_TRACE(5);
-                        int s = it % TC_STAGES;
-                        uint32_t ph = (it / TC_STAGES) & 1;
-                        mbar_wait(&bars->full[s], ph);
-                        tc_fence_after();
-                        uint64_t da = make_kmajor_sw128_desc(tiles + s * STAGE_BYTES);
-                        uint64_t dbb = make_kmajor_sw128_desc(tiles + s * STAGE_BYTES + TC_TILE_BYTES);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {      // 32 bytes of K per MMA: 8 tf32 or 16 bf16 elements
-                            if (BF16) mma_bf16_ss(tmem + a * BN, desc_advance(da, k * 32), desc_advance(dbb, k * 32), idesc, (kb | k) != 0);
-                            else mma_tf32_ss(tmem + a * BN, desc_advance(da, k * 32), desc_advance(dbb, k * 32), idesc, (kb | k) != 0);
-                        }
-                        tc_commit(&bars->empty[s]);
-                    }
-                    tc_commit(&bars->tmem_full[a]);
-                    RC_TRACE(6);
-                }
-        }
-    } else {
-        uint32_t nj = 0;
-        for (int64_t step = 1; step < T; step++) {
-            const int src = (int)((step - 1) & 1), dst = (int)(step & 1);
-            for (int ln = blockIdx.x; ln < nlanes; ln += gridDim.x, nj++) {
-                const int a = nj & 1;
-                int m0, n0, dir, chain;
-                decode(ln, m0, n0, dir, chain);
-                const TcDir d = dir ? db : df;
-                float *spa = sp + a * 3 * BN;
-                if (GAUSS) {
-                    for (int c = threadIdx.x; c < BN; c += 128) {
-                        int j = n0 + c;
-                        float sd = em.p1[j];
-                        spa[c] = em.p0[j];
-                        spa[BN + c] = -0.5f * 1.4426950408889634f / (sd * sd);
-                        spa[2 * BN + c] = -log2f(sd * 2.5066282746310002f);
-                    }
-                }
-                // the previous step's row sums of this chain come from other CTAs: acquire them
-                if (warp == 0) RC_TRACE(8);
-                wait_chain(done + chain, (uint32_t)(ntile_n * (step - 1)));
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int64_t b = m0 + warp * 32 + lane;
-                const bool live = b < B;
-                const int64_t t = dir ? (T - 1 - step) : step;
-                float r = 0.f, x = 0.f;
-                const float *brow = nullptr;
-                if (live) {
-                    const float *ps = d.psum + (b * 2 + src) * NT;
-                    float c = 0.f;
-                    for (int k = 0; k < NT; k++) c += __ldcg(ps + k);     // written by other SMs: bypass L1
-                    r = 1.0f / c;
-                    if (n0 == 0) d.logacc[b] += log((double)c);
-                    if (GAUSS) {
-                        x = load_real<float>(em.obs, em.obs_dtype, b * T + t);
-                    } else {
-                        int sym = load_symbol(em.obs, em.obs_dtype, b * T + t);
-                        sym = sym < 0 ? 0 : (sym >= em.M ? em.M - 1 : sym);
-                        brow = em.p0 + (int64_t)sym * N + n0;
-                    }
-                }
-                if (warp == 0) RC_TRACE(9);
-                mbar_wait(&bars->tmem_full[a], (nj >> 1) & 1);
-                if (warp == 0) RC_TRACE(10);
-                tc_fence_after();
-                float rowsum = 0.f;
-                float *out = d.W + (b * 2 + dst) * N + n0;
-                uint32_t *outh = reinterpret_cast<uint32_t *>(d.W) + (((b * 2 + dst) * N + n0) >> 1);   // bf16 pairs
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    if (c0 == 128) {
-                        if (live) d.psum[(b * 2 + dst) * NT + (n0 >> 7)] = rowsum;
-                        rowsum = 0.f;
-                    }
-                    uint32_t acc[32];
-                    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + a * BN + c0, acc);
-                    tmem_ld_wait();
-                    if (live) {
-                        float v[32];
-#pragma unroll
-                        for (int q = 0; q < 32; q++) {
-                            v[q] = __uint_as_float(acc[q]) * r * tc_emission<GAUSS, BN>(em, spa, c0 + q, x, brow);
-                            rowsum += v[q];
-                        }
-                        if (BF16) {
-#pragma unroll
-                            for (int q = 0; q < 4; q++)
-                                reinterpret_cast<uint4 *>(outh + (c0 >> 1))[q] =
-                                    make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                               pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 8; q++)
-                                reinterpret_cast<float4 *>(out + c0)[q] = make_float4(round_tf32(v[4 * q]), round_tf32(v[4 * q + 1]),
-                                                                                      round_tf32(v[4 * q + 2]), round_tf32(v[4 * q + 3]));
-                        }
-                    }
-                }
-                if (live) d.psum[(b * 2 + dst) * NT + (n0 >> 7) + 1] = rowsum;
-                // accumulator a may be overwritten
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->tmem_empty[a]);
-                // publish the job: every thread's W / row-sum / log-accumulator stores, then one release increment
-                __threadfence();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done + chain) : "memory");
-                if (warp == 0) RC_TRACE(11);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem, 512);
-}
 
 // ------------------------------------------------------------------------------------------------------
-// Whole-recursion kernel, second generation.  The clock64 timeline of tc_recursion_kernel (tools/dbg_rc_trace.py)
+// Whole-recursion kernel (second generation; the first one, tc_recursion_kernel, is in the history of this file:
+// one epilogue warpgroup, lanes dealt to CTAs once).  ONE cooperative launch runs every time step: the work of a step
+// is a set of independent CHAINS -- (row tile of 128 sequences, direction) -- each made of N/BN column-tile jobs that
+// only depend on the same chain's jobs of the previous step; a job waits for its inputs on a per-chain completion
+// counter in global memory (release by the producing epilogue, acquire by the consuming TMA thread) instead of on a
+// kernel boundary, and only ever for jobs that precede it in every CTA's order, so the globally smallest unfinished
+// job can always run (all CTAs are co-resident).  The clock64 timeline of the first generation (tools/dbg_rc_trace.py)
 // showed a job's MMAs taking 8.7k cycles (bf16) while its epilogue took 19k -- 9.5k of exposed L2 latency before the
 // accumulator is even needed (serial row-sum loads, emission constants, a CTA barrier) and 9.4k of TMEM reads,
 // emission evaluation and thread-per-row stores -- with ONE epilogue warpgroup serialising both; and 108 of the 148
@@ -1301,15 +731,15 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     }
-    // KHMM_RC_MODE (development switch): 1 = first-generation kernels, 2 = whole-recursion kernel, second generation, on
-    // single CTAs, 3 = on CTA pairs where the shape allows.  Measured at c5 (B = 4096, T = 1024, N = 1024): bf16 17.5 ms
+    // KHMM_RC_MODE (development switch): 1 = one launch per step (the path without cooperative launch), 2 = whole-recursion
+    // kernel on single CTAs, 3 = on CTA pairs where the shape allows.  Measured at c5 (B = 4096, T = 1024, N = 1024): bf16 17.5 ms
     // single / 17.9 ms pairs; tf32 ~29 ms single / 25.8 ms pairs
     int rc_mode = KHMM_RC2 ? ((KHMM_RC2_PAIR && !bf16) ? 3 : 2) : 1;
     if (const char *e = getenv("KHMM_RC_MODE")) rc_mode = atoi(e);
     const bool use_rc2 = coop && rc_mode >= 2;         // any N % 128 == 0, any batch: one launch for all T-1 steps
     if (bf16) {
-        if (!use_rc2 && !(N % 256 == 0 && coop && (Bp / TC_BM) * (N / 256) * ndir >= sm_count())) {
-            set_error("fwdbwd_loglik_tc: bf16 operands need a device with cooperative launch");
+        if (!use_rc2) {
+            set_error("fwdbwd_loglik_tc: bf16 operands need the whole-recursion kernel (cooperative launch)");
             return KHMM_ERR_UNSUPPORTED;
         }
         tc_to_bf16_kernel<<<64, 256, 0, st>>>(A, (__nv_bfloat16 *)Ar, N * N);
@@ -1362,7 +792,6 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
         set_error("tensor map creation for the transition matrix failed");
         return KHMM_ERR_CUDA;
     }
-    const bool pair = KHMM_TC_PAIR && BN == 256 && ((Bp / TC_BM) % 2 == 0);
     if (use_rc2) {
         const int mtiles = (int)(Bp / TC_BM);
         const bool rpair = rc_mode == 3 && BN == 256 && mtiles % 2 == 0;
@@ -1410,74 +839,17 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
             le = cudaLaunchKernel(kern, dim3(grid), dim3(320), args, smem, st);
         }
         KHMM_CUDA_CHECK(le);
-    } else if (coop && (KHMM_TC_WHOLE || bf16) && BN == 256) {
-        // one cooperative launch for all T-1 steps
-        const int mtiles = (int)(Bp / TC_BM);
-        const int nlanes = mtiles * (N / 256) * ndir;
-        int grid = nlanes < sm_count() ? nlanes : sm_count();
-        size_t smem = TC_STAGES * (size_t)(TC_TILE_BYTES + 256 * TC_BK * 4) + sizeof(TcPBars<false>) + 2 * 3 * 256 * sizeof(float) + 1024;
-        auto kern = bf16 ? tc_recursion_kernel<GAUSS, true> : tc_recursion_kernel<GAUSS, false>;
-        KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        KHMM_CUDA_CHECK(cudaMemsetAsync(done, 0, 2 * (size_t)mtiles * sizeof(uint32_t), st));
-        int Ni = N, mt = mtiles, nd = ndir;
-        int64_t Bv = B, Tv = T;
-        void *args[] = {&mapX[0][0], &mapX[0][1], &mapX[1][0], &mapX[1][1], &mapM[0], &mapM[1], &d[0], &d[1], &em,
-                        &Bv, &Tv, &Ni, &mt, &nd, &done, &g_rc_trace};
-        KHMM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(192), args, smem, st));
-    } else if (KHMM_TC_PERSIST && BN == 256) {
-        const int mtiles = (int)(Bp / TC_BM);
-        const bool ppair = KHMM_TC_PERSIST_PAIR && (mtiles % 2 == 0);
-        CUtensorMap mapH[2];
-        if (ppair && (make_tmap_f32_rowmajor(&mapH[0], ATr, N, N, 128) || make_tmap_f32_rowmajor(&mapH[1], Ar, N, N, 128))) {
-            set_error("tensor map creation for the transition matrix failed");
-            return KHMM_ERR_CUDA;
-        }
-        const int stages = ppair ? 6 : TC_STAGES;
-        const size_t stage_bytes = TC_TILE_BYTES + (size_t)(ppair ? 128 : 256) * TC_BK * 4;
-        size_t smem = stages * stage_bytes + (ppair ? sizeof(TcPBars<true>) : sizeof(TcPBars<false>)) +
-                      2 * 3 * 256 * sizeof(float) + 1024;
-        auto kern = ppair ? tc_step_persist_pair_kernel<GAUSS> : tc_step_persist_kernel<GAUSS>;
-        KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int njobs = (ppair ? mtiles / 2 : mtiles) * (N / 256) * ndir;
-        int grid;
-        if (ppair) {
-            int walkers = sm_count() / 2;
-            grid = 2 * (njobs < walkers ? njobs : walkers);
-        } else {
-            grid = njobs < sm_count() ? njobs : sm_count();
-        }
-        for (int step = 1; step < T; step++) {
-            int src = (step - 1) & 1;
-            kern<<<grid, 192, smem, st>>>(mapX[0][src], mapX[1][src], ppair ? mapH[0] : mapM[0], ppair ? mapH[1] : mapM[1], d[0],
-                                          d[1], em, B, T, N, step, mtiles, ndir);
-        }
-        KHMM_LAUNCH_CHECK("tc_step_persist_kernel");
-    } else if (pair) {
-        // CTA-pair kernel: each CTA loads 128 of the 256 matrix rows of its pair's tile
-        CUtensorMap mapH[2];
-        if (make_tmap_f32_rowmajor(&mapH[0], ATr, N, N, 128) || make_tmap_f32_rowmajor(&mapH[1], Ar, N, N, 128)) {
-            set_error("tensor map creation for the transition matrix failed");
-            return KHMM_ERR_CUDA;
-        }
-        size_t smem = TC2_STAGES * (size_t)TC2_STAGE_BYTES + sizeof(Tc2Bars) + 3 * 256 * sizeof(float) + 1024;
-        auto kern = tc_step2_kernel<GAUSS>;
-        KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)(Bp / TC_BM), N / 256, ndir);
-        for (int step = 1; step < T; step++) {
-            int src = (step - 1) & 1;
-            kern<<<grid, 192, smem, st>>>(mapX[0][src], mapX[1][src], mapH[0], mapH[1], d[0], d[1], em, B, T, N, step);
-        }
-        KHMM_LAUNCH_CHECK("tc_step2_kernel");
     } else {
-    size_t smem = TC_STAGES * (size_t)(TC_TILE_BYTES + BN * TC_BK * 4) + sizeof(TcBars) + 3 * BN * sizeof(float) + 1024;
-    auto kern = BN == 256 ? tc_step_kernel<GAUSS, 256> : tc_step_kernel<GAUSS, 128>;
-    KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)(Bp / TC_BM), N / BN, ndir);
-    for (int step = 1; step < T; step++) {
-        int src = (step - 1) & 1;
-        kern<<<grid, 192, smem, st>>>(mapX[0][src], mapX[1][src], mapM[0], mapM[1], d[0], d[1], em, B, T, N, step);
-    }
-    KHMM_LAUNCH_CHECK("tc_step_kernel");
+        // no cooperative launch (or KHMM_RC_MODE=1): one launch per time step, tf32 operands
+        size_t smem = TC_STAGES * (size_t)(TC_TILE_BYTES + BN * TC_BK * 4) + sizeof(TcBars) + 3 * BN * sizeof(float) + 1024;
+        auto kern = BN == 256 ? tc_step_kernel<GAUSS, 256> : tc_step_kernel<GAUSS, 128>;
+        KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)(Bp / TC_BM), N / BN, ndir);
+        for (int step = 1; step < T; step++) {
+            int src = (step - 1) & 1;
+            kern<<<grid, 192, smem, st>>>(mapX[0][src], mapX[1][src], mapM[0], mapM[1], d[0], d[1], em, B, T, N, step);
+        }
+        KHMM_LAUNCH_CHECK("tc_step_kernel");
     }
     if (bf16) tc_final_kernel<true><<<dim3((unsigned)B, ndir), 256, 0, st>>>(d[0], d[1], pi, B, T, N, loglik, loglik_bwd);
     else tc_final_kernel<false><<<dim3((unsigned)B, ndir), 256, 0, st>>>(d[0], d[1], pi, B, T, N, loglik, loglik_bwd);

@@ -696,8 +696,8 @@ def test_loglik_host_batch_pipelined_path_matches_device_path(K):
 
 
 def test_tensor_core_loglik_persistent_tiles(K):
-    """N = 512 with more (row tile, column tile, direction) jobs than SMs: the persistent per-step kernel
-    (double-buffered TMEM accumulators, several jobs per CTA) against the float64 oracle."""
+    """N = 512 with more (row tile, column tile, direction) jobs than SMs (several jobs per CTA and step, TMEM
+    accumulators double-buffered) against the float64 oracle."""
     import torch
     N, B, T = 512, 38 * 128, 6
     np.random.seed(95)
