@@ -320,16 +320,21 @@ static int launch_viterbi_tile(int64_t B, int64_t T, int M, const double *logpi,
 // 320-390 ms instead of 187 ms at c3) and in shared memory, grouped by four sources, for N = 128 (the same layout at
 // N = 64 measured 224-230 ms against 187 ms for the register copy and 349 ms for the float64 kernel).  8 warps per
 // CTA in both cases: at N = 128 sixteen warps leave 128 registers and spill (48.9 ms at B = 16384, T = 512, no
-// better than the float64 register-tile kernel's 47.7 ms); eight warps with 255 registers run 24.6 ms.
-#ifndef KHMM_VIT_AREG_MAX
-#define KHMM_VIT_AREG_MAX 64
+// better than the float64 register-tile kernel's 47.7 ms); eight warps with 255 registers run 24.6 ms.  A hybrid at
+// N = 64 (one target per lane in registers, the other in shared memory; 10 / 12 / 16 warps) measured 224 / 198 / 230 ms.
+#ifndef KHMM_VIT_JR64
+#define KHMM_VIT_JR64 2        /* N = 64: targets per lane whose fl32(logA) column sits in registers (0..2) */
+#endif
+#ifndef KHMM_VIT_WARPS64
+#define KHMM_VIT_WARPS64 8
 #endif
 template <int NN>
 struct VitScreen {
-    static constexpr bool AREG = NN <= KHMM_VIT_AREG_MAX;
-    static constexpr int WARPS = 8;
+    static constexpr int JT = NN / 32;
+    static constexpr int JR = NN < 64 ? JT : (NN == 64 ? KHMM_VIT_JR64 : 0);   // targets per lane with a register copy
+    static constexpr int WARPS = NN == 64 ? KHMM_VIT_WARPS64 : 8;
     static constexpr size_t smem_bytes() {
-        return sizeof(double) * (NN * NN + WARPS * NN) + sizeof(float) * WARPS * NN + (AREG ? 0 : sizeof(float) * NN * NN);
+        return sizeof(double) * (NN * NN + WARPS * NN) + sizeof(float) * WARPS * NN + (JR == JT ? 0 : sizeof(float) * NN * NN);
     }
 };
 template <int NN, typename PSI>
@@ -338,8 +343,7 @@ viterbi_screen_kernel(int64_t B, int64_t T, int M, const double *__restrict__ lo
                       const double *__restrict__ logBsm, const void *__restrict__ obs, int obs_dtype,
                       const int32_t *__restrict__ lengths, PSI *__restrict__ psi, int32_t *__restrict__ last_state,
                       double *__restrict__ logp) {
-    constexpr int JT = NN / 32, WARPS = VitScreen<NN>::WARPS;
-    constexpr bool kVitAReg = VitScreen<NN>::AREG;
+    constexpr int JT = NN / 32, WARPS = VitScreen<NN>::WARPS, JR = VitScreen<NN>::JR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *A64 = reinterpret_cast<double *>(smem_raw);                 // [NN][NN]
     double *drow = A64 + NN * NN;                                       // [WARPS][NN]  delta_{t-1}, float64
@@ -361,17 +365,16 @@ viterbi_screen_kernel(int64_t B, int64_t T, int M, const double *__restrict__ lo
     for (int k = 1; k < WARPS; k++) ap = fmaxf(ap, apos_red[k]);
     const float apos2 = 2.f * ap;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    float4 a4r[kVitAReg ? JT : 1][kVitAReg ? NN / 4 : 1];      // register copy: a4r[q][g] = fl32(logA[4g .. 4g+3][l + 32 q])
-    if (kVitAReg) {
+    float4 a4r[JR ? JR : 1][JR ? NN / 4 : 1];      // register copy: a4r[q][g] = fl32(logA[4g .. 4g+3][l + 32 q]), q < JR
 #pragma unroll
-        for (int q = 0; q < JT; q++)
+    for (int q = 0; q < JR; q++)
 #pragma unroll
-            for (int g = 0; g < NN / 4; g++) {
-                const int j = l + 32 * q;
-                a4r[kVitAReg ? q : 0][kVitAReg ? g : 0] = make_float4((float)A64[(4 * g) * NN + j], (float)A64[(4 * g + 1) * NN + j],
-                                                                      (float)A64[(4 * g + 2) * NN + j], (float)A64[(4 * g + 3) * NN + j]);
-            }
-    } else {
+        for (int g = 0; g < NN / 4; g++) {
+            const int j = l + 32 * q;
+            a4r[JR ? q : 0][JR ? g : 0] = make_float4((float)A64[(4 * g) * NN + j], (float)A64[(4 * g + 1) * NN + j],
+                                                      (float)A64[(4 * g + 2) * NN + j], (float)A64[(4 * g + 3) * NN + j]);
+        }
+    if (JR < JT) {
         for (int k = threadIdx.x; k < (NN / 4) * NN; k += blockDim.x) {
             const int g = k / NN, j = k % NN;
             A32g[k] = make_float4((float)A64[(4 * g) * NN + j], (float)A64[(4 * g + 1) * NN + j], (float)A64[(4 * g + 2) * NN + j],
@@ -456,7 +459,7 @@ viterbi_screen_kernel(int64_t B, int64_t T, int M, const double *__restrict__ lo
 #pragma unroll
                     for (int g = 0; g < NN / 4; g++) {
                         const float4 x4 = *reinterpret_cast<const float4 *>(dlw + 4 * g);
-                        const float4 a4 = kVitAReg ? a4r[kVitAReg ? q : 0][kVitAReg ? g : 0] : A32g[g * NN + l + 32 * q];
+                        const float4 a4 = q < JR ? a4r[q < JR ? q : 0][JR ? g : 0] : A32g[g * NN + l + 32 * q];
                         const float2 s01 = __fadd2_rn(make_float2(x4.x, x4.y), make_float2(a4.x, a4.y));
                         const float2 s23 = __fadd2_rn(make_float2(x4.z, x4.w), make_float2(a4.z, a4.w));
                         float pg = s01.x;
