@@ -14,7 +14,11 @@
 
 namespace khmm {
 
+// Sequences per CTA: 4 share every transition-matrix element a thread loads; small batches (fewer groups of four than
+// SMs -- a single sequence of the reference's own tests is the extreme) run one sequence per CTA instead: the
+// per-step instruction count of a lone warp drops ~4x (its predicated-off slots are gone) and more SMs get a CTA.
 constexpr int kSeqPerCta = 4;
+static int seq_per_cta(int64_t B) { return (B + kSeqPerCta - 1) / kSeqPerCta < sm_count() ? 1 : kSeqPerCta; }
 
 template <typename R, int S>
 struct RowBuf {  // [N][S] rows in shared memory, vector access of the S values of a state
@@ -62,12 +66,11 @@ __device__ __forceinline__ void load_matrix_smem(R *dst, const R *src, int n) {
 }
 
 // --------------------------------------------------------------------------- forward
-template <typename R, class Emis, bool A_SMEM>
+template <typename R, class Emis, bool A_SMEM, int S>
 __global__ void __launch_bounds__(1024)
 forward_generic_kernel(int64_t B, int64_t T, int N, const R *__restrict__ pi, const R *__restrict__ A, Emis em,
                        const int32_t *__restrict__ lengths, R *__restrict__ alpha, R *__restrict__ scale,
                        double *__restrict__ loglik) {
-    constexpr int S = kSeqPerCta;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x, nwarps = NT >> 5, j = threadIdx.x;
     R *rows = reinterpret_cast<R *>(smem_raw);          // [2][NT][S]
@@ -160,13 +163,12 @@ struct EstepOut {
     int M;
 };
 
-template <typename R, class Emis, bool A_SMEM, bool ESTEP>
+template <typename R, class Emis, bool A_SMEM, bool ESTEP, int S>
 __global__ void __launch_bounds__(1024)
 backward_generic_kernel(int64_t B, int64_t T, int N, const R *__restrict__ AT, Emis em,
                         const int32_t *__restrict__ lengths, const R *__restrict__ scale,
                         const R *__restrict__ alpha, R *__restrict__ beta, R *__restrict__ gamma, int gamma_kind,
                         R *__restrict__ V, EstepOut eo) {
-    constexpr int S = kSeqPerCta;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x, nwarps = NT >> 5, i = threadIdx.x;
     R *rows = reinterpret_cast<R *>(smem_raw);  // [2][NT][S]
@@ -330,9 +332,9 @@ backward_generic_kernel(int64_t B, int64_t T, int N, const R *__restrict__ AT, E
 
 // ------------------------------------------------------------------------ launchers
 template <typename R>
-static size_t generic_smem(int N, bool a_smem) {
+static size_t generic_smem(int N, bool a_smem, int S = kSeqPerCta) {
     int NT = ((N + 31) / 32) * 32;
-    size_t b = sizeof(R) * ((size_t)2 * NT * kSeqPerCta + 2 * kSeqPerCta * 32);
+    size_t b = sizeof(R) * ((size_t)2 * NT * S + 2 * S * 32);
     if (a_smem) b += sizeof(R) * (size_t)N * N;
     return b;
 }
@@ -340,8 +342,8 @@ static size_t generic_smem(int N, bool a_smem) {
 template <typename R>
 static bool a_fits_smem(int N) { return generic_smem<R>(N, true) <= 200 * 1024; }
 
-static int grid_for(int64_t B, int ctas_per_sm) {
-    int64_t ngroups = (B + kSeqPerCta - 1) / kSeqPerCta;
+static int grid_for(int64_t B, int ctas_per_sm, int S = kSeqPerCta) {
+    int64_t ngroups = (B + S - 1) / S;
     int64_t cap = (int64_t)sm_count() * ctas_per_sm;
     return (int)(ngroups < cap ? (ngroups > 0 ? ngroups : 1) : cap);
 }
@@ -364,12 +366,14 @@ static int launch_forward(int64_t B, int64_t T, int N, const R *pi, const R *A, 
     KHMM_REQUIRE(pi && A, "forward: pi/A must not be NULL");
     int NT = ((N + 31) / 32) * 32;
     bool as = a_fits_smem<R>(N);
-    size_t smem = generic_smem<R>(N, as);
+    const int S = seq_per_cta(B);
+    size_t smem = generic_smem<R>(N, as, S);
     // occupancy-aware grid: small CTAs -> several per SM
     int per_sm = NT <= 64 ? 16 : (NT <= 128 ? 8 : (NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)));
     if (as && smem > 48 * 1024) per_sm = (int)max((size_t)1, min((size_t)per_sm, (size_t)(220 * 1024) / smem));
-    int grid = grid_for(B, per_sm);
-    auto kern = as ? forward_generic_kernel<R, Emis, true> : forward_generic_kernel<R, Emis, false>;
+    int grid = grid_for(B, per_sm, S);
+    auto kern = S == 1 ? (as ? forward_generic_kernel<R, Emis, true, 1> : forward_generic_kernel<R, Emis, false, 1>)
+                       : (as ? forward_generic_kernel<R, Emis, true, kSeqPerCta> : forward_generic_kernel<R, Emis, false, kSeqPerCta>);
     if (smem > 48 * 1024)
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NT, smem, (cudaStream_t)stream>>>(B, T, N, pi, A, em, lengths, alpha, scale, loglik);
@@ -389,11 +393,14 @@ static int launch_backward(int64_t B, int64_t T, int N, const R *AT, Emis em, co
     KHMM_REQUIRE(!ESTEP || (alpha && eo.counts), "estep: needs alpha and counts");
     int NT = ((N + 31) / 32) * 32;
     bool as = a_fits_smem<R>(N);
-    size_t smem = generic_smem<R>(N, as);
+    const int S = seq_per_cta(B);
+    size_t smem = generic_smem<R>(N, as, S);
     int per_sm = NT <= 64 ? 16 : (NT <= 128 ? 8 : (NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)));
     if (as && smem > 48 * 1024) per_sm = (int)max((size_t)1, min((size_t)per_sm, (size_t)(220 * 1024) / smem));
-    int grid = grid_for(B, per_sm);
-    auto kern = as ? backward_generic_kernel<R, Emis, true, ESTEP> : backward_generic_kernel<R, Emis, false, ESTEP>;
+    int grid = grid_for(B, per_sm, S);
+    auto kern = S == 1 ? (as ? backward_generic_kernel<R, Emis, true, ESTEP, 1> : backward_generic_kernel<R, Emis, false, ESTEP, 1>)
+                       : (as ? backward_generic_kernel<R, Emis, true, ESTEP, kSeqPerCta>
+                             : backward_generic_kernel<R, Emis, false, ESTEP, kSeqPerCta>);
     if (smem > 48 * 1024)
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NT, smem, (cudaStream_t)stream>>>(B, T, N, AT, em, lengths, scale, alpha, beta, gamma, gamma_kind, V,

@@ -19,13 +19,12 @@ namespace khmm {
 
 constexpr int kVitSeq = 4;
 
-template <typename PSI, bool A_SMEM>
+template <typename PSI, bool A_SMEM, int S>
 __global__ void __launch_bounds__(1024)
 viterbi_generic_kernel(int64_t B, int64_t T, int N, int M, const double *__restrict__ logpi,
                        const double *__restrict__ logA, const double *__restrict__ logBsm, const void *__restrict__ obs,
                        int obs_dtype, const int32_t *__restrict__ lengths, PSI *__restrict__ psi,
                        int32_t *__restrict__ last_state, double *__restrict__ logp) {
-    constexpr int S = kVitSeq;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x, j = threadIdx.x;
     double *rows = reinterpret_cast<double *>(smem_raw);  // [2][NT][S]
@@ -84,23 +83,33 @@ viterbi_generic_kernel(int64_t B, int64_t T, int N, int M, const double *__restr
 #pragma unroll
                 for (int s = 0; s < S; s++) { best[s] = lpj; arg[s] = 0; }
             } else if (active) {
-                {
-                    double a0 = Am[j];
-                    double2 p0 = *reinterpret_cast<const double2 *>(prev);
-                    double2 p1 = *reinterpret_cast<const double2 *>(prev + 2);
-                    best[0] = p0.x + a0; best[1] = p0.y + a0; best[2] = p1.x + a0; best[3] = p1.y + a0;
+                auto load_row = [&](int i, double (&p)[S]) {       // the S values delta_{t-1}[i] of the CTA's sequences
+                    if constexpr (S == 4) {
+                        const double2 p0 = *reinterpret_cast<const double2 *>(prev + i * S);
+                        const double2 p1 = *reinterpret_cast<const double2 *>(prev + i * S + 2);
+                        p[0] = p0.x; p[1] = p0.y; p[2] = p1.x; p[3] = p1.y;
+                    } else {
 #pragma unroll
-                    for (int s = 0; s < S; s++) arg[s] = 0;
+                        for (int s = 0; s < S; s++) p[s] = prev[i * S + s];
+                    }
+                };
+                {
+                    const double a0 = Am[j];
+                    double p[S];
+                    load_row(0, p);
+#pragma unroll
+                    for (int s = 0; s < S; s++) { best[s] = p[s] + a0; arg[s] = 0; }
                 }
 #pragma unroll 4
                 for (int i = 1; i < N; i++) {
-                    double aij = Am[i * N + j];
-                    double2 p0 = *reinterpret_cast<const double2 *>(prev + i * S);
-                    double2 p1 = *reinterpret_cast<const double2 *>(prev + i * S + 2);
-                    double v[S] = {p0.x + aij, p0.y + aij, p1.x + aij, p1.y + aij};
+                    const double aij = Am[i * N + j];
+                    double p[S];
+                    load_row(i, p);
 #pragma unroll
-                    for (int s = 0; s < S; s++)
-                        if (v[s] > best[s]) { best[s] = v[s]; arg[s] = i; }
+                    for (int s = 0; s < S; s++) {
+                        const double v = p[s] + aij;
+                        if (v > best[s]) { best[s] = v; arg[s] = i; }
+                    }
                 }
             }
 #pragma unroll
@@ -591,7 +600,8 @@ template <typename PSI>
 static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, const double *logA,
                        const double *logBsm, const void *obs, int obs_dtype, const int32_t *lengths, void *backptr,
                        void *path, int path_dtype, double *logp, cudaStream_t st) {
-    constexpr int S = kVitSeq;
+    // small batches: one sequence per CTA (a lone warp then issues a quarter of the instructions per step)
+    const int S = (B + kVitSeq - 1) / kVitSeq < sm_count() ? 1 : kVitSeq;
     int NT = ((N + 31) / 32) * 32;
     size_t rows_b = sizeof(double) * 2 * NT * S;
     size_t a_b = sizeof(double) * (size_t)N * N;
@@ -621,7 +631,8 @@ static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, 
         int64_t ngroups = (B + S - 1) / S;
         int64_t cap = (int64_t)sm_count() * per_sm;
         int grid = (int)(ngroups < cap ? ngroups : cap);
-        auto kern = as ? viterbi_generic_kernel<PSI, true> : viterbi_generic_kernel<PSI, false>;
+        auto kern = S == 1 ? (as ? viterbi_generic_kernel<PSI, true, 1> : viterbi_generic_kernel<PSI, false, 1>)
+                           : (as ? viterbi_generic_kernel<PSI, true, kVitSeq> : viterbi_generic_kernel<PSI, false, kVitSeq>);
         if (smem > 48 * 1024)
             KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NT, smem, st>>>(B, T, N, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp);
