@@ -659,6 +659,26 @@ def test_baumwelch_config4_full_size_properties(K):
     np.testing.assert_allclose(ll_simt[:4], ref, rtol=F32_RTOL)
 
 
+@pytest.mark.parametrize("N,B,T", [(128, 1, 1), (256, 3, 2), (128, 1, 7), (512, 129, 3)])
+def test_tensor_core_loglik_degenerate_shapes(K, N, B, T):
+    """The whole-recursion kernel at its edges: a single time step (no recursion job at all), two steps, a single
+    sequence (one row tile with 127 padded rows), one sequence more than a row tile."""
+    import torch
+    np.random.seed(400 + N + T)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(401 + B)
+    x = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T))).astype(np.float32)
+    ref = O.loglik(O.forward(pi, A, O.emissions_gaussian_1d(mean, sd, x.astype(np.float64)))[1])
+    # operands rounded to tf32 / bf16: ~2^-11 / 2^-8 per emission value, and with sd = 1 only a few states carry a step's
+    # probability, so the ABSOLUTE error of log P is ~1e-3 / ~1e-2 per step at worst -- visible on these tiny T
+    for mode, atol in ((True, 3e-3 * T), ("bf16", 2e-2 * T)):
+        ll, llb = h.log_likelihood_batch(torch.from_numpy(x).cuda(), tensor_cores=mode)
+        assert np.isfinite(ll.cpu().numpy()).all() and np.isfinite(llb.cpu().numpy()).all()
+        np.testing.assert_allclose(ll.cpu().numpy(), ref, rtol=0, atol=atol)
+        np.testing.assert_allclose(llb.cpu().numpy(), ref, rtol=0, atol=atol)
+
+
 def test_fwdbwd_config2_shape_properties(K):
     """N=8 Gaussian, T=2048 at a reduced batch: forward and backward likelihoods agree, and the
     oracle agrees on a sub-sample."""
