@@ -141,7 +141,9 @@ forward_generic_kernel(int64_t B, int64_t T, int N, const R *__restrict__ pi, co
                     if (alpha && active) alpha[(b * T + t) * N + j] = val[s];
                     if (j == 0) {
                         if (scale) scale[b * T + t] = c[s];
-                        ll[s] += log((double)c[s]);
+                        // with the scale factors going to memory, log P is summed from them afterwards by
+                        // loglik_from_scale_kernel: a float64 log per step on thread 0 is on every step's critical path
+                        else ll[s] += log((double)c[s]);
                     }
                 }
             }
@@ -149,12 +151,42 @@ forward_generic_kernel(int64_t B, int64_t T, int N, const R *__restrict__ pi, co
             __syncthreads();
             cur ^= 1;
         }
-        if (j == 0 && loglik) {
+        if (j == 0 && loglik && !scale) {
 #pragma unroll
             for (int s = 0; s < S; s++)
                 if (b0 + s < B) loglik[b0 + s] = ll[s];
         }
     }
+}
+
+// log P(O_b) = sum_t log c_t from the stored scale factors: one warp per sequence, lane l adds t = l, l+32, ... in
+// order, then a fixed shuffle tree (deterministic; abstract_hmm.py:241-248 sums the same logs)
+template <typename R>
+__global__ void loglik_from_scale_kernel(int64_t B, int64_t T, const int32_t *__restrict__ lengths, const R *__restrict__ scale,
+                                         double *__restrict__ loglik) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    const int len = lengths ? lengths[b] : (int)T;
+    double acc = 0.0;
+    for (int t = lane; t < len; t += 32) acc += log((double)scale[b * T + t]);
+    acc = warp_sum(acc);
+    if (lane == 0) loglik[b] = acc;
+}
+
+// E-step: sum over the batch of log P(O_b) = sum_{b,t} log c_t into the count buffer's tail (a float64 log per step on
+// thread 0 of the backward kernel was on every step's critical path)
+template <typename R>
+__global__ void estep_loglik_kernel(int64_t B, int64_t T, const int32_t *__restrict__ lengths, const R *__restrict__ scale,
+                                    double *__restrict__ tail) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    const int len = lengths ? lengths[b] : (int)T;
+    double acc = 0.0;
+    for (int t = lane; t < len; t += 32) acc += log((double)scale[b * T + t]);
+    acc = warp_sum(acc);
+    if (lane == 0 && len > 0) atomicAdd(tail, acc);
 }
 
 // ------------------------------------------------------------- backward (+gamma, +E-step)
@@ -182,7 +214,7 @@ backward_generic_kernel(int64_t B, int64_t T, int N, const R *__restrict__ AT, E
     const bool active = i < N;
     const int64_t ngroups = (B + S - 1) / S;
     // E-step accumulators owned by state i (flushed once per CTA)
-    double acc_pi = 0, acc_gam = 0, acc_den = 0, acc_ll = 0, acc_nseq = 0;
+    double acc_pi = 0, acc_gam = 0, acc_den = 0, acc_nseq = 0;    // (sum log c_t: estep_loglik_kernel)
     int flag = 0;
     double *c_pi = nullptr, *c_gam = nullptr, *c_num = nullptr, *c_den = nullptr, *c_tail = nullptr;
     if (ESTEP) {
@@ -302,7 +334,6 @@ backward_generic_kernel(int64_t B, int64_t T, int N, const R *__restrict__ AT, E
                         if (t < len[s] - 1) acc_gam += w;
                         if (V) V[((b0 + s) * T + t) * N + i] = vnew[s];
                     }
-                    if (i == 0 && t < len[s]) acc_ll += log((double)ct[s]);
                 }
             }
             RowBuf<R, S> vnext{rows + (cur ^ 1) * NT * S};
@@ -323,7 +354,6 @@ backward_generic_kernel(int64_t B, int64_t T, int N, const R *__restrict__ AT, E
             atomicAdd(c_den + i, acc_den);
         }
         if (i == 0) {
-            atomicAdd(c_tail + 0, acc_ll);
             atomicAdd(c_tail + 1, acc_nseq);
         }
         if (flag && i == 0) atomicAdd(c_tail + 2, 1.0);
@@ -378,6 +408,11 @@ static int launch_forward(int64_t B, int64_t T, int N, const R *pi, const R *A, 
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NT, smem, (cudaStream_t)stream>>>(B, T, N, pi, A, em, lengths, alpha, scale, loglik);
     KHMM_LAUNCH_CHECK("forward_generic_kernel");
+    if (loglik && scale) {
+        const int64_t nthreads = B * 32;
+        loglik_from_scale_kernel<R><<<(unsigned)((nthreads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(B, T, lengths, scale, loglik);
+        KHMM_LAUNCH_CHECK("loglik_from_scale_kernel");
+    }
     return KHMM_OK;
 }
 
@@ -406,6 +441,11 @@ static int launch_backward(int64_t B, int64_t T, int N, const R *AT, Emis em, co
     kern<<<grid, NT, smem, (cudaStream_t)stream>>>(B, T, N, AT, em, lengths, scale, alpha, beta, gamma, gamma_kind, V,
                                                    eo);
     KHMM_LAUNCH_CHECK("backward_generic_kernel");
+    if (ESTEP) {
+        double *tail = eo.counts + N + (int64_t)N * N + N + (int64_t)eo.M * N + N;      // [loglik, nseq, flags]
+        estep_loglik_kernel<R><<<(unsigned)((B * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(B, T, lengths, scale, tail);
+        KHMM_LAUNCH_CHECK("estep_loglik_kernel");
+    }
     return KHMM_OK;
 }
 
