@@ -370,8 +370,8 @@ TC_TF32, TC_BF16 = 0, 1
 
 def fwdbwd_loglik_tc(p: ModelParams, ob: Obs, both=True, precision=TC_TF32):
     """Tensor-core (tcgen05) forward(+backward) log-likelihood -> (loglik, loglik_bwd|None).
-    precision: TC_TF32 (default) or TC_BF16 (bf16 operands, fp32 accumulation; twice the MMA rate; falls back to
-    tf32 when the shape is not covered)."""
+    precision: TC_TF32 (default) or TC_BF16 (bf16 operands, fp32 accumulation; twice the MMA rate; tf32 is used
+    instead on a device without cooperative launch, the one case the bf16 kernel does not cover)."""
     t = require_cuda()
     dm = DeviceModel(p, t.float32)
     dev = device()
