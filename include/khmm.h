@@ -274,6 +274,15 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
                                size_t workspace_bytes, double *counts, float *alpha_out, float *scale_out,
                                khmm_stream_t stream);
 
+/* The same with per-sequence lengths (1 <= lengths[b] <= T, device int32[B]; NULL = every sequence has T steps): rows
+ * are padded to T, the padding symbols may be anything.  The statistics are those of the unpadded sequences
+ * (DiscreteHMM.do_pass on each sequence, summed); the recursion simply runs through the padding and three per-row
+ * switches remove it from the counts, so a ragged batch costs what the padded batch costs. */
+int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *AT,
+                                      const float *Bsm, const void *obs, int obs_dtype, const int32_t *lengths,
+                                      void *workspace, size_t workspace_bytes, double *counts, float *alpha_out,
+                                      float *scale_out, khmm_stream_t stream);
+
 /* Device durations (CUDA events on the launching stream) of the forward and the backward kernel of the
  * most recent khmm_estep_tc_discrete_f32 call of this process; waits for that call to finish.  For
  * measurement (bench.py reports the dominant kernel's roofline from it). */

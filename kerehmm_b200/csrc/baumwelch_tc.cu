@@ -68,11 +68,19 @@ struct BwObs {
     const void *obs;
     int dtype, M;
     int64_t T;
+    const int32_t *lengths;    // NULL: every sequence has T steps; else 1 <= lengths[b] <= T (ragged batch, rows padded to T)
     __device__ __forceinline__ int sym(int64_t b, int64_t t) const {
         int s = load_symbol(obs, dtype, b * T + t);
         return s < 0 ? 0 : (s >= M ? M - 1 : s);
     }
+    __device__ __forceinline__ int len(int64_t b) const { return lengths ? lengths[b] : (int)T; }
 };
+// Ragged batches cost nothing extra: the recursions simply run on through a sequence's padding (its symbols index valid
+// table rows, every value stays finite) and three per-row switches remove the padding from the statistics -- the forward
+// kernel stashes ZERO rows for t >= len (so gamma_t = W_t . beta_t and the W_t^T V2_{t+1} products of those steps vanish)
+// and leaves their c_t out of log P; the backward kernel sets beta_t = 1 for every t >= len - 1 (the reference's start value,
+// abstract_hmm.py:337) and V2_t = 0 for t >= len (the pair (len-1, len) must not count); the reduction warps take a row's
+// "last step" at t = len - 1 and skip its padding.
 
 // ------------------------------------------------------------------------------- forward
 // The first versions of this kernel did the emission gather and the stash store thread-per-row (each LDG/STG
@@ -241,6 +249,7 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t b = tile * 128 + row;
             const bool live = b < B;
+            const int len_b = live ? ob.len(b) : 0;   // steps of this sequence (0: a row past the batch)
             float r = 1.f;           // 1 / c_{t-1}
             float prod = 1.f;        // mantissa of prod_t c_t
             int esum = 0;            // its exponent
@@ -283,7 +292,7 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                     for (int q = 0; q < 32; q++) {
                         float v = __uint_as_float(acc[q]) * r * e[q];
                         rowsum += v;
-                        e[q] = live ? v : 0.f;   // rows past the batch: the backward MMA2 must see zeros
+                        e[q] = t < len_b ? v : 0.f;   // rows past the batch / steps past the sequence: zeros in the stash
                         w[q] = tf32_bits(v);
                     }
                     if (t + 1 < T) tmem_st_32x32(tmem + lane_base + 128 + c0, w);
@@ -305,9 +314,11 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                 mbar_arrive(&bars->w_ready[cur]);
                 if (warp == 0) FW_TRACE(14);
                 r = 1.0f / rowsum;
-                int ex;
-                prod = frexpf(prod * rowsum, &ex);
-                esum += ex;
+                if (t < len_b) {     // the padding's scale factors are not part of log P
+                    int ex;
+                    prod = frexpf(prod * rowsum, &ex);
+                    esum += ex;
+                }
             }
             if (live && half == 0) loglik[b] = (double)esum * 0.6931471805599453 + log((double)prod);
         }
@@ -487,11 +498,13 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             const int64_t b = tile * 128 + row;
             const bool live = b < B;
             const int64_t bc = live ? b : B - 1;
+            const int len_b = live ? ob.len(b) : 0;
             for (int64_t t = T - 1; t >= 0; t--) {
                 const bool last = (t == T - 1);
+                const bool bone = last || t >= len_b - 1;      // beta_t = 1: the sequence's own last step, or its padding
                 const float *sct = scale + (tile * T + t) * 128 + row;   // tile-major scale [tile][t][row]
                 const float rc1 = last ? 1.f : 1.0f / sct[128];
-                const float rcm1 = t > 0 ? 1.0f / sct[-128] : 0.f;
+                const float rcm1 = (t > 0 && t < len_b) ? 1.0f / sct[-128] : 0.f;   // V2_t = 0 in the padding
                 if (!last) {
                     mbar_wait(&bars->d1_full, nd & 1);
                     nd++;
@@ -521,7 +534,7 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                     if (!last) tmem_ld_wait();
 #pragma unroll
                     for (int q = 0; q < 32; q++) {
-                        beta[q] = last ? 1.f : __uint_as_float(acc[q]) * rc1;
+                        beta[q] = bone ? 1.f : __uint_as_float(acc[q]) * rc1;
                         g[q] *= beta[q];
                     }
                 };
@@ -662,10 +675,12 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             int64_t bq[4];
             bool lv[4];
+            int lenq[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 bq[k] = tile * 128 + quad * 32 + k * 8 + (lane >> 2);
                 lv[k] = bq[k] < B;
+                lenq[k] = lv[k] ? ob.len(bq[k]) : 0;
             }
             for (int64_t t = T - 1; t >= 0; t--) {
                 int sym[4];
@@ -698,7 +713,7 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
                         const int k = half * 2 + e;   // row = quad*32 + 8k + lane/4
-                        if (!lv[k]) continue;
+                        if (t >= lenq[k]) continue;       // a row past the batch, or a step of the row's padding
                         float *dst = tab + (size_t)sym[k] * BW_N + colq;
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
@@ -712,10 +727,10 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                                 if (RED_PACE_NS) asm volatile("nanosleep.u32 %0;" ::"n"(RED_PACE_NS));
                             }
                         }
-                        if (t == 0 || t == T - 1) {
+                        if (t == 0 || t == lenq[k] - 1) {
 #pragma unroll 1
                             for (int which = 0; which < 2; which++) {
-                                if ((which == 0 && t != 0) || (which == 1 && t != T - 1)) continue;
+                                if ((which == 0 && t != 0) || (which == 1 && t != lenq[k] - 1)) continue;
                                 float *d2 = tab + (size_t)(M + which) * BW_N + colq;
 #pragma unroll
                                 for (int c = 0; c < 4; c++)
@@ -844,6 +859,14 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
                                const float *Bsm, const void *obs, int obs_dtype, void *workspace,
                                size_t workspace_bytes, double *counts, float *alpha_out, float *scale_out,
                                khmm_stream_t stream) {
+    return khmm_estep_tc_discrete_ragged_f32(B, T, N, M, pi, A, AT, Bsm, obs, obs_dtype, nullptr, workspace, workspace_bytes,
+                                             counts, alpha_out, scale_out, stream);
+}
+
+int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *AT,
+                                      const float *Bsm, const void *obs, int obs_dtype, const int32_t *lengths,
+                                      void *workspace, size_t workspace_bytes, double *counts, float *alpha_out,
+                                      float *scale_out, khmm_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     KHMM_REQUIRE(B >= 0 && T >= 1 && M >= 1, "estep_tc: bad shape");
     if (N != BW_N) {
@@ -877,7 +900,7 @@ int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *
     }
     const int64_t ntiles = (B + 127) / 128;
     const int sms = sm_count();
-    BwObs ob{obs, obs_dtype, M, T};
+    BwObs ob{obs, obs_dtype, M, T, lengths};
     {
         size_t smem = BW_TILE + 2 * (size_t)FW_EBUF + 6 * 128 * sizeof(float) + sizeof(FwdBars) + 1024;
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

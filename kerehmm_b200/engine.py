@@ -490,9 +490,8 @@ TC_AUTO_MIN_ROWS = 1 << 22
 
 
 def estep_tc_supported(p: ModelParams, ob: Obs, real) -> bool:
-    """The fused tcgen05 E-step covers N = 128, float32, equal-length sequences."""
-    return (p.kind == "discrete" and p.N == 128 and ob.lengths is None and real == torch().float32
-            and ob.T < 2 ** 31)
+    """The fused tcgen05 E-step covers N = 128, float32 (equal-length or ragged batches)."""
+    return (p.kind == "discrete" and p.N == 128 and real == torch().float32 and ob.T < 2 ** 31)
 
 
 _ws_cache = {}
@@ -548,8 +547,9 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
     for b0 in range(0, ob.B, chunk):
         nb = min(chunk, ob.B - b0)
         obs_c = ob.tensor[b0:b0 + nb]
-        _lib.call("khmm_estep_tc_discrete_f32", nb, ob.T, N, M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.Bsm),
-                  ptr(obs_c), ob.code, wsp, nbytes, ptr(counts.buf), ptr(W), ptr(sc), stream_ptr())
+        len_c = ob.lengths[b0:b0 + nb] if ob.lengths is not None else None
+        _lib.call("khmm_estep_tc_discrete_ragged_f32", nb, ob.T, N, M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.Bsm),
+                  ptr(obs_c), ob.code, ptr(len_c), wsp, nbytes, ptr(counts.buf), ptr(W), ptr(sc), stream_ptr())
     if stash_out:
         W = W.permute(0, 2, 1, 3).reshape(-1, ob.T, N)[:nb0]     # -> [b][t][:]
         sc = sc.permute(0, 2, 1).reshape(-1, ob.T)[:nb0]

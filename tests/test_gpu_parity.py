@@ -494,6 +494,38 @@ def test_tensor_core_estep_many_tiles_vs_simt(K):
             np.testing.assert_allclose(c[key], ref[key], rtol=5e-4, err_msg=key)
 
 
+@pytest.mark.parametrize("B,T,M", [(300, 12, 16), (148 * 128 + 77, 9, 32)])
+def test_tensor_core_estep_ragged_batches(K, B, T, M):
+    """Ragged batches on the fused tensor-core E-step (rows padded to T with ARBITRARY symbols): the statistics are
+    those of the unpadded sequences -- against the float32 SIMT path (itself pinned to the oracle on ragged batches)
+    at the tf32 bounds of the equal-length test, and against the oracle's per-sequence statement on a sub-sample."""
+    N = 128
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=81)
+    rng = np.random.default_rng(82 + B)
+    obs = rng.integers(0, M, size=(B, T)).astype(np.uint8)
+    lengths = rng.integers(1, T + 1, size=B)
+    lengths[:4] = [1, T, 2, T - 1]
+    for b in range(B):
+        obs[b, lengths[b]:] = rng.integers(0, 256)             # padding: anything, including out-of-alphabet symbols
+    ref = h.estep_batch(obs, lengths=lengths, tensor_cores=False).host()
+    c = h.estep_batch(obs, lengths=lengths, tensor_cores=True).host()
+    assert c["nseq"] == B and c["flags"] == 0
+    assert np.isclose(c["loglik"], ref["loglik"], rtol=1e-5)
+    for key in ("pi", "gam", "emis_den", "emis_num", "xi_raw"):
+        np.testing.assert_allclose(c[key], ref[key], rtol=5e-4, atol=1e-6 * np.abs(ref[key]).max(), err_msg=key)
+    # the same statistics from the oracle, sequence by sequence, on the first 40 sequences
+    sub = slice(0, 40)
+    c40 = h.estep_batch(obs[sub], lengths=lengths[sub], tensor_cores=True).host()
+    tot = None
+    for b in range(40):
+        st = O.batch_stats_discrete(pi, A, Bm, obs[b:b + 1, :lengths[b]].astype(np.int64))
+        tot = st if tot is None else {k: tot[k] + st[k] for k in st}
+    assert np.isclose(c40["loglik"], tot["loglik"], rtol=2e-5)
+    np.testing.assert_allclose(c40["emis_den"], tot["emis_den"], rtol=2e-3)
+    np.testing.assert_allclose(c40["pi"], tot["pi"], rtol=2e-3, atol=1e-9)
+    np.testing.assert_allclose(c40["xi_raw"] * A, tot["xi"], rtol=1e-2, atol=1e-6 * tot["xi"].max())
+
+
 def test_tensor_core_do_pass_batch(K):
     """One Baum-Welch pass through the public API with tensor_cores=True: re-estimated parameters
     against the oracle's M-step at the stated tf32 bound; they stay valid distributions."""
