@@ -220,6 +220,19 @@ int khmm_fwdbwd_loglik_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const
                                        const float *AT, const float *Bsm, const void *obs, int obs_dtype,
                                        void *workspace, size_t workspace_bytes, double *loglik, double *loglik_bwd,
                                        int operand_precision, khmm_stream_t stream);
+/* The same for ragged batches: lengths[b] in [1, T] (device int32[B]; NULL = equal lengths), rows padded to T with
+ * anything.  Both recursions run through the padding with the emission factor set to 1 (a continuation that emits
+ * "anything" leaves the likelihood unchanged), so a ragged batch costs what the padded batch costs. */
+int khmm_fwdbwd_loglik_tc_gauss_ragged_f32(int64_t B, int64_t T, int N, const float *pi, const float *A, const float *AT,
+                                           const float *mean, const float *sd, const void *obs, int obs_dtype,
+                                           const int32_t *lengths, void *workspace, size_t workspace_bytes, double *loglik,
+                                           double *loglik_bwd, int operand_precision, khmm_stream_t stream);
+int khmm_fwdbwd_loglik_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A,
+                                              const float *AT, const float *Bsm, const void *obs, int obs_dtype,
+                                              const int32_t *lengths, void *workspace, size_t workspace_bytes,
+                                              double *loglik, double *loglik_bwd, int operand_precision,
+                                              khmm_stream_t stream);
+
 
 /* ---------------------------------------------------------------------------------------
  * Baum-Welch E-step -- the statistics DiscreteHMM.do_pass forms (discrete_hmm.py:117-159)

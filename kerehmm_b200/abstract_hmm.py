@@ -347,7 +347,7 @@ class AbstractHMM(object):
                              tensor_cores=True):
         """log P(O_b | model) for every sequence -> `(loglik, loglik_from_backward | None)`.
         float32, N <= 16: the fused forward+backward register kernel.  float32, N a multiple of 128
-        (<= 1024), equal lengths and `tensor_cores=True`: the tcgen05 (tf32) recursion, forward and
+        (<= 1024) and `tensor_cores=True`: the tcgen05 (tf32) recursion (ragged batches included), forward and
         backward together in one cooperative launch; `tensor_cores="bf16"` uses bf16 operands (twice the MMA
         rate, looser bound on short sequences -- DESIGN.md 3.4).  Otherwise the generic forward kernel (second
         value None)."""

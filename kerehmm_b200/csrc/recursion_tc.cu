@@ -53,6 +53,12 @@ struct TcEmis {
     const float *p0, *p1;   // gauss: mean, sd ; discrete: Bsm [M][N]
     const void *obs;
     int obs_dtype, M;
+    // ragged batches (whole-recursion kernel only): 1 <= lengths[b] <= T, rows padded to T; NULL = equal lengths.  Both
+    // recursions run on through the padding with the emission factor set to 1 there: the continuation of a sequence by
+    // steps that emit "anything" has the same likelihood, so nothing else changes (the forward pass, which can tell its
+    // padding's scale factors apart, leaves them out; the backward pass keeps them -- they multiply to 1 up to the
+    // operand rounding of A's row sums, ~1e-6 per step).
+    const int32_t *lengths;
 };
 
 // Round to nearest tf32 (10-bit mantissa).  The tensor core TRUNCATES fp32 operands to tf32, which
@@ -288,7 +294,7 @@ __device__ __forceinline__ void mma2_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
 }
 
-template <bool GAUSS, bool BF16, bool PAIR, int BN>
+template <bool GAUSS, bool BF16, bool PAIR, int BN, bool RAGGED>
 __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, const CUtensorMap &mapXf1, const CUtensorMap &mapXb0,
                                                    const CUtensorMap &mapXb1, const CUtensorMap &mapMf, const CUtensorMap &mapMb,
                                                    TcDir df, TcDir db, TcEmis em, int64_t B, int64_t T, int N, int mtiles,
@@ -448,6 +454,8 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
             const int64_t b = m0 + wq * 32 + lane;
             const bool live = b < B;
             const int64_t t = dir ? (T - 1 - jw.step) : jw.step;
+            const int64_t len_b = (RAGGED && live) ? (int64_t)em.lengths[b] : T;
+            const bool pad = RAGGED && t >= len_b;            // a step of this row's padding: emission factor 1
             float r = 0.f, x = 0.f;
             const float *brow = nullptr;
             if (live) {       // nothing here depends on the previous step
@@ -470,7 +478,9 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
                 const float c = (((p2[0].x + p2[0].y) + (p2[1].x + p2[1].y)) + ((p2[2].x + p2[2].y) + (p2[3].x + p2[3].y))) +
                                 (((p2[4].x + p2[4].y) + (p2[5].x + p2[5].y)) + ((p2[6].x + p2[6].y) + (p2[7].x + p2[7].y)));
                 r = 1.0f / c;
-                if (n0 == 0 && h == 0) __stcg(d.logacc + b, __ldcg(d.logacc + b) + log((double)c));
+                // (forward, ragged: c_{t-1} of a padding step is not part of log P)
+                if (n0 == 0 && h == 0 && !(RAGGED && dir == 0 && t - 1 >= len_b))
+                    __stcg(d.logacc + b, __ldcg(d.logacc + b) + log((double)c));
             }
             if (warp == 0) RC2_TRACE(9, nj);
             mbar_wait(&bars->tmem_full[a], (uint32_t)((nj / NACC) & 1));
@@ -504,10 +514,10 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
                         const float2 a0 = __ffma2_rn(__fmul2_rn(d0, d0), make_float2(kk.x, kk.y), make_float2(ll.x, ll.y));
                         const float2 a1 = __ffma2_rn(__fmul2_rn(d1, d1), make_float2(kk.z, kk.w), make_float2(ll.z, ll.w));
                         float e0, e1, e2, e3;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0.x));
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a0.y));
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(a1.x));
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(a1.y));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(pad ? 0.f : a0.x));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(pad ? 0.f : a0.y));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(pad ? 0.f : a1.x));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(pad ? 0.f : a1.y));
                         v[2 * q] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])), rr), make_float2(e0, e1));
                         v[2 * q + 1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), rr), make_float2(e2, e3));
                     }
@@ -515,7 +525,8 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
                     const float4 *b4 = reinterpret_cast<const float4 *>(brow + h * HALF + c0);
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
-                        const float4 e = __ldg(b4 + q);
+                        float4 e = __ldg(b4 + q);
+                        if (pad) e = make_float4(1.f, 1.f, 1.f, 1.f);
                         v[2 * q] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])), rr), make_float2(e.x, e.y));
                         v[2 * q + 1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), rr), make_float2(e.z, e.w));
                     }
@@ -596,13 +607,13 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
 #undef RC2_TRACE
 }
 
-template <bool GAUSS, bool BF16, int BN>
+template <bool GAUSS, bool BF16, int BN, bool RAGGED>
 __global__ void __launch_bounds__(320, 1)
 tc_recursion2_kernel(const __grid_constant__ CUtensorMap mapXf0, const __grid_constant__ CUtensorMap mapXf1,
                      const __grid_constant__ CUtensorMap mapXb0, const __grid_constant__ CUtensorMap mapXb1,
                      const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df, TcDir db,
                      TcEmis em, int64_t B, int64_t T, int N, int mtiles, int ndir, uint32_t *done, long long *trace) {
-    tc_recursion2_body<GAUSS, BF16, false, BN>(mapXf0, mapXf1, mapXb0, mapXb1, mapMf, mapMb, df, db, em, B, T, N, mtiles, ndir, done, trace);
+    tc_recursion2_body<GAUSS, BF16, false, BN, RAGGED>(mapXf0, mapXf1, mapXb0, mapXb1, mapMf, mapMb, df, db, em, B, T, N, mtiles, ndir, done, trace);
 }
 template <bool GAUSS, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
@@ -610,7 +621,7 @@ tc_recursion2_pair_kernel(const __grid_constant__ CUtensorMap mapXf0, const __gr
                           const __grid_constant__ CUtensorMap mapXb0, const __grid_constant__ CUtensorMap mapXb1,
                           const __grid_constant__ CUtensorMap mapMf, const __grid_constant__ CUtensorMap mapMb, TcDir df, TcDir db,
                           TcEmis em, int64_t B, int64_t T, int N, int mtiles, int ndir, uint32_t *done, long long *trace) {
-    tc_recursion2_body<GAUSS, BF16, true, 256>(mapXf0, mapXf1, mapXb0, mapXb1, mapMf, mapMb, df, db, em, B, T, N, mtiles, ndir, done, trace);
+    tc_recursion2_body<GAUSS, BF16, true, 256, false>(mapXf0, mapXf1, mapXb0, mapXb1, mapMf, mapMb, df, db, em, B, T, N, mtiles, ndir, done, trace);
 }
 
 // step 0: W_0 = start . b(o_first): start = pi (forward, t = 0) or ones (backward, t = T-1)
@@ -622,6 +633,7 @@ __global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__res
     const int64_t b = blockIdx.x;
     const int NT = N / TC_BN;
     const int64_t t = dir ? T - 1 : 0;
+    const bool pad = em.lengths && t >= em.lengths[b];      // (backward start of a padded row: emission factor 1)
     float x = 0.f;
     const float *brow = nullptr;
     if (GAUSS) {
@@ -641,6 +653,7 @@ __global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__res
         } else {
             e = brow[j];
         }
+        if (pad) e = 1.f;
         float v = (dir ? 1.f : pi[j]) * e;
         if (BF16) reinterpret_cast<__nv_bfloat16 *>(d.W)[(b * 2 + 0) * N + j] = __float2bfloat16_rn(v);
         else d.W[(b * 2 + 0) * N + j] = round_tf32(v);
@@ -663,7 +676,8 @@ __global__ void tc_init_kernel(TcDir df, TcDir db, TcEmis em, const float *__res
 // closing: forward log P = logacc + log c_{T-1}; backward log P = logacc + log(pi . w_0)
 template <bool BF16 = false>
 __global__ void tc_final_kernel(TcDir df, TcDir db, const float *__restrict__ pi, int64_t B, int64_t T, int N,
-                                double *__restrict__ loglik, double *__restrict__ loglik_bwd) {
+                                const int32_t *__restrict__ lengths, double *__restrict__ loglik,
+                                double *__restrict__ loglik_bwd) {
     const int dir = blockIdx.y;
     const TcDir d = dir ? db : df;
     const int64_t b = blockIdx.x;
@@ -682,7 +696,9 @@ __global__ void tc_final_kernel(TcDir df, TcDir db, const float *__restrict__ pi
     if (threadIdx.x == 0) {
         float tot = 0.f;
         for (int k = 0; k < (int)(blockDim.x >> 5); k++) tot += red[k];
-        double ll = d.logacc[b] + log((double)tot);
+        // (forward, ragged: the last step of a padded row is padding -- its c_{T-1} is not part of log P)
+        const bool skip_last = dir == 0 && lengths && lengths[b] < T;
+        double ll = d.logacc[b] + (skip_last ? 0.0 : log((double)tot));
         if (dir) { if (loglik_bwd) loglik_bwd[b] = ll; } else loglik[b] = ll;
     }
 }
@@ -737,6 +753,10 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
     int rc_mode = KHMM_RC2 ? ((KHMM_RC2_PAIR && !bf16) ? 3 : 2) : 1;
     if (const char *e = getenv("KHMM_RC_MODE")) rc_mode = atoi(e);
     const bool use_rc2 = coop && rc_mode >= 2;         // any N % 128 == 0, any batch: one launch for all T-1 steps
+    if (em.lengths && !use_rc2) {
+        set_error("fwdbwd_loglik_tc: ragged batches need the whole-recursion kernel (cooperative launch)");
+        return KHMM_ERR_UNSUPPORTED;
+    }
     if (bf16) {
         if (!use_rc2) {
             set_error("fwdbwd_loglik_tc: bf16 operands need the whole-recursion kernel (cooperative launch)");
@@ -794,7 +814,8 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
     }
     if (use_rc2) {
         const int mtiles = (int)(Bp / TC_BM);
-        const bool rpair = rc_mode == 3 && BN == 256 && mtiles % 2 == 0;
+        const bool ragged = em.lengths != nullptr;
+        const bool rpair = rc_mode == 3 && BN == 256 && mtiles % 2 == 0 && !ragged;      // (the pair kernel has no ragged variant)
         CUtensorMap mapH[2];
         if (rpair && (bf16 ? (make_tmap_bf16_rowmajor(&mapH[0], ATr, N, N, 128) || make_tmap_bf16_rowmajor(&mapH[1], Ar, N, N, 128))
                            : (make_tmap_f32_rowmajor(&mapH[0], ATr, N, N, 128) || make_tmap_f32_rowmajor(&mapH[1], Ar, N, N, 128)))) {
@@ -806,8 +827,10 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
                                                : (size_t)TcRBars<false, 128>::STAGES * (TC_TILE_BYTES + 128 * 128));
         const size_t smem = ring + 2 * (size_t)TC_TILE_BYTES + sizeof(TcRBars<true, 256>) + 16 + 3 * (size_t)N * sizeof(float) + 1024;
         void *kern = rpair ? (bf16 ? (void *)tc_recursion2_pair_kernel<GAUSS, true> : (void *)tc_recursion2_pair_kernel<GAUSS, false>)
-                   : BN == 256 ? (bf16 ? (void *)tc_recursion2_kernel<GAUSS, true, 256> : (void *)tc_recursion2_kernel<GAUSS, false, 256>)
-                               : (bf16 ? (void *)tc_recursion2_kernel<GAUSS, true, 128> : (void *)tc_recursion2_kernel<GAUSS, false, 128>);
+                   : ragged ? (BN == 256 ? (bf16 ? (void *)tc_recursion2_kernel<GAUSS, true, 256, true> : (void *)tc_recursion2_kernel<GAUSS, false, 256, true>)
+                                         : (bf16 ? (void *)tc_recursion2_kernel<GAUSS, true, 128, true> : (void *)tc_recursion2_kernel<GAUSS, false, 128, true>))
+                   : BN == 256 ? (bf16 ? (void *)tc_recursion2_kernel<GAUSS, true, 256, false> : (void *)tc_recursion2_kernel<GAUSS, false, 256, false>)
+                               : (bf16 ? (void *)tc_recursion2_kernel<GAUSS, true, 128, false> : (void *)tc_recursion2_kernel<GAUSS, false, 128, false>);
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int nlanes = (rpair ? mtiles / 2 : mtiles) * (N / BN) * ndir;
         int walkers = rpair ? sm_count() / 2 : sm_count();
@@ -851,8 +874,8 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
         }
         KHMM_LAUNCH_CHECK("tc_step_kernel");
     }
-    if (bf16) tc_final_kernel<true><<<dim3((unsigned)B, ndir), 256, 0, st>>>(d[0], d[1], pi, B, T, N, loglik, loglik_bwd);
-    else tc_final_kernel<false><<<dim3((unsigned)B, ndir), 256, 0, st>>>(d[0], d[1], pi, B, T, N, loglik, loglik_bwd);
+    if (bf16) tc_final_kernel<true><<<dim3((unsigned)B, ndir), 256, 0, st>>>(d[0], d[1], pi, B, T, N, em.lengths, loglik, loglik_bwd);
+    else tc_final_kernel<false><<<dim3((unsigned)B, ndir), 256, 0, st>>>(d[0], d[1], pi, B, T, N, em.lengths, loglik, loglik_bwd);
     KHMM_LAUNCH_CHECK("tc_final_kernel");
     return KHMM_OK;
 }
@@ -873,27 +896,44 @@ size_t khmm_fwdbwd_loglik_tc_workspace_bytes(int64_t B, int N) {
     return tc_workspace_floats(B, N) * sizeof(float);
 }
 
+int khmm_fwdbwd_loglik_tc_gauss_ragged_f32(int64_t B, int64_t T, int N, const float *pi, const float *A, const float *AT,
+                                           const float *mean, const float *sd, const void *obs, int obs_dtype,
+                                           const int32_t *lengths, void *workspace, size_t workspace_bytes, double *loglik,
+                                           double *loglik_bwd, int operand_precision, khmm_stream_t stream) {
+    KHMM_REQUIRE(B == 0 || (mean && sd && obs), "fwdbwd_loglik_tc_gauss: NULL pointer argument");
+    KHMM_REQUIRE(obs_dtype == KHMM_F32 || obs_dtype == KHMM_F64, "gauss: obs dtype code %d is not f32/f64", obs_dtype);
+    TcEmis em{1, mean, sd, obs, obs_dtype, 0, lengths};
+    return run_tc<true>(B, T, N, pi, A, AT, em, workspace, workspace_bytes, loglik, loglik_bwd, operand_precision,
+                        (cudaStream_t)stream);
+}
+
 int khmm_fwdbwd_loglik_tc_gauss_f32(int64_t B, int64_t T, int N, const float *pi, const float *A, const float *AT,
                                     const float *mean, const float *sd, const void *obs, int obs_dtype, void *workspace,
                                     size_t workspace_bytes, double *loglik, double *loglik_bwd, int operand_precision,
                                     khmm_stream_t stream) {
-    KHMM_REQUIRE(B == 0 || (mean && sd && obs), "fwdbwd_loglik_tc_gauss: NULL pointer argument");
-    KHMM_REQUIRE(obs_dtype == KHMM_F32 || obs_dtype == KHMM_F64, "gauss: obs dtype code %d is not f32/f64", obs_dtype);
-    TcEmis em{1, mean, sd, obs, obs_dtype, 0};
-    return run_tc<true>(B, T, N, pi, A, AT, em, workspace, workspace_bytes, loglik, loglik_bwd, operand_precision,
-                        (cudaStream_t)stream);
+    return khmm_fwdbwd_loglik_tc_gauss_ragged_f32(B, T, N, pi, A, AT, mean, sd, obs, obs_dtype, nullptr, workspace,
+                                                  workspace_bytes, loglik, loglik_bwd, operand_precision, stream);
+}
+
+int khmm_fwdbwd_loglik_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A,
+                                              const float *AT, const float *Bsm, const void *obs, int obs_dtype,
+                                              const int32_t *lengths, void *workspace, size_t workspace_bytes,
+                                              double *loglik, double *loglik_bwd, int operand_precision,
+                                              khmm_stream_t stream) {
+    KHMM_REQUIRE(B == 0 || (Bsm && obs && M >= 1), "fwdbwd_loglik_tc_discrete: NULL pointer argument");
+    KHMM_REQUIRE(obs_dtype >= KHMM_U8 && obs_dtype <= KHMM_I64, "discrete: obs dtype code %d is not an integer type",
+                 obs_dtype);
+    TcEmis em{0, Bsm, nullptr, obs, obs_dtype, M, lengths};
+    return run_tc<false>(B, T, N, pi, A, AT, em, workspace, workspace_bytes, loglik, loglik_bwd, operand_precision,
+                         (cudaStream_t)stream);
 }
 
 int khmm_fwdbwd_loglik_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A,
                                        const float *AT, const float *Bsm, const void *obs, int obs_dtype,
                                        void *workspace, size_t workspace_bytes, double *loglik, double *loglik_bwd,
                                        int operand_precision, khmm_stream_t stream) {
-    KHMM_REQUIRE(B == 0 || (Bsm && obs && M >= 1), "fwdbwd_loglik_tc_discrete: NULL pointer argument");
-    KHMM_REQUIRE(obs_dtype >= KHMM_U8 && obs_dtype <= KHMM_I64, "discrete: obs dtype code %d is not an integer type",
-                 obs_dtype);
-    TcEmis em{0, Bsm, nullptr, obs, obs_dtype, M};
-    return run_tc<false>(B, T, N, pi, A, AT, em, workspace, workspace_bytes, loglik, loglik_bwd, operand_precision,
-                         (cudaStream_t)stream);
+    return khmm_fwdbwd_loglik_tc_discrete_ragged_f32(B, T, N, M, pi, A, AT, Bsm, obs, obs_dtype, nullptr, workspace,
+                                                     workspace_bytes, loglik, loglik_bwd, operand_precision, stream);
 }
 
 }  // extern "C"

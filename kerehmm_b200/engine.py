@@ -360,9 +360,8 @@ def fwdbwd_loglik_small_host(p: ModelParams, obs, both=True, nchunks=4, min_byte
 
 
 def tc_supported(p: ModelParams, ob: Obs) -> bool:
-    """The tcgen05 recursion covers N = 128, 256, ..., 1024 with equal-length sequences."""
-    return (p.kind in ("discrete", "gauss") and p.N >= 128 and p.N % 128 == 0 and p.N <= 1024
-            and ob.lengths is None)
+    """The tcgen05 recursion covers N = 128, 256, ..., 1024 (equal-length or ragged batches)."""
+    return p.kind in ("discrete", "gauss") and p.N >= 128 and p.N % 128 == 0 and p.N <= 1024
 
 
 TC_TF32, TC_BF16 = 0, 1
@@ -381,11 +380,13 @@ def fwdbwd_loglik_tc(p: ModelParams, ob: Obs, both=True, precision=TC_TF32):
     ws, wsp = workspace(nbytes, 256)
     def run(prec):
         if p.kind == "gauss":
-            _lib.call("khmm_fwdbwd_loglik_tc_gauss_f32", ob.B, ob.T, p.N, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.mean),
-                      ptr(dm.sd), ptr(ob.tensor), ob.code, wsp, nbytes, ptr(ll), ptr(llb), prec, stream_ptr())
+            _lib.call("khmm_fwdbwd_loglik_tc_gauss_ragged_f32", ob.B, ob.T, p.N, ptr(dm.pi), ptr(dm.A), ptr(dm.AT),
+                      ptr(dm.mean), ptr(dm.sd), ptr(ob.tensor), ob.code, ptr(ob.lengths), wsp, nbytes, ptr(ll), ptr(llb),
+                      prec, stream_ptr())
         else:
-            _lib.call("khmm_fwdbwd_loglik_tc_discrete_f32", ob.B, ob.T, p.N, p.M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT),
-                      ptr(dm.Bsm), ptr(ob.tensor), ob.code, wsp, nbytes, ptr(ll), ptr(llb), prec, stream_ptr())
+            _lib.call("khmm_fwdbwd_loglik_tc_discrete_ragged_f32", ob.B, ob.T, p.N, p.M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT),
+                      ptr(dm.Bsm), ptr(ob.tensor), ob.code, ptr(ob.lengths), wsp, nbytes, ptr(ll), ptr(llb), prec,
+                      stream_ptr())
     try:
         run(precision)
     except _lib.KhmmError as e:

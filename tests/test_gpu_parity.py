@@ -389,10 +389,18 @@ def test_tensor_core_loglik_discrete(K):
     ref = O.loglik(O.forward(pi, A, O.emissions_discrete(Bm, obs))[1])
     np.testing.assert_allclose(ll, ref, rtol=2e-5)
     np.testing.assert_allclose(llb, ref, rtol=2e-5)
-    # ragged batches are not covered by the tensor-core kernel: they take the generic path
-    lengths = np.full(B, T); lengths[3] = T - 5
-    ll2, none = h.log_likelihood_batch(obs, lengths=lengths)
-    assert none is None and np.isclose(ll2[0], ref[0], rtol=F32_RTOL)
+    # ragged batches stay on the tensor-core kernel (discrete table gather; the padding may hold any symbol)
+    lengths = np.full(B, T); lengths[3] = T - 5; lengths[7] = 1
+    obs2 = obs.copy(); obs2[3, T - 5:] = 255; obs2[7, 1:] = 200
+    ll2, llb2 = h.log_likelihood_batch(obs2, lengths=lengths)
+    ref2 = ref.copy()
+    for b in (3, 7):
+        ref2[b] = O.loglik(O.forward(pi, A, O.emissions_discrete(Bm, obs[b, :lengths[b]]))[1])
+    np.testing.assert_allclose(ll2, ref2, rtol=2e-5, atol=3e-3)
+    np.testing.assert_allclose(llb2, ref2, rtol=2e-5, atol=3e-3)
+    ll3, none = h.log_likelihood_batch(obs2, lengths=lengths, tensor_cores=False)      # float32 SIMT forward kernel
+    assert none is None
+    np.testing.assert_allclose(ll3, ref2, rtol=F32_RTOL)
 
 
 def test_gaussian_forward_backward_batch_generic(K):
@@ -709,6 +717,31 @@ def test_tensor_core_loglik_degenerate_shapes(K, N, B, T):
         assert np.isfinite(ll.cpu().numpy()).all() and np.isfinite(llb.cpu().numpy()).all()
         np.testing.assert_allclose(ll.cpu().numpy(), ref, rtol=0, atol=atol)
         np.testing.assert_allclose(llb.cpu().numpy(), ref, rtol=0, atol=atol)
+
+
+@pytest.mark.parametrize("N,B,T", [(256, 200, 20), (1024, 300, 12), (128, 70, 33)])
+@pytest.mark.parametrize("mode,tol", [(True, 5e-5), ("bf16", 3e-4)])
+def test_tensor_core_loglik_ragged_batches(K, N, B, T, mode, tol):
+    """Ragged batches on the whole-recursion tensor-core kernel (rows padded to T with garbage, NaN included): the
+    forward and the backward log-likelihood of every sequence against the float64 oracle run on the unpadded sequence."""
+    import torch
+    np.random.seed(500 + N)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    h = gaussian_model(K, pi, A, mean, sd)
+    rng = np.random.default_rng(501 + B)
+    x = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T))).astype(np.float32)
+    lengths = rng.integers(1, T + 1, size=B)
+    lengths[:4] = [1, T, 2, T - 1]
+    for b in range(B):
+        x[b, lengths[b]:] = np.nan if b % 3 == 0 else 1e6 * rng.standard_normal()
+    ll, llb = h.log_likelihood_batch(torch.from_numpy(x).cuda(), lengths=lengths, tensor_cores=mode)
+    ll, llb = ll.cpu().numpy(), llb.cpu().numpy()
+    ref = np.array([O.loglik(O.forward(pi, A, O.emissions_gaussian_1d(mean, sd, x[b, :lengths[b]].astype(np.float64)))[1])
+                    for b in range(B)])
+    # short sequences: the absolute error of one step's rounded emission values dominates (see the degenerate-shape test)
+    atol = (3e-3 if mode is True else 2e-2)
+    np.testing.assert_allclose(ll, ref, rtol=tol, atol=atol)
+    np.testing.assert_allclose(llb, ref, rtol=tol, atol=atol)
 
 
 def test_fwdbwd_config2_shape_properties(K):
