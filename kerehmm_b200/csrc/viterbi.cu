@@ -346,7 +346,7 @@ struct VitScreen {
         return sizeof(double) * (NN * NN + WARPS * NN) + sizeof(float) * WARPS * NN + (JR == JT ? 0 : sizeof(float) * NN * NN);
     }
 };
-template <int NN, typename PSI>
+template <int NN, typename PSI, bool GAUSS>
 __global__ void __launch_bounds__(32 * VitScreen<NN>::WARPS, 1)
 viterbi_screen_kernel(int64_t B, int64_t T, int M, const double *__restrict__ logpi, const double *__restrict__ logA,
                       const double *__restrict__ logBsm, const void *__restrict__ obs, int obs_dtype,
@@ -402,34 +402,46 @@ viterbi_screen_kernel(int64_t B, int64_t T, int M, const double *__restrict__ lo
     for (int64_t b = (int64_t)blockIdx.x * WARPS + w; b < B; b += (int64_t)gridDim.x * WARPS) {
         const int len = lengths ? lengths[b] : (int)T;
         if (len <= 0) continue;
+        // observation token of step tt (clamped into the sequence): the symbol, or (GAUSS) the real observation; and the
+        // log-emissions of this lane's targets for a token.  GAUSS (extension, khmm_viterbi_gauss_f64): logBsm holds
+        // [3][NN] = mean, sd, log-constant and log b_j(x) = (-0.5 z) z + logc_j, z = (x - mean_j) / sd_j, one rounding per
+        // operation in that order (no FMA contraction), as the generic kernel and the oracle evaluate it
+        auto token_at = [&](int tt) -> double {
+            const int64_t idx = b * T + (tt < len ? tt : len - 1);
+            if (GAUSS) return load_real<double>(obs, obs_dtype, idx);
+            int sy = load_symbol(obs, obs_dtype, idx);
+            return (double)(sy < 0 ? 0 : (sy >= M ? M - 1 : sy));
+        };
+        auto log_emissions = [&](double tok, double (&eo)[JT]) {
+#pragma unroll
+            for (int q = 0; q < JT; q++) {
+                const int j = l + 32 * q;
+                if (GAUSS) {
+                    const double z = __ddiv_rn(__dsub_rn(tok, __ldg(logBsm + j)), __ldg(logBsm + NN + j));
+                    eo[q] = __dadd_rn(__dmul_rn(__dmul_rn(-0.5, z), z), __ldg(logBsm + 2 * NN + j));
+                } else {
+                    eo[q] = __ldg(logBsm + (int64_t)(int)tok * NN + j);
+                }
+            }
+        };
         double d[JT];
         {
-            int sym = load_symbol(obs, obs_dtype, b * T);
-            sym = sym < 0 ? 0 : (sym >= M ? M - 1 : sym);
+            double e0[JT];
+            log_emissions(token_at(0), e0);
 #pragma unroll
-            for (int q = 0; q < JT; q++) d[q] = lp[q] + __ldg(logBsm + (int64_t)sym * NN + l + 32 * q);
+            for (int q = 0; q < JT; q++) d[q] = lp[q] + e0[q];
         }
         int exact_until = 0, streak = 0;       // steps < exact_until skip the screen
-        // the symbol of step t+2 and the emission row of step t+1 are requested during step t (both are L2 latencies)
-        auto symbol_at = [&](int tt) {
-            int sy = load_symbol(obs, obs_dtype, b * T + (tt < len ? tt : len - 1));
-            return sy < 0 ? 0 : (sy >= M ? M - 1 : sy);
-        };
+        // the token of step t+2 and the emission row of step t+1 are requested during step t (both are L2 latencies)
         double e_next[JT];
-        {
-            const int s1 = symbol_at(1);
-#pragma unroll
-            for (int q = 0; q < JT; q++) e_next[q] = __ldg(logBsm + (int64_t)s1 * NN + l + 32 * q);
-        }
-        int sym_next = symbol_at(2);
+        log_emissions(token_at(1), e_next);
+        double tok_next = token_at(2);
         for (int t = 1; t < len; t++) {
             double e[JT];
 #pragma unroll
-            for (int q = 0; q < JT; q++) {
-                e[q] = e_next[q];
-                e_next[q] = __ldg(logBsm + (int64_t)sym_next * NN + l + 32 * q);
-            }
-            sym_next = symbol_at(t + 2);
+            for (int q = 0; q < JT; q++) e[q] = e_next[q];
+            log_emissions(tok_next, e_next);
+            tok_next = token_at(t + 2);
             // reference level R = fl32(max of the previous row): one integer warp reduction on the order-preserving
             // integer image of the float32 values (the screen only needs delta - R to be small near the top)
             float lf = (float)d[0];
@@ -561,11 +573,11 @@ viterbi_screen_kernel(int64_t B, int64_t T, int M, const double *__restrict__ lo
     }
 }
 
-template <int NN, typename PSI>
+template <int NN, typename PSI, bool GAUSS>
 static int launch_viterbi_screen(int64_t B, int64_t T, int M, const double *logpi, const double *logA, const double *logBsm,
                                  const void *obs, int obs_dtype, const int32_t *lengths, PSI *psi, int32_t *last,
                                  double *logp, cudaStream_t st) {
-    auto kern = viterbi_screen_kernel<NN, PSI>;
+    auto kern = viterbi_screen_kernel<NN, PSI, GAUSS>;
     constexpr int kVitScreenWarps = VitScreen<NN>::WARPS;
     const size_t smem = VitScreen<NN>::smem_bytes();
     if (smem > 48 * 1024) KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -614,11 +626,17 @@ static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, 
     int rc_tile = -1;
     const char *vs_env = getenv("KHMM_VIT_SCREEN");      // development / cross-check switch, read on every call
     const bool use_screen = !(vs_env && atoi(vs_env) == 0);
-    if (M > 0 && sizeof(PSI) == 1 && B >= 64 && use_screen && (N == 32 || N == 64 || N == 128)) {
-        // float32-screened warp-per-sequence kernel
-        if (N == 32) rc_tile = launch_viterbi_screen<32, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
-        else if (N == 64) rc_tile = launch_viterbi_screen<64, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
-        else rc_tile = launch_viterbi_screen<128, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+    if (sizeof(PSI) == 1 && B >= 64 && use_screen && (N == 32 || N == 64 || N == 128)) {
+        // float32-screened warp-per-sequence kernel (M == 0: Gaussian emissions, logBsm = [3][N] mean / sd / log-constant)
+        if (M > 0) {
+            if (N == 32) rc_tile = launch_viterbi_screen<32, PSI, false>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+            else if (N == 64) rc_tile = launch_viterbi_screen<64, PSI, false>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+            else rc_tile = launch_viterbi_screen<128, PSI, false>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+        } else {
+            if (N == 32) rc_tile = launch_viterbi_screen<32, PSI, true>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+            else if (N == 64) rc_tile = launch_viterbi_screen<64, PSI, true>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+            else rc_tile = launch_viterbi_screen<128, PSI, true>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
+        }
     } else if (M > 0 && sizeof(PSI) == 1 && B >= 64) {   // register-tile kernels (small batches stay on the generic kernel)
         if (N == 32) rc_tile = launch_viterbi_tile<32, 4, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);
         else if (N == 64) rc_tile = launch_viterbi_tile<64, 4, PSI>(B, T, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp, st);

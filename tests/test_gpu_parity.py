@@ -264,7 +264,8 @@ def test_viterbi_screened_kernel_adversarial(K, N, kind):
 
 
 @pytest.mark.parametrize("N,B,T,dtype", [(3, 5, 40, np.float64), (8, 70, 100, np.float32), (64, 66, 30, np.float32),
-                                          (300, 4, 25, np.float64)])
+                                          (300, 4, 25, np.float64), (32, 64, 50, np.float64), (128, 70, 40, np.float32),
+                                          (64, 200, 300, np.float64)])
 def test_viterbi_batch_gaussian_extension(K, N, B, T, dtype):
     """EXTENSION: batched Viterbi for 1-D Gaussian emissions, bit-exact against the oracle's
     statement of the same definition (ragged lengths included); the single-sequence reference method keeps failing
