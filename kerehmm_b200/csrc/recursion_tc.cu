@@ -54,10 +54,9 @@ struct TcEmis {
     const void *obs;
     int obs_dtype, M;
     // ragged batches (whole-recursion kernel only): 1 <= lengths[b] <= T, rows padded to T; NULL = equal lengths.  Both
-    // recursions run on through the padding with the emission factor set to 1 there: the continuation of a sequence by
-    // steps that emit "anything" has the same likelihood, so nothing else changes (the forward pass, which can tell its
-    // padding's scale factors apart, leaves them out; the backward pass keeps them -- they multiply to 1 up to the
-    // operand rounding of A's row sums, ~1e-6 per step).
+    // recursions run on through the padding with the emission factor set to 1 there (every value stays finite whatever
+    // the padding holds); the forward pass leaves the padding's scale factors out of log P; the backward pass holds
+    // w = 1 through the padding and restarts exactly at the row's last step, w_{len-1} = b(o_{len-1}).
     const int32_t *lengths;
 };
 
@@ -456,6 +455,10 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
             const int64_t t = dir ? (T - 1 - jw.step) : jw.step;
             const int64_t len_b = (RAGGED && live) ? (int64_t)em.lengths[b] : T;
             const bool pad = RAGGED && t >= len_b;            // a step of this row's padding: emission factor 1
+            // backward pass of a padded row: w_t = 1 in the padding and w_{len-1} = b(o_{len-1}) EXACTLY, as if the
+            // recursion started there (running the normalised constant vector through the padding instead would bias
+            // log P: all its entries round to tf32 / bf16 the same way, +-2e-4 per step, measured)
+            const bool restart = RAGGED && dir == 1 && t >= len_b - 1;
             float r = 0.f, x = 0.f;
             const float *brow = nullptr;
             if (live) {       // nothing here depends on the previous step
@@ -478,8 +481,9 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
                 const float c = (((p2[0].x + p2[0].y) + (p2[1].x + p2[1].y)) + ((p2[2].x + p2[2].y) + (p2[3].x + p2[3].y))) +
                                 (((p2[4].x + p2[4].y) + (p2[5].x + p2[5].y)) + ((p2[6].x + p2[6].y) + (p2[7].x + p2[7].y)));
                 r = 1.0f / c;
-                // (forward, ragged: c_{t-1} of a padding step is not part of log P)
-                if (n0 == 0 && h == 0 && !(RAGGED && dir == 0 && t - 1 >= len_b))
+                // (ragged: the scale factors of padding steps are not part of log P -- forward: c_{t-1} with t-1 >= len;
+                // backward: the sum of w_{t+1} with t+1 >= len)
+                if (n0 == 0 && h == 0 && !(RAGGED && dir == 0 && t - 1 >= len_b) && !restart)
                     __stcg(d.logacc + b, __ldcg(d.logacc + b) + log((double)c));
             }
             if (warp == 0) RC2_TRACE(9, nj);
@@ -518,8 +522,11 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
                         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(pad ? 0.f : a0.y));
                         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(pad ? 0.f : a1.x));
                         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(pad ? 0.f : a1.y));
-                        v[2 * q] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])), rr), make_float2(e0, e1));
-                        v[2 * q + 1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), rr), make_float2(e2, e3));
+                        float2 ar0 = __fmul2_rn(make_float2(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])), rr);
+                        float2 ar1 = __fmul2_rn(make_float2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), rr);
+                        if (restart) { ar0 = make_float2(1.f, 1.f); ar1 = ar0; }
+                        v[2 * q] = __fmul2_rn(ar0, make_float2(e0, e1));
+                        v[2 * q + 1] = __fmul2_rn(ar1, make_float2(e2, e3));
                     }
                 } else {
                     const float4 *b4 = reinterpret_cast<const float4 *>(brow + h * HALF + c0);
@@ -527,8 +534,11 @@ __device__ __forceinline__ void tc_recursion2_body(const CUtensorMap &mapXf0, co
                     for (int q = 0; q < 8; q++) {
                         float4 e = __ldg(b4 + q);
                         if (pad) e = make_float4(1.f, 1.f, 1.f, 1.f);
-                        v[2 * q] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])), rr), make_float2(e.x, e.y));
-                        v[2 * q + 1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), rr), make_float2(e.z, e.w));
+                        float2 ar0 = __fmul2_rn(make_float2(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])), rr);
+                        float2 ar1 = __fmul2_rn(make_float2(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), rr);
+                        if (restart) { ar0 = make_float2(1.f, 1.f); ar1 = ar0; }
+                        v[2 * q] = __fmul2_rn(ar0, make_float2(e.x, e.y));
+                        v[2 * q + 1] = __fmul2_rn(ar1, make_float2(e.z, e.w));
                     }
                 }
                 if (c0 == 64) {       // (BN = 256) the first 64 columns of this half are one row-sum slot

@@ -359,9 +359,32 @@ def fwdbwd_loglik_small_host(p: ModelParams, obs, both=True, nchunks=4, min_byte
     return host[0], (host[1] if both else None)
 
 
+TC_MIN_STATES = 65      # below this the padding to 128 states costs more than the float32 SIMT kernels
+
+
 def tc_supported(p: ModelParams, ob: Obs) -> bool:
-    """The tcgen05 recursion covers N = 128, 256, ..., 1024 (equal-length or ragged batches)."""
-    return p.kind in ("discrete", "gauss") and p.N >= 128 and p.N % 128 == 0 and p.N <= 1024
+    """The tcgen05 recursion covers 65 <= N <= 1024 (state spaces that are not a multiple of 128 are padded with
+    unreachable states), equal-length or ragged batches."""
+    return p.kind in ("discrete", "gauss") and TC_MIN_STATES <= p.N <= 1024
+
+
+def pad_states(p: ModelParams, multiple: int = 128) -> ModelParams:
+    """The same model with its state space padded to a multiple of `multiple` by UNREACHABLE states: start
+    probability 0, no transitions in or out, and emission 0 (a zero table row; a Gaussian with sd = inf, whose density
+    the kernels evaluate as exp2(-inf) = 0).  Their alpha and beta are exactly 0 at every step, every likelihood and
+    every scale factor is unchanged."""
+    N = p.N
+    Np = -(-N // multiple) * multiple
+    if Np == N:
+        return p
+    pi = np.zeros(Np); pi[:N] = p.pi
+    A = np.zeros((Np, Np)); A[:N, :N] = p.A
+    if p.kind == "discrete":
+        B = np.zeros((Np, p.M)); B[:N] = p.B
+        return ModelParams(kind="discrete", pi=pi, A=A, B=B)
+    mean = np.zeros(Np); mean[:N] = p.mean
+    sd = np.full(Np, np.inf); sd[:N] = p.sd
+    return ModelParams(kind="gauss", pi=pi, A=A, mean=mean, sd=sd)
 
 
 TC_TF32, TC_BF16 = 0, 1
@@ -372,6 +395,7 @@ def fwdbwd_loglik_tc(p: ModelParams, ob: Obs, both=True, precision=TC_TF32):
     precision: TC_TF32 (default) or TC_BF16 (bf16 operands, fp32 accumulation; twice the MMA rate; tf32 is used
     instead on a device without cooperative launch, the one case the bf16 kernel does not cover)."""
     t = require_cuda()
+    p = pad_states(p)               # N not a multiple of 128: unreachable padding states
     dm = DeviceModel(p, t.float32)
     dev = device()
     ll = t.empty((ob.B,), dtype=t.float64, device=dev)

@@ -745,6 +745,35 @@ def test_tensor_core_loglik_ragged_batches(K, N, B, T, mode, tol):
     np.testing.assert_allclose(llb, ref, rtol=tol, atol=atol)
 
 
+@pytest.mark.parametrize("N,kind", [(100, "gauss"), (200, "gauss"), (1000, "gauss"), (65, "discrete"), (300, "discrete")])
+def test_tensor_core_loglik_any_state_count(K, N, kind):
+    """State spaces that are not a multiple of 128 run on the tensor-core kernel padded with unreachable states
+    (start probability 0, no transitions, emission 0): likelihoods unchanged, ragged batches included."""
+    import torch
+    B, T = 150, 24
+    rng = np.random.default_rng(600 + N)
+    lengths = rng.integers(1, T + 1, size=B)
+    if kind == "gauss":
+        np.random.seed(601 + N)
+        pi, A, mean, sd = O.random_gaussian_model(N)
+        h = gaussian_model(K, pi, A, mean, sd)
+        x = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T))).astype(np.float32)
+        E = O.emissions_gaussian_1d(mean, sd, x.astype(np.float64))
+    else:
+        h, (pi, A, Bm) = random_discrete(K, N, 40, seed=602 + N)
+        x = rng.integers(0, 40, size=(B, T)).astype(np.uint8)
+        E = O.emissions_discrete(Bm, x)
+    ref = O.loglik(O.forward(pi, A, E)[1])
+    ll, llb = h.log_likelihood_batch(torch.from_numpy(x).cuda(), tensor_cores=True)
+    assert llb is not None                                           # it really took the tensor-core path
+    np.testing.assert_allclose(ll.cpu().numpy(), ref, rtol=5e-5)
+    np.testing.assert_allclose(llb.cpu().numpy(), ref, rtol=5e-5)
+    ref_r = np.array([O.loglik(O.forward(pi, A, E[b, :lengths[b]])[1]) for b in range(B)])
+    ll, llb = h.log_likelihood_batch(torch.from_numpy(x).cuda(), lengths=lengths, tensor_cores=True)
+    np.testing.assert_allclose(ll.cpu().numpy(), ref_r, rtol=5e-5, atol=3e-3)
+    np.testing.assert_allclose(llb.cpu().numpy(), ref_r, rtol=5e-5, atol=3e-3)
+
+
 def test_fwdbwd_config2_shape_properties(K):
     """N=8 Gaussian, T=2048 at a reduced batch: forward and backward likelihoods agree, and the
     oracle agrees on a sub-sample."""
