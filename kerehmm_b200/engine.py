@@ -515,8 +515,9 @@ TC_AUTO_MIN_ROWS = 1 << 22
 
 
 def estep_tc_supported(p: ModelParams, ob: Obs, real) -> bool:
-    """The fused tcgen05 E-step covers N = 128, float32 (equal-length or ragged batches)."""
-    return (p.kind == "discrete" and p.N == 128 and real == torch().float32 and ob.T < 2 ** 31)
+    """The fused tcgen05 E-step covers 65 <= N <= 128 (N < 128 padded with unreachable states), float32, equal-length
+    or ragged batches."""
+    return (p.kind == "discrete" and TC_MIN_STATES <= p.N <= 128 and real == torch().float32 and ob.T < 2 ** 31)
 
 
 _ws_cache = {}
@@ -546,6 +547,23 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
     """Fused tensor-core E-step (khmm_estep_tc_discrete_f32).  With `stash_out` also returns the
     forward stash W[b][t][:] = c_t alpha_t and the scale factors of the LAST chunk (tests)."""
     t = require_cuda()
+    if p.N < 128:
+        # pad to 128 states with unreachable ones (pad_states): their statistics are exactly zero; the real states'
+        # counts are then picked out of the 128-state buffer.  (The per-sequence smoothing of gamma_0 floors the padded
+        # entries at 1e-10 like any other zero: a 1e-8 relative effect on pi, far below the tf32 bound.)
+        if stash_out:
+            raise ValueError("stash_out needs N = 128")
+        n = p.N
+        big = estep_discrete_tc(pad_states(p), ob, chunk=chunk)
+        counts = counts or Counts(n, p.M)
+        b, c = big.buf, counts.buf
+        c[counts.sl["pi"]] += b[big.sl["pi"]][:n]
+        c[counts.sl["xi"]] += b[big.sl["xi"]].view(128, 128)[:n, :n].reshape(-1)
+        c[counts.sl["gam"]] += b[big.sl["gam"]][:n]
+        c[counts.sl["emis_num"]] += b[big.sl["emis_num"]].view(p.M, 128)[:, :n].reshape(-1)
+        c[counts.sl["emis_den"]] += b[big.sl["emis_den"]][:n]
+        c[counts.sl["tail"]] += b[big.sl["tail"]]
+        return counts
     dm = DeviceModel(p, t.float32)
     N, M, dev = p.N, p.M, device()
     counts = counts or Counts(N, M)
