@@ -535,9 +535,9 @@ def test_tensor_core_estep_ragged_batches(K, B, T, M):
     np.testing.assert_allclose(c40["xi_raw"] * A, tot["xi"], rtol=1e-2, atol=1e-6 * tot["xi"].max())
 
 
-@pytest.mark.parametrize("N", [65, 100])
+@pytest.mark.parametrize("N", [8, 16, 65, 100])
 def test_tensor_core_estep_fewer_than_128_states(K, N):
-    """65 <= N < 128 on the fused tensor-core E-step (padded with unreachable states): statistics against the float32
+    """8 <= N < 128 on the fused tensor-core E-step (padded with unreachable states): statistics against the float32
     SIMT path at the tf32 bounds, ragged batch included; one Baum-Welch pass leaves valid distributions."""
     M, B, T = 24, 148 * 128 + 50, 8
     h, (pi, A, Bm) = random_discrete(K, N, M, seed=90 + N)
