@@ -486,10 +486,16 @@ def run_ours(args):
                                                       "backpointer stream is 1.4 % of HBM (DESIGN.md 3.2)"}
         if kind in ("c2",):
             flops = transitions / world * 4.0          # 2 (forward) + 2 (backward) flop per transition
-            out["roofline"]["fp32_simt"] = {"achieved_tflops": flops / (ms_per_step * 1e-3) / 1e12,
-                                            "nominal_peak_tflops": 74.4,
-                                            "note": "matrix-vector FMAs only; the recursion is FP32-issue bound, "
-                                                    "not HBM bound (DESIGN.md)"}
+            ach_tf = flops / (ms_per_step * 1e-3) / 1e12
+            out["roofline"]["fp32_simt"] = {"achieved_tflops": ach_tf, "nominal_peak_tflops": 74.4,
+                                            "measured_packed_ffma2_peak_tflops": 67.7, "frac_of_measured_peak": ach_tf / 67.7,
+                                            "fma_pipe_busy_ncu": 0.61,
+                                            "note": "the binding roof of this kernel: FP32 issue, not HBM (DESIGN.md 3.1).  "
+                                                    "achieved = the 4 N^2 flop per (sequence, step) of the two matrix-vector "
+                                                    "products alone; with the emission and scaling arithmetic the FMA pipe "
+                                                    "is 61 % busy (ncu, profiles/r1_ncu_c2_fwdbwd_small_summary.csv); the "
+                                                    "packed-FFMA2 peak was measured on this pool "
+                                                    "(profiles/r1_microbench_pipes.json)"}
         if world == 1 and not args.no_cpu:
             cv, sample, cores, dt = cpu_leg(kind, model, obs_h if kind != "c4" else obs_h, args.cpu_cores)
             out["cpu_baseline"] = {"value": cv, "unit": "transitions/s", "cores": cores, "kind": "port",
