@@ -500,7 +500,11 @@ def test_tensor_core_estep_many_tiles_vs_simt(K):
         assert c["nseq"] == B and c["flags"] == 0
         assert np.isclose(c["loglik"], ref["loglik"], rtol=1e-5)
         for key in ("pi", "gam", "emis_den", "emis_num", "xi_raw"):
-            np.testing.assert_allclose(c[key], ref[key], rtol=5e-4, err_msg=key)
+            # xi_raw carries a common factor of about 1 - 3.6e-4 (fp32 stash words truncated to tf32 by MMA2; it cancels in
+            # the M-step's row normalisation): its bound is 1e-3, the normalised rows are checked below
+            np.testing.assert_allclose(c[key], ref[key], rtol=1e-3 if key == "xi_raw" else 5e-4, err_msg=key)
+        np.testing.assert_allclose(c["xi_raw"] / c["xi_raw"].sum(axis=1, keepdims=True),
+                                   ref["xi_raw"] / ref["xi_raw"].sum(axis=1, keepdims=True), rtol=3e-4)
 
 
 @pytest.mark.parametrize("B,T,M", [(300, 12, 16), (148 * 128 + 77, 9, 32)])
@@ -521,7 +525,8 @@ def test_tensor_core_estep_ragged_batches(K, B, T, M):
     assert c["nseq"] == B and c["flags"] == 0
     assert np.isclose(c["loglik"], ref["loglik"], rtol=1e-5)
     for key in ("pi", "gam", "emis_den", "emis_num", "xi_raw"):
-        np.testing.assert_allclose(c[key], ref[key], rtol=5e-4, atol=1e-6 * np.abs(ref[key]).max(), err_msg=key)
+        np.testing.assert_allclose(c[key], ref[key], rtol=1e-3 if key == "xi_raw" else 5e-4,
+                                   atol=1e-6 * np.abs(ref[key]).max(), err_msg=key)
     # the same statistics from the oracle, sequence by sequence, on the first 40 sequences
     sub = slice(0, 40)
     c40 = h.estep_batch(obs[sub], lengths=lengths[sub], tensor_cores=True).host()
