@@ -89,8 +89,8 @@ class DiscreteHMM(AbstractHMM):
                     tensor_cores="auto"):
         """Reference-weighted sufficient statistics summed over a batch as an
         `engine.Counts` on the device -- the buffer that is all-reduced across GPUs.
-        tensor_cores: True / False / "auto".  The fused tcgen05 (tf32) E-step covers N = 128,
-        float32, equal-length and ragged batches; "auto" takes it from 2**22 (sequence, step) rows, where its
+        tensor_cores: True / False / "auto".  The fused tcgen05 (tf32) E-step covers 8 <= N <= 128
+        (padded to 128 states), float32, equal-length and ragged batches; "auto" takes it from 2**22 (sequence, step) rows, where its
         unbiased per-term rounding error has averaged out below the float32 bound."""
         ob = self._prep(observations, lengths)
         return engine.estep_discrete(self._params(), ob, self._real(dtype), counts=counts, chunk=chunk,
