@@ -296,9 +296,13 @@ int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const 
                                       void *workspace, size_t workspace_bytes, double *counts, float *alpha_out,
                                       float *scale_out, khmm_stream_t stream);
 
-/* Device durations (CUDA events on the launching stream) of the forward and the backward kernel of the
- * most recent khmm_estep_tc_discrete_f32 call of this process; waits for that call to finish.  For
- * measurement (bench.py reports the dominant kernel's roofline from it). */
+/* Measurement hook (bench.py's roofline): khmm_estep_tc_timing(1) arms CUDA events on the launching stream around the
+ * forward and the backward kernel of every following khmm_estep_tc_* call (per device, a ring of the last 64 calls;
+ * nothing is created or recorded while disarmed).  khmm_estep_tc_kernel_ms(k, ...) returns the durations of the call
+ * k calls back (0 = the most recent) on the current device and waits for that call to finish;
+ * khmm_estep_tc_last_kernel_ms is k = 0. */
+int khmm_estep_tc_timing(int enable);
+int khmm_estep_tc_kernel_ms(int calls_back, float *forward_ms_host, float *backward_ms_host);
 int khmm_estep_tc_last_kernel_ms(float *forward_ms_host, float *backward_ms_host);
 
 /* Development hook: arm (device buffer of 2*8*32 int64) or disarm (NULL) a clock64 timeline of the warp roles
@@ -359,6 +363,58 @@ int khmm_mstep_gauss_f64(int N, const double *counts, const double *A, double sd
 int khmm_mstep_discrete_f64(int N, int M, const double *counts, const double *A,
                             double *pi_new, double *A_new, double *B_new, int32_t *status,
                             khmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Device-resident training loop.  In the reference every Baum-Welch iteration ends on the host:
+ * DiscreteHMM.do_pass installs the re-estimated pi / A / B as new NumPy arrays (discrete_hmm.py:168-173) and
+ * AbstractHMM.train (abstract_hmm.py:400-441) calls it once per iteration.  khmm_train_commit_discrete_* keeps that
+ * hand-over on the GPU: it installs the outputs of khmm_mstep_discrete_f64 (pi_src[N], A_src[N][N], B_src[N][M]
+ * state-major, float64) as the master parameters pi64 / A64 / B64 and writes the operand copies the recursion
+ * kernels read -- pi_op[Np], A_op[Np][Np], AT_op[Np][Np] and the SYMBOL-MAJOR table Bsm_op[M][Np] -- padded to
+ * Np >= N states with unreachable states (start probability 0, no transitions, zero emission row).
+ * status_it (may be NULL): the M-step's status word of this iteration; sticky (may be NULL): int32[2] =
+ * {status bits of the first failing iteration, that iteration + 1}.  Once either is non-zero nothing is installed
+ * any more: the masters keep the parameters of the last good iteration (the reference raises inside do_pass at
+ * that point; the host raises the same exception when it reads `sticky` after the loop).
+ * Passing the masters themselves as sources (pi_src == pi64, ...) only (re)writes the operand copies.
+ */
+int khmm_train_commit_discrete_f32(int N, int M, int Np, int iteration, const int32_t *status_it, int32_t *sticky,
+                                   const double *pi_src, const double *A_src, const double *B_src, double *pi64,
+                                   double *A64, double *B64, float *pi_op, float *A_op, float *AT_op, float *Bsm_op,
+                                   khmm_stream_t stream);
+int khmm_train_commit_discrete_f64(int N, int M, int Np, int iteration, const int32_t *status_it, int32_t *sticky,
+                                   const double *pi_src, const double *A_src, const double *B_src, double *pi64,
+                                   double *A64, double *B64, double *pi_op, double *A_op, double *AT_op, double *Bsm_op,
+                                   khmm_stream_t stream);
+
+/* min_max[0..1] (device int64) = smallest / largest symbol among the live positions (t < lengths[b]) of obs[B][T].
+ * DiscreteDistribution.get_probability indexes a NumPy table with the symbol (distribution.py:35-36): a symbol >= M
+ * (or < -M) raises IndexError and a negative one wraps; the kernels clamp, so the host checks the range once per
+ * batch with this reduction and raises / wraps before any kernel sees the data. */
+int khmm_symbol_range(int64_t B, int64_t T, const void *obs, int obs_dtype, const int32_t *lengths, int64_t *min_max,
+                      khmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, sequences sharded across ranks, and ONE collective per Baum-Welch iteration --
+ * the in-place sum of the packed float64 count buffer (layout above) over all ranks, after which every rank runs
+ * the same M-step on identical bits (no parameter broadcast).  The reference is single-process; the sums are the
+ * per-sequence statistics of DiscreteHMM.do_pass (discrete_hmm.py:117-159) added over all sequences (SURVEY.md
+ * 8(e)).  NCCL is bound at run time (libnccl.so.2 already loaded in the process, else found by the loader, else
+ * $KHMM_NCCL_LIB); without it these return KHMM_ERR_UNSUPPORTED.
+ *   khmm_comm_unique_id     rank 0 creates the 128-byte rendezvous id; the caller ships it to the other ranks
+ *                           (any side channel: torch.distributed store, MPI, a file);
+ *   khmm_comm_init_rank     collective over all `world` ranks; binds `device`; *comm_out is an opaque handle;
+ *   khmm_allreduce_counts   counts[n] += the other ranks' counts, asynchronous on `stream` (ncclAllReduce, sum, f64);
+ *   khmm_comm_info          rank / world as given at init and the communicator's own rank count (ncclCommCount);
+ *   khmm_comm_destroy       releases the communicator (NULL is a no-op).
+ */
+#define KHMM_COMM_ID_BYTES 128
+int khmm_comm_nccl_version(int *version_host);
+int khmm_comm_unique_id(void *id128_host);
+int khmm_comm_init_rank(const void *id128_host, int rank, int world, int device, void **comm_out);
+int khmm_comm_info(void *comm, int *rank_host, int *world_host, int *nccl_world_host);
+int khmm_allreduce_counts(void *comm, double *counts, size_t n, khmm_stream_t stream);
+int khmm_comm_destroy(void *comm);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,10 @@ class AbstractHMM(object):
     def _feature_dims(self) -> int:
         return 0
 
+    def _alphabet(self):
+        """Table size the symbols index (discrete models), else None."""
+        return None
+
     def _prep(self, observations, lengths=None, single=False):
         obs = observations
         if single:
@@ -59,7 +63,8 @@ class AbstractHMM(object):
                 obs = obs[None]
             else:
                 obs = np.asarray(obs)[None]
-        return engine.prepare_obs(obs, symbols=self._symbols(), lengths=lengths, feature_dims=self._feature_dims())
+        return engine.prepare_obs(obs, symbols=self._symbols(), lengths=lengths, feature_dims=self._feature_dims(),
+                                  alphabet=self._alphabet())
 
     # ---------------------------------------------------------------- state alignment
     def compute_initprob_mapping_score(self, to_hmm, mapping):

@@ -787,8 +787,18 @@ static __global__ void bw_fold_kernel(const float *__restrict__ tab, int M, doub
     if (blockIdx.x == 0 && i == 0) atomicAdd(c_tail + 1, (double)B);
 }
 
-static long long *g_bw_trace = nullptr;
-static cudaEvent_t g_bw_ev[3] = {nullptr, nullptr, nullptr};   // around the forward and backward launches of the last call
+static long long *g_bw_trace = nullptr;   // development timeline (khmm_debug_bw_trace); NULL in production
+
+// Optional kernel timing for bench.py's roofline (khmm_estep_tc_timing): a per-device ring of CUDA-event triples
+// around the forward and backward launches of the last BW_RING calls.  Nothing is created or recorded unless armed.
+constexpr int BW_RING = 64, BW_MAX_DEV = 64;
+struct BwTiming {
+    cudaEvent_t ev[BW_RING][3];
+    bool created;
+    unsigned long long calls;
+};
+static bool g_bw_timing = false;
+static BwTiming g_bw_tm[BW_MAX_DEV];
 
 struct BwWorkspace {
     float *stash, *scale, *tab, *Ar, *ATr;
@@ -842,12 +852,28 @@ int khmm_debug_bw_trace(int64_t *dev_buf) {
     return KHMM_OK;
 }
 
-int khmm_estep_tc_last_kernel_ms(float *forward_ms, float *backward_ms) {
-    KHMM_REQUIRE(g_bw_ev[2] != nullptr, "estep_tc_last_kernel_ms: no tensor-core E-step has been launched");
-    KHMM_CUDA_CHECK(cudaEventSynchronize(g_bw_ev[2]));
-    if (forward_ms) KHMM_CUDA_CHECK(cudaEventElapsedTime(forward_ms, g_bw_ev[0], g_bw_ev[1]));
-    if (backward_ms) KHMM_CUDA_CHECK(cudaEventElapsedTime(backward_ms, g_bw_ev[1], g_bw_ev[2]));
+int khmm_estep_tc_timing(int enable) {
+    g_bw_timing = enable != 0;
     return KHMM_OK;
+}
+
+int khmm_estep_tc_kernel_ms(int calls_back, float *forward_ms, float *backward_ms) {
+    int dev = 0;
+    KHMM_CUDA_CHECK(cudaGetDevice(&dev));
+    KHMM_REQUIRE(dev < BW_MAX_DEV && g_bw_tm[dev].created && g_bw_tm[dev].calls > 0,
+                 "estep_tc_kernel_ms: no timed tensor-core E-step on this device (arm it with khmm_estep_tc_timing(1))");
+    BwTiming &tm = g_bw_tm[dev];
+    KHMM_REQUIRE(calls_back >= 0 && calls_back < BW_RING && (unsigned long long)calls_back < tm.calls,
+                 "estep_tc_kernel_ms: only the last %d timed calls are kept", BW_RING);
+    cudaEvent_t *ev = tm.ev[(tm.calls - 1 - calls_back) % BW_RING];
+    KHMM_CUDA_CHECK(cudaEventSynchronize(ev[2]));
+    if (forward_ms) KHMM_CUDA_CHECK(cudaEventElapsedTime(forward_ms, ev[0], ev[1]));
+    if (backward_ms) KHMM_CUDA_CHECK(cudaEventElapsedTime(backward_ms, ev[1], ev[2]));
+    return KHMM_OK;
+}
+
+int khmm_estep_tc_last_kernel_ms(float *forward_ms, float *backward_ms) {
+    return khmm_estep_tc_kernel_ms(0, forward_ms, backward_ms);
 }
 
 size_t khmm_estep_tc_workspace_bytes(int64_t B, int64_t T, int N, int M) {
@@ -901,16 +927,29 @@ int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const 
     const int64_t ntiles = (B + 127) / 128;
     const int sms = sm_count();
     BwObs ob{obs, obs_dtype, M, T, lengths};
+    cudaEvent_t *tev = nullptr;   // timing events of this call (armed by khmm_estep_tc_timing)
     {
         size_t smem = BW_TILE + 2 * (size_t)FW_EBUF + 6 * 128 * sizeof(float) + sizeof(FwdBars) + 1024;
         KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = (int)(ntiles < sms ? ntiles : sms);
-        for (int k = 0; k < 3; k++)
-            if (!g_bw_ev[k]) KHMM_CUDA_CHECK(cudaEventCreate(&g_bw_ev[k]));
-        KHMM_CUDA_CHECK(cudaEventRecord(g_bw_ev[0], st));
+        if (g_bw_timing) {
+            int dev = 0;
+            KHMM_CUDA_CHECK(cudaGetDevice(&dev));
+            if (dev < BW_MAX_DEV) {
+                BwTiming &tm = g_bw_tm[dev];
+                if (!tm.created) {
+                    for (int r = 0; r < BW_RING; r++)
+                        for (int k = 0; k < 3; k++) KHMM_CUDA_CHECK(cudaEventCreate(&tm.ev[r][k]));
+                    tm.created = true;
+                }
+                tev = tm.ev[tm.calls % BW_RING];
+                tm.calls++;
+            }
+        }
+        if (tev) KHMM_CUDA_CHECK(cudaEventRecord(tev[0], st));
         bw_forward_tc_kernel<<<grid, 384, smem, st>>>(mapAT, mapStashSt, pi, Bsm, ob, B, T, w.scale, w.loglik, g_bw_trace);
         KHMM_LAUNCH_CHECK("bw_forward_tc_kernel");
-        KHMM_CUDA_CHECK(cudaEventRecord(g_bw_ev[1], st));
+        if (tev) KHMM_CUDA_CHECK(cudaEventRecord(tev[1], st));
     }
     {
         size_t smem = 3 * (size_t)BW_TILE + 2 * (size_t)BW_ECHUNK + sizeof(BwdBars) + 1024;
@@ -921,7 +960,7 @@ int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const 
         BwdOut out{g_bw_trace, w.tab, c_xi, c_tail + 2};
         bw_backward_tc_kernel<<<grid, 384, smem, st>>>(mapA, mapStash, Bsm, ob, B, T, w.scale, out);
         KHMM_LAUNCH_CHECK("bw_backward_tc_kernel");
-        KHMM_CUDA_CHECK(cudaEventRecord(g_bw_ev[2], st));
+        if (tev) KHMM_CUDA_CHECK(cudaEventRecord(tev[2], st));
     }
     bw_fold_kernel<<<64, 128, 0, st>>>(w.tab, M, counts, w.loglik, B);
     KHMM_LAUNCH_CHECK("bw_fold_kernel");

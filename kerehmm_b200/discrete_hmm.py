@@ -41,6 +41,9 @@ class DiscreteHMM(AbstractHMM):
     def _symbols(self):
         return True
 
+    def _alphabet(self):
+        return int(self.alphabetSize)
+
     def _assign(self, pi, A, Bm):
         """Install re-estimated parameters the way do_pass does (discrete_hmm.py:168-173):
         new arrays for pi/A, new distribution objects, a sanity_check after each."""
@@ -98,28 +101,38 @@ class DiscreteHMM(AbstractHMM):
 
     def do_pass_batch(self, observations, lengths=None, dtype="float32", chunk=None, group=None,
                       tensor_cores="auto"):
-        """One Baum-Welch pass over a batch of sequences (this rank's shard when torch.distributed
-        is initialised: the packed counts are all-reduced before the M-step, which every rank then
+        """One Baum-Welch pass over a batch of sequences (this rank's shard when a process group is
+        initialised: the packed counts are all-reduced before the M-step, which every rank then
         performs identically).  Returns the summed log-likelihood of the batch under the OLD
         parameters."""
-        from . import dist
-        p = self._params()
-        counts = self.estep_batch(observations, lengths, dtype, chunk, tensor_cores=tensor_cores)
-        dist.all_reduce_counts(counts.buf, group=group)
-        loglik = float(counts.buf[counts.sl["tail"]][0].item())
-        self._assign(*engine.mstep_discrete(p, counts))
-        return loglik
+        return self.train_batch(observations, lengths, 1, dtype, chunk, group, None, tensor_cores)[0]
 
     def train_batch(self, observations, lengths=None, iterations=10, dtype="float32", chunk=None, group=None,
                     tol=None, tensor_cores="auto"):
         """`iterations` batched Baum-Welch passes; returns the list of per-pass log-likelihoods.
-        Stops early when `tol` is given and the log-likelihood gain drops below it."""
-        history = []
-        for _ in range(iterations):
-            history.append(self.do_pass_batch(observations, lengths, dtype, chunk, group, tensor_cores))
-            if tol is not None and len(history) > 1 and history[-1] - history[-2] <= tol:
-                break
-        return history
+        Stops early when `tol` is given and the log-likelihood gain drops below it.
+
+        The loop is device-resident (`engine.DiscreteTrainer`): the observations are copied to the GPU once, and
+        E-step, count all-reduce, M-step and the parameter hand-over of every iteration are queued without a host
+        synchronisation (with `tol` the host reads one double per iteration).  The model attributes are replaced
+        once, after the last iteration, the way do_pass installs them (discrete_hmm.py:168-173).  If an iteration
+        hits one of the reference's exceptional cases (ZeroDivisionError / ValueError of smooth_probabilities, a
+        failed sanity_check) the parameters of the last good iteration are installed and that exception is raised."""
+        ob = self._prep(observations, lengths)
+        trainer = engine.DiscreteTrainer(self._params(), self._real(dtype), max_iterations=iterations)
+        for it in range(iterations):
+            trainer.step(ob, chunk=chunk, tensor_cores=tensor_cores, group=group)
+            if tol is not None and it > 0:
+                h = trainer.history[it - 1:it + 1].cpu().numpy()
+                if h[1] - h[0] <= tol:
+                    break
+        pi, A, Bm, history = trainer.finish()
+        if trainer.status and trainer.failed_iteration == 0:
+            engine._raise_mstep_status(trainer.status)       # nothing was installed on the device either
+        self._assign(pi, A, Bm)
+        if trainer.status:
+            engine._raise_mstep_status(trainer.status)
+        return [float(x) for x in history]
 
     def setup_left_to_right(self, set_emissions=False):
         """discrete_hmm.py:196-227: A[s,s] = A[s,s+1] = 0.5 - (N-2)*DELTA_P (cyclic), rest DELTA_P."""

@@ -127,9 +127,35 @@ def _as_tensor(x):
     return t.from_numpy(np.ascontiguousarray(a))
 
 
-def prepare_obs(obs, symbols: bool, lengths=None, feature_dims: int = 0, u16_bits: bool = False) -> Obs:
+_UNSIGNED_LIMIT = {_lib.U8: 256, _lib.U16: 65536}
+
+
+def check_symbols(x, code: int, B: int, T: int, lengths, alphabet: int):
+    """The reference indexes a NumPy table with every symbol (distribution.py:35-36): a symbol >= M or < -M raises
+    IndexError and a negative one wraps to M + s.  The kernels only clamp (so that padding can hold anything), hence
+    the live positions are range-checked here, once per batch, with one device reduction (`khmm_symbol_range`).
+    -> the tensor to use (a wrapped copy when negative symbols are present)."""
+    if code in _UNSIGNED_LIMIT and alphabet >= _UNSIGNED_LIMIT[code]:
+        return x                      # every representable value is a valid symbol
+    t = torch()
+    mm = t.empty((2,), dtype=t.int64, device=x.device)
+    _lib.call("khmm_symbol_range", B, T, ptr(x), code, ptr(lengths), ptr(mm), stream_ptr())
+    lo, hi = (int(v) for v in mm.cpu().numpy())
+    if B == 0 or lo > hi:
+        return x
+    if hi >= alphabet or lo < -alphabet:
+        bad = hi if hi >= alphabet else lo
+        raise IndexError("index %d is out of bounds for axis 0 with size %d" % (bad, alphabet))
+    if lo < 0:                        # NumPy wraps negative indices
+        x = t.where(x < 0, x + alphabet, x)
+    return x
+
+
+def prepare_obs(obs, symbols: bool, lengths=None, feature_dims: int = 0, u16_bits: bool = False,
+                alphabet: int = None) -> Obs:
     """Move a batch of observations to the device.  symbols=True: integer symbols (B, T);
-    else real observations (B, T) or (B, T, D)."""
+    else real observations (B, T) or (B, T, D).  `alphabet` (discrete models): the table size M the live symbols are
+    checked against, with the reference's IndexError / negative-index behaviour."""
     t = require_cuda()
     was_u16 = (not isinstance(obs, t.Tensor)) and np.asarray(obs).dtype == np.uint16
     x = _as_tensor(obs)
@@ -172,6 +198,8 @@ def prepare_obs(obs, symbols: bool, lengths=None, feature_dims: int = 0, u16_bit
         if B and (la.min() < 1 or la.max() > T):
             raise ValueError("lengths must lie in [1, T]")
         L = t.as_tensor(la.astype(np.int32)).to(device())
+    if symbols and alphabet is not None:
+        x = check_symbols(x, code, B, T, L, int(alphabet))
     return Obs(tensor=x, code=code, B=B, T=T, on_host=on_host, lengths=L, h2d_bytes=h2d)
 
 
@@ -546,9 +574,23 @@ def release_workspace():
     _ws_cache.clear()
 
 
-def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=None, stash_out=False):
+def _pick_counts(big: "Counts", counts: "Counts", n: int):
+    """Add the real states' statistics of a 128-state (padded) count buffer into an n-state one (device ops)."""
+    b, c, M = big.buf, counts.buf, counts.M
+    c[counts.sl["pi"]] += b[big.sl["pi"]][:n]
+    c[counts.sl["xi"]] += b[big.sl["xi"]].view(128, 128)[:n, :n].reshape(-1)
+    c[counts.sl["gam"]] += b[big.sl["gam"]][:n]
+    c[counts.sl["emis_num"]] += b[big.sl["emis_num"]].view(M, 128)[:, :n].reshape(-1)
+    c[counts.sl["emis_den"]] += b[big.sl["emis_den"]][:n]
+    c[counts.sl["tail"]] += b[big.sl["tail"]]
+    return counts
+
+
+def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=None, stash_out=False, operands=None):
     """Fused tensor-core E-step (khmm_estep_tc_discrete_f32).  With `stash_out` also returns the
-    forward stash W[b][t][:] = c_t alpha_t and the scale factors of the LAST chunk (tests)."""
+    forward stash W[b][t][:] = c_t alpha_t and the scale factors of the LAST chunk (tests).
+    `operands`: device-resident float32 operand set at 128 states (pi, A, AT, Bsm attributes -- the training loop's,
+    `DiscreteTrainer`); `p` is then only consulted for its shape (N may be < 128: the operands are already padded)."""
     t = require_cuda()
     if p.N < 128:
         # pad to 128 states with unreachable ones (pad_states): their statistics are exactly zero; the real states'
@@ -557,17 +599,13 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
         if stash_out:
             raise ValueError("stash_out needs N = 128")
         n = p.N
-        big = estep_discrete_tc(pad_states(p), ob, chunk=chunk)
-        counts = counts or Counts(n, p.M)
-        b, c = big.buf, counts.buf
-        c[counts.sl["pi"]] += b[big.sl["pi"]][:n]
-        c[counts.sl["xi"]] += b[big.sl["xi"]].view(128, 128)[:n, :n].reshape(-1)
-        c[counts.sl["gam"]] += b[big.sl["gam"]][:n]
-        c[counts.sl["emis_num"]] += b[big.sl["emis_num"]].view(p.M, 128)[:, :n].reshape(-1)
-        c[counts.sl["emis_den"]] += b[big.sl["emis_den"]][:n]
-        c[counts.sl["tail"]] += b[big.sl["tail"]]
-        return counts
-    dm = DeviceModel(p, t.float32)
+        if operands is not None:
+            big = estep_discrete_tc(ModelParams(kind="discrete", pi=np.empty(128), A=np.empty((128, 0)),
+                                                B=np.empty((128, p.M))), ob, chunk=chunk, operands=operands)
+        else:
+            big = estep_discrete_tc(pad_states(p), ob, chunk=chunk)
+        return _pick_counts(big, counts or Counts(n, p.M), n)
+    dm = operands if operands is not None else DeviceModel(p, t.float32)
     N, M, dev = p.N, p.M, device()
     counts = counts or Counts(N, M)
     L = _lib.lib()
@@ -603,18 +641,23 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
     return counts
 
 
-def estep_discrete(p: ModelParams, ob: Obs, real, counts: Counts = None, chunk=None, tensor_cores="auto"):
+def estep_uses_tc(p: ModelParams, ob: Obs, real, tensor_cores="auto") -> bool:
+    if tensor_cores == "auto":
+        tensor_cores = ob.B * ob.T >= TC_AUTO_MIN_ROWS
+    return bool(tensor_cores) and estep_tc_supported(p, ob, real)
+
+
+def estep_discrete(p: ModelParams, ob: Obs, real, counts: Counts = None, chunk=None, tensor_cores="auto", operands=None):
     """Accumulate the reference-weighted Baum-Welch statistics of a batch into `counts`.
-    tensor_cores: True / False / "auto" (tf32 tcgen05 path for N = 128 once the batch is large)."""
+    tensor_cores: True / False / "auto" (tf32 tcgen05 path for N = 128 once the batch is large).
+    `operands`: device-resident operand set in `real` (see `DiscreteTrainer`) used instead of uploading `p`."""
     t = require_cuda()
     if p.kind != "discrete":
         raise NotImplementedError("Baum-Welch is defined for discrete emissions "
                                   "(GaussianHMM.do_pass is broken in the reference, SURVEY.md Q9)")
-    if tensor_cores == "auto":
-        tensor_cores = ob.B * ob.T >= TC_AUTO_MIN_ROWS
-    if tensor_cores and estep_tc_supported(p, ob, real):
-        return estep_discrete_tc(p, ob, counts=counts, chunk=chunk)
-    dm = DeviceModel(p, real)
+    if estep_uses_tc(p, ob, real, tensor_cores):
+        return estep_discrete_tc(p, ob, counts=counts, chunk=chunk, operands=operands)
+    dm = operands if operands is not None else DeviceModel(p, real)
     N, M, dev = p.N, p.M, device()
     counts = counts or Counts(N, M)
     esize = 4 if real == t.float32 else 8
@@ -647,7 +690,11 @@ def mstep_discrete(p: ModelParams, counts: Counts):
     status = t.zeros((1,), dtype=t.int32, device=dev)
     _lib.call("khmm_mstep_discrete_f64", N, M, ptr(counts.buf), ptr(A_old), ptr(pi_new), ptr(A_new), ptr(B_new),
               ptr(status), stream_ptr())
-    st = int(status.item())
+    _raise_mstep_status(int(status.item()))
+    return pi_new.cpu().numpy(), A_new.cpu().numpy(), B_new.cpu().numpy()
+
+
+def _raise_mstep_status(st: int):
     if st & 1:
         raise ZeroDivisionError("float division by zero")          # util.py:57-58 with k == n
     if st & 2:
@@ -655,7 +702,97 @@ def mstep_discrete(p: ModelParams, counts: Counts):
                          "(smooth_probabilities 2-D path with 2 <= k < n small entries, util.py:51-53)")
     if st & 4:
         raise AssertionError("sanity_check failed: a re-estimated distribution does not sum to 1")
-    return pi_new.cpu().numpy(), A_new.cpu().numpy(), B_new.cpu().numpy()
+
+
+class _Operands:
+    """Device operand set of a discrete model in one real type: pi[Np], A[Np][Np], AT, symbol-major Bsm[M][Np]."""
+
+    def __init__(self, Np, M, real):
+        t, dev = torch(), device()
+        self.real = real
+        self.suffix = "f32" if real == t.float32 else "f64"
+        self.pi = t.empty((Np,), dtype=real, device=dev)
+        self.A = t.empty((Np, Np), dtype=real, device=dev)
+        self.AT = t.empty((Np, Np), dtype=real, device=dev)
+        self.Bsm = t.empty((M, Np), dtype=real, device=dev)
+
+
+class DiscreteTrainer:
+    """Device-resident Baum-Welch loop for a DiscreteHMM (AbstractHMM.train + DiscreteHMM.do_pass,
+    abstract_hmm.py:400-441 / discrete_hmm.py:95-191, batched): the float64 master parameters, the operand copies the
+    kernels read and the count buffer all stay on the GPU between iterations -- E-step, count all-reduce, M-step
+    (`khmm_mstep_discrete_f64`) and the hand-over (`khmm_train_commit_discrete_*`) are queued on the stream without a
+    host synchronisation; the host reads parameters, log-likelihood history and the reference's exceptional-case flags
+    once, in `finish()`."""
+
+    def __init__(self, p: ModelParams, real, max_iterations: int = 1):
+        t = require_cuda()
+        if p.kind != "discrete":
+            raise NotImplementedError("Baum-Welch is defined for discrete emissions "
+                                      "(GaussianHMM.do_pass is broken in the reference, SURVEY.md Q9)")
+        dev = device()
+        self.shape = ModelParams(kind="discrete", pi=np.empty(p.N), A=np.empty((p.N, 0)), B=np.empty((p.N, p.M)))
+        self.N, self.M, self.real = p.N, p.M, real
+        self.pi64, self.A64, self.B64 = _dev(p.pi, t.float64), _dev(p.A, t.float64), _dev(p.B, t.float64)
+        self.pi_n, self.A_n, self.B_n = t.empty_like(self.pi64), t.empty_like(self.A64), t.empty_like(self.B64)
+        self.status_it = t.zeros((1,), dtype=t.int32, device=dev)
+        self.sticky = t.zeros((2,), dtype=t.int32, device=dev)
+        self.history = t.zeros((max(1, max_iterations),), dtype=t.float64, device=dev)
+        self.counts = Counts(self.N, self.M)
+        self.ops = {}           # Np -> _Operands (N itself, or 128 for the padded tensor-core E-step)
+        self.iteration = 0
+
+    def operands(self, Np):
+        ops = self.ops.get(Np)
+        if ops is None:
+            ops = self.ops[Np] = _Operands(Np, self.M, self.real)
+            self._commit(ops, Np, None, initial=True)
+        return ops
+
+    def _commit(self, ops, Np, status, initial=False):
+        src = (self.pi64, self.A64, self.B64) if initial else (self.pi_n, self.A_n, self.B_n)
+        _lib.call("khmm_train_commit_discrete_" + ops.suffix, self.N, self.M, Np, self.iteration, ptr(status),
+                  None if initial else ptr(self.sticky), ptr(src[0]), ptr(src[1]), ptr(src[2]), ptr(self.pi64),
+                  ptr(self.A64), ptr(self.B64), ptr(ops.pi), ptr(ops.A), ptr(ops.AT), ptr(ops.Bsm), stream_ptr())
+
+    def step(self, ob: Obs, chunk=None, tensor_cores="auto", group=None):
+        """One Baum-Welch iteration over this rank's batch, asynchronous on the current stream."""
+        from . import dist as kdist
+        use_tc = estep_uses_tc(self.shape, ob, self.real, tensor_cores)
+        Np = 128 if use_tc else self.N
+        ops = self.operands(Np)
+        self.counts.buf.zero_()
+        estep_discrete(self.shape, ob, self.real, counts=self.counts, chunk=chunk, tensor_cores=use_tc, operands=ops)
+        kdist.all_reduce_counts(self.counts.buf, group=group)
+        if self.iteration < self.history.numel():
+            o = self.counts.sl["tail"].start
+            self.history[self.iteration:self.iteration + 1].copy_(self.counts.buf[o:o + 1])
+        _lib.call("khmm_mstep_discrete_f64", self.N, self.M, ptr(self.counts.buf), ptr(self.A64), ptr(self.pi_n),
+                  ptr(self.A_n), ptr(self.B_n), ptr(self.status_it), stream_ptr())
+        # every operand set in use follows the masters (normally one)
+        first = True
+        for np_, o_ in self.ops.items():
+            if first:
+                self._commit(o_, np_, self.status_it)
+                first = False
+            else:
+                self._commit(o_, np_, None, initial=True)
+        self.iteration += 1
+
+    def last_loglik(self) -> float:
+        """Summed log-likelihood (under the parameters the iteration started from) of the last iteration; synchronises."""
+        return float(self.history[self.iteration - 1].item())
+
+    def finish(self):
+        """-> (pi, A, B (N, M), loglik history) on the host; raises what the reference's do_pass would have raised in
+        the first iteration that hit an exceptional case (the parameters are those of the last good iteration)."""
+        t = torch()
+        sticky = self.sticky.cpu().numpy()
+        hist = self.history[:self.iteration].cpu().numpy().copy()
+        pi, A, B = self.pi64.cpu().numpy(), self.A64.cpu().numpy(), self.B64.cpu().numpy()
+        self.failed_iteration = int(sticky[1]) - 1 if sticky[0] else None
+        self.status = int(sticky[0])
+        return pi, A, B, hist
 
 
 # ---------------------------------------------------------------------------------- sampling

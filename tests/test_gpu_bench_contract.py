@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("workload,extra", [("c1", []), ("c2", ["--batch", "2048"])])
+@pytest.mark.parametrize("workload,extra", [("c1", []), ("c2", ["--batch", "2048"]), ("c4", ["--batch", "1024"])])
 def test_bench_prints_the_contract_line(workload, extra):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", workload, "--steps", "3", "--warmup", "3"]
                          + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
@@ -30,7 +30,10 @@ def test_bench_prints_the_contract_line(workload, extra):
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in d["roofline"], key
-    assert d["roofline"]["bound"] in ("hbm", "tensor")
+    # the default workload (c4) reports against HBM; sub-workloads name their own binding roof
+    assert d["roofline"]["bound"] in ("hbm", "tensor", "fp32_simt", "fp64_pipe")
+    if workload == "c4":
+        assert d["roofline"]["bound"] == "hbm" and d["config"]["mstep_status"] == 0
     for key in ("sm_mhz", "sm_max_mhz", "reasons"):
         assert key in d["clocks"], key
     for key in ("value", "unit", "cores", "kind", "sample"):

@@ -28,7 +28,7 @@ obs = np.random.default_rng(6).integers(0, 20, size=(101, 48))
 lo, hi = kdist.shard_bounds(len(obs))
 hist = h.train_batch(obs[lo:hi], iterations=3, dtype="float64")
 out = dict(rank=rank, lo=lo, hi=hi, hist=hist, A=h.transitionMatrix.tolist(), B=h.emission_matrix().tolist(),
-           pi=h.initialProbabilities.tolist())
+           pi=h.initialProbabilities.tolist(), comm=list(kdist.comm_info()))   # libkhmm's own NCCL communicator
 json.dump(out, open(os.path.join(sys.argv[1], "rank%%d.json" %% rank), "w"))
 dist.destroy_process_group()
 """ % ROOT
@@ -47,6 +47,7 @@ def test_two_rank_baum_welch_matches_single_rank(tmp_path):
     r0 = json.load(open(tmp_path / "rank0.json"))
     r1 = json.load(open(tmp_path / "rank1.json"))
     assert (r0["lo"], r0["hi"], r1["lo"], r1["hi"]) == (0, 51, 51, 101)
+    assert r0["comm"] == [0, 2, 2] and r1["comm"] == [1, 2, 2]      # khmm_comm_init_rank: NCCL itself counts 2 ranks
     assert r0["A"] == r1["A"] and r0["B"] == r1["B"] and r0["pi"] == r1["pi"]      # bitwise identical ranks
     assert r0["hist"] == r1["hist"]
     np.random.seed(5)

@@ -1,0 +1,153 @@
+"""GPU tests of the round-2 host/device plumbing around the hot path: the device-resident Baum-Welch loop
+(`engine.DiscreteTrainer`, what `DiscreteHMM.train_batch` runs), the range check of live symbols with the reference's
+IndexError / negative-index behaviour, and libkhmm's own NCCL communicator entry points (single rank here; two ranks in
+tests/test_gpu_dist.py)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import hmm_oracle as O
+from test_gpu_parity import K, discrete_model, random_discrete  # noqa: F401  (K is a fixture)
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_train(pi, A, Bm, obs, iterations):
+    hist = []
+    for _ in range(iterations):
+        stats = O.batch_stats_discrete(pi, A, Bm, obs)
+        hist.append(stats["loglik"])
+        pi, A, Bm = O.mstep_discrete(stats)
+    return pi, A, Bm, hist
+
+
+@pytest.mark.parametrize("N,M,B,T,dtype,rtol", [(6, 8, 40, 64, "float64", 1e-8), (16, 12, 64, 48, "float32", 2e-4),
+                                                (128, 24, 200, 32, "float64", 1e-8)])
+def test_device_resident_loop_tracks_the_oracle(K, N, M, B, T, dtype, rtol):
+    """`train_batch` keeps parameters on the GPU between iterations; after k iterations they must equal the oracle's
+    k E/M passes (the float32 bound loosens with the iteration count: errors feed back through the parameters)."""
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=141)
+    obs = np.random.default_rng(142).integers(0, M, size=(B, T))
+    hist = h.train_batch(obs, iterations=3, dtype=dtype, tensor_cores=False)
+    rpi, rA, rB, rhist = _oracle_train(pi, A, Bm, obs, 3)
+    np.testing.assert_allclose(hist, rhist, rtol=1e-9 if dtype == "float64" else 1e-5)
+    np.testing.assert_allclose(h.initialProbabilities, rpi, rtol=rtol, atol=1e-13)
+    np.testing.assert_allclose(h.transitionMatrix, rA, rtol=rtol, atol=1e-13)
+    np.testing.assert_allclose(h.emission_matrix(), rB, rtol=rtol, atol=1e-13)
+    h.sanity_check()
+
+
+def test_device_resident_loop_equals_repeated_single_passes(K):
+    """k iterations in one device-resident loop == k calls of do_pass_batch (host round trip each time), bit for bit
+    in float64: the hand-over kernel installs exactly what the M-step wrote."""
+    h1, _ = random_discrete(K, 12, 20, seed=5)
+    h2, _ = random_discrete(K, 12, 20, seed=5)
+    obs = np.random.default_rng(6).integers(0, 20, size=(101, 48))
+    hist1 = h1.train_batch(obs, iterations=3, dtype="float64")
+    hist2 = [h2.do_pass_batch(obs, dtype="float64") for _ in range(3)]
+    assert hist1 == hist2
+    assert np.array_equal(h1.transitionMatrix, h2.transitionMatrix)
+    assert np.array_equal(h1.emission_matrix(), h2.emission_matrix())
+    assert np.array_equal(h1.initialProbabilities, h2.initialProbabilities)
+
+
+def test_device_resident_loop_tensor_core_path_and_padding(K):
+    """The loop on the fused tcgen05 E-step (N = 128, and N = 40 padded to 128 on the device by the hand-over kernel)
+    against the float32 SIMT loop, 2 iterations."""
+    for N in (128, 40):
+        M, B, T = 32, 384, 40
+        h1, _ = random_discrete(K, N, M, seed=9)
+        h2, _ = random_discrete(K, N, M, seed=9)
+        obs = np.random.default_rng(10).integers(0, M, size=(B, T))
+        hist1 = h1.train_batch(obs, iterations=2, tensor_cores=True)
+        hist2 = h2.train_batch(obs, iterations=2, tensor_cores=False)
+        np.testing.assert_allclose(hist1, hist2, rtol=3e-5)
+        np.testing.assert_allclose(h1.transitionMatrix, h2.transitionMatrix, rtol=5e-3)
+        np.testing.assert_allclose(h1.emission_matrix(), h2.emission_matrix(), rtol=5e-3)
+        h1.sanity_check()
+
+
+def test_loop_reports_the_reference_exceptions_once_at_the_end(K):
+    """A model that drives smooth_probabilities' 2-D ValueError case (two tiny entries in a transition row): the
+    device loop keeps the last good parameters and raises after the loop, like do_pass raises inside it."""
+    N, M = 4, 5
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=3)
+    A = A.copy()
+    A[1] = [1e-300, 1e-300, 0.5, 0.5]
+    h.transitionMatrix = A
+    obs = np.random.default_rng(4).integers(0, M, size=(6, 20))
+    with pytest.raises(Exception) as ei:
+        O.mstep_discrete(O.batch_stats_discrete(pi, A, Bm, obs))
+    with pytest.raises(type(ei.value)):
+        h.train_batch(obs, iterations=3, dtype="float64")
+    assert np.array_equal(h.transitionMatrix, A)          # nothing was installed
+
+
+def test_tol_stops_early(K):
+    h, _ = random_discrete(K, 5, 6, seed=8)
+    obs = np.random.default_rng(9).integers(0, 6, size=(30, 40))
+    hist = h.train_batch(obs, iterations=50, dtype="float64", tol=1e9)     # any gain is below this tolerance
+    assert len(hist) == 2
+
+
+# ---------------------------------------------------------------------------------- symbols
+def test_out_of_range_symbols_raise_like_numpy_indexing(K):
+    """distribution.py:35-36 indexes the table with the symbol: >= M or < -M raises IndexError, negatives wrap."""
+    h, (pi, A, Bm) = random_discrete(K, 4, 5, seed=0)
+    good = np.random.default_rng(1).integers(0, 5, size=(3, 12))
+    bad = good.copy()
+    bad[1, 7] = 5
+    for call in (h.forward_batch, h.viterbi_batch, h.log_likelihood_batch, h.estep_batch):
+        with pytest.raises(IndexError):
+            call(bad)
+    with pytest.raises(IndexError):
+        h.forward(bad[1])
+    bad[1, 7] = -6
+    with pytest.raises(IndexError):
+        h.viterbi_batch(bad)
+    # negative symbols wrap: -1 is the last symbol
+    neg = good.copy()
+    neg[neg == 4] = -1
+    a1, s1, l1 = h.forward_batch(good, dtype="float64")
+    a2, s2, l2 = h.forward_batch(neg, dtype="float64")
+    assert np.array_equal(a1, a2) and np.array_equal(l1, l2)
+    p1, lp1 = h.viterbi_batch(good)
+    p2, lp2 = h.viterbi_batch(neg)
+    assert np.array_equal(p1, p2) and np.array_equal(lp1, lp2)
+    # padding past a sequence's length may hold anything
+    rag = good.copy()
+    rag[0, 6:] = 99
+    a3, _, l3 = h.forward_batch(rag, lengths=[6, 12, 12], dtype="float64")
+    np.testing.assert_array_equal(l3[1:], l1[1:])
+    # uint8 symbols with a 256-symbol table can never be out of range (no check, no sync)
+    h256, _ = random_discrete(K, 4, 256, seed=2)
+    h256.log_likelihood_batch(np.random.default_rng(3).integers(0, 256, size=(4, 9), dtype=np.uint8))
+
+
+# ------------------------------------------------------------------------------ communicator
+def test_comm_entry_points_single_rank(K):
+    """khmm_comm_* with world = 1: id creation, init, info, an all-reduce that is the identity, destroy."""
+    import torch
+    from kerehmm_b200 import _lib
+    from kerehmm_b200 import dist as kdist
+    L = _lib.lib()
+    ver = ctypes.c_int()
+    _lib.call("khmm_comm_nccl_version", ctypes.byref(ver))
+    assert ver.value >= 20000
+    assert kdist._comm is None
+    kdist.init_comm(rank=0, world_size=1)
+    try:
+        assert kdist.world() == (0, 1)
+        r, w, n = kdist.comm_info()
+        assert (r, w) == (0, 1) and n in (1, -1)
+        buf = torch.arange(7, dtype=torch.float64, device="cuda")
+        kdist.all_reduce_counts(buf)
+        torch.cuda.synchronize()
+        assert buf.cpu().tolist() == list(range(7))
+    finally:
+        kdist.destroy_comm()
+    assert kdist._comm is None
+    with pytest.raises(_lib.KhmmError):
+        _lib.call("khmm_comm_init_rank", ctypes.create_string_buffer(128), 3, 2, 0, ctypes.byref(ctypes.c_void_p()))
+    assert L.khmm_comm_destroy(None) == 0

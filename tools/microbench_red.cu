@@ -6,6 +6,7 @@
 //   3: thread per row, scalar red.f32 (128 per row)
 //   4: warp per row, red.v2.f32
 //   5: like 1 but into R=8 replicas of the table chosen by blockIdx
+//   bulk: TMA bulk reductions (cp.reduce.async.bulk) of whole rows staged in shared memory, into 8 replicas
 // Prints rows/us and float adds per clock per SM.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench_red tools/microbench_red.cu
 #include <cuda_runtime.h>
@@ -56,6 +57,50 @@ __global__ void __launch_bounds__(128) k(float *table, int rows_per_thread_or_wa
     }
 }
 
+// TMA bulk reduction: rows staged in shared memory, `issuers` lanes of warp 0 each send whole 512-byte rows with
+// cp.reduce.async.bulk.global.shared::cta.add.f32 (one instruction per row), groups of `per_group` rows per commit.
+__global__ void __launch_bounds__(128) k_bulk(float *table, int rows_per_cta, int M, int issuers, int row_bytes) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    float *rows = reinterpret_cast<float *>(sm);            // 64 rows x 512 B staging
+    for (int k = threadIdx.x; k < 64 * 128; k += blockDim.x) rows[k] = 1e-6f * (k & 31);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    table += (size_t)(blockIdx.x & 7) * M * 128;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32 && lane < issuers) {
+        const int pieces = 512 / row_bytes;
+        for (int it = lane; it < rows_per_cta; it += issuers) {
+            int row = hash(blockIdx.x * 7919u + it) % M;
+            for (int pc = 0; pc < pieces; pc++) {
+                float *dst = table + (size_t)row * 128 + pc * (row_bytes / 4);
+                uint32_t src = (uint32_t)__cvta_generic_to_shared(rows + (it & 63) * 128 + pc * (row_bytes / 4));
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                             ::"l"(dst), "r"(src), "r"(row_bytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (((it / issuers) & 15) == 15) asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+static void run_bulk(const char *name, float *table, int M, int sms, double mhz, int issuers, int row_bytes) {
+    const int ctas = sms, per = 16384;
+    double rows = (double)ctas * per;
+    k_bulk<<<ctas, 128, 64 * 512>>>(table, per / 8, M, issuers, row_bytes);
+    cudaDeviceSynchronize();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    k_bulk<<<ctas, 128, 64 * 512>>>(table, per, M, issuers, row_bytes);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("%-44s %8.3f ms  %8.1f rows/us  %6.2f float-adds/clk/SM (at %.0f MHz)  err=%s\n", name, ms, rows / ms * 1e-3,
+           rows * 128 / (ms * 1e-3) / sms / (mhz * 1e6), mhz, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int MODE>
 static void run(const char *name, float *table, int M, int sms, double mhz) {
     const int ctas = sms * 8;
@@ -92,5 +137,10 @@ int main() {
     run<2>("warp/row red.f32 coalesced", table, M, p.multiProcessorCount, mhz);
     run<3>("thread/row red.f32 (128 per row)", table, M, p.multiProcessorCount, mhz);
     run<5>("warp/row red.v4 coalesced, 8 replicas", table, M, p.multiProcessorCount, mhz);
+    run_bulk("TMA bulk reduce 512 B rows, 1 issuer/CTA", table, M, p.multiProcessorCount, mhz, 1, 512);
+    run_bulk("TMA bulk reduce 512 B rows, 4 issuers/CTA", table, M, p.multiProcessorCount, mhz, 4, 512);
+    run_bulk("TMA bulk reduce 512 B rows, 32 issuers/CTA", table, M, p.multiProcessorCount, mhz, 32, 512);
+    run_bulk("TMA bulk reduce 4 x 128 B pieces, 4 issuers", table, M, p.multiProcessorCount, mhz, 4, 128);
+    run_bulk("TMA bulk reduce 4 x 128 B pieces, 32 issuers", table, M, p.multiProcessorCount, mhz, 32, 128);
     return 0;
 }
