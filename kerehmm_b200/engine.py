@@ -135,8 +135,8 @@ def check_symbols(x, code: int, B: int, T: int, lengths, alphabet: int):
     IndexError and a negative one wraps to M + s.  The kernels only clamp (so that padding can hold anything), hence
     the live positions are range-checked here, once per batch, with one device reduction (`khmm_symbol_range`).
     -> the tensor to use (a wrapped copy when negative symbols are present)."""
-    if code in _UNSIGNED_LIMIT and alphabet >= _UNSIGNED_LIMIT[code]:
-        return x                      # every representable value is a valid symbol
+    if B == 0 or (code in _UNSIGNED_LIMIT and alphabet >= _UNSIGNED_LIMIT[code]):
+        return x                      # nothing to check / every representable value is a valid symbol
     t = torch()
     mm = t.empty((2,), dtype=t.int64, device=x.device)
     _lib.call("khmm_symbol_range", B, T, ptr(x), code, ptr(lengths), ptr(mm), stream_ptr())
