@@ -305,6 +305,10 @@ int khmm_estep_tc_timing(int enable);
 int khmm_estep_tc_kernel_ms(int calls_back, float *forward_ms_host, float *backward_ms_host);
 int khmm_estep_tc_last_kernel_ms(float *forward_ms_host, float *backward_ms_host);
 
+/* Development hook: which backward kernel the fused E-step uses -- 1 = thread per sequence (the default), 2 = the
+ * transposed thread-per-state kernel, 0 = back to the default / $KHMM_BW_BACKWARD.  Both compute the same statistics
+ * (tests/test_gpu_parity.py runs the tensor-core E-step tests on both). */
+int khmm_debug_bw_backward_version(int version);
 /* Development hook: arm (device buffer of 2*8*32 int64) or disarm (NULL) a clock64 timeline of the warp roles
  * of the backward and forward kernels (block 0, steps 8..15; tools/dbg_bw_trace.py prints it). */
 int khmm_debug_bw_trace(int64_t *dev_buf);

@@ -27,6 +27,10 @@
 //
 // HBM traffic per (sequence, step): 512 B stash write + 512 B stash read + 6 B observations/scales
 // (the generic path moves 2.5 KB).  Precision: tf32 multiplies, fp32 accumulation; tests state the bound.
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -752,6 +756,421 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------- backward, transposed (round 2)
+// The round-1 kernel above has thread = sequence (TMEM lane = sequence).  Its timeline (profiles/r2_trace_c4_backward_v1.txt)
+// shows a serial chain MMA1 (2,100 cycles) -> epilogue pass (3,400) -> V2 pass (1,600) per step, all three bound by the
+// 64 B/clk TMEM READ port: D1 is read once, V is read back for the shared-memory copy, the gamma staging area is read
+// back by the reduction warps, and MMA1's A operand (V) comes from TMEM as well -- 256 KB of TMEM reads per step.
+//
+// This kernel transposes the problem: TMEM lane = STATE.  Per step t (one tile of 128 sequences):
+//     MMA1  D1^T[i][b]  = sum_j A[i][j] V_{t+1}[b][j]      A operand = the transition matrix, resident in TMEM for the
+//                                                          whole kernel; B operand = V (K-major, written by the compute warps)
+//     MMA2  Xi^T[j][i] += sum_b V2_{t+1}[b][j] W_t[b][i]   A operand = V2^T in TMEM -- the compute thread of state j OWNS
+//                                                          row j of V2^T, so it stores it with tcgen05.st; B operand =
+//                                                          the W_t tile exactly as TMA delivers it (MN-major)
+//     compute warps (8), thread = state i, 64 sequences each (4 lane quadrants x 2 sequence halves):
+//         beta_t[b] = D1^T[i][b] / c_{t+1}[b];  gamma_ref = W_t[b][i] beta;  V_t[b][i] = b_i(o_t[b]) beta -> shared memory
+//         (MMA1's operand) and, divided by c_{t-1}, -> TMEM (MMA2's).  Every access is contiguous across the warp.
+//     slabs: four 16 KB buffers [32 sequences][128 states], one per (half, chunk).  A TMA gather4 (4 table rows per
+//         instruction, no LSU involvement) fills a slab with the emission rows b(o_t[b]) one step ahead; the compute warps
+//         read them and overwrite them IN PLACE with gamma_ref; four reduction warps then stream each row into row o_t[b]
+//         of the fp32 count table with one coalesced red.global.add.v4.f32 per row (the L2 atomic rate, ~0.6 sector-ops
+//         per clock per SM, is the floor of this kernel) and hand the slab back to the gather.  At t = 0 they apply
+//         smooth1d(gamma[0]) per sequence with warp-wide reductions (discrete_hmm.py:132, util.py:56-60).
+// TMEM is read exactly once per step by the threads (D1); the W tile is read into registers at the start of the step and
+// released at once, so ONE buffer gives the TMA producer a whole step of prefetch distance.  Per-sequence scalars (table
+// row, 1/c_{t+1}, 1/c_{t-1}, ragged-batch switches) are staged one step ahead by a helper warp.
+constexpr uint32_t C2_A = 0, C2_D1 = 128, C2_XI = 256, C2_V2T = 384;
+constexpr int BW_SLAB = 32 * 128 * 4;   // [32 sequences][128 states] fp32
+
+struct __align__(8) Bwd2Bars {
+    uint64_t w_full, w_empty, v_ready, d1_full, mma2_q[4], prep_full[2], prep_empty[2], e_full[4], g_full[4], s_empty[4];
+    uint32_t tmem_base;
+};
+struct __align__(16) Bwd2Prep {
+    int srow[128];     // 128 * clamped symbol (float offset of the table row) | bit 31: (row, step) not live (t >= len, or a
+                       // row past the batch) | bit 30: t == len - 1
+    float mulb[128];   // 1 / c_{t+1}, or 0 where beta_t = 1 (t >= len - 1: the sequence's last step or its padding)
+    float rcm1[128];   // 1 / c_{t-1} for 0 < t < len, else 0 (V2_t = 0: the pair (t-1, t) does not count)
+};
+constexpr int SROW_MASK = 0x3fffffff, SROW_LAST = 0x40000000;
+
+// No "memory" clobber: nothing in the kernel reads the count table, and the clobber would pin every shared-memory access
+// between two reductions.
+__device__ __forceinline__ void red_add_v4_nc(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+__device__ __forceinline__ void tma_gather4(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int r0, int r1,
+                                            int r2, int r3) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
+#define BW2_TRACE(ev)                                                                                  \
+    do {                                                                                               \
+        if (out.trace && blockIdx.x == 0 && tile == blockIdx.x && (Ti - 1 - t) >= 8 && (Ti - 1 - t) < 16 && \
+            (threadIdx.x & 31) == 0)                                                                   \
+            out.trace[((Ti - 1 - t) - 8) * 32 + (ev)] = clock64();                                      \
+    } while (0)
+
+__global__ void __launch_bounds__(512, 1)
+bw_backward_tc2_kernel(const __grid_constant__ CUtensorMap mapStash, const __grid_constant__ CUtensorMap mapB,
+                       const float *__restrict__ Ar, BwObs ob, int64_t B, int64_t T, const float *__restrict__ scale,
+                       BwdOut out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *sW = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // W_t tile (TMA, MN-major 32 B atoms)
+    unsigned char *sVk = sW + BW_TILE;      // V_{t+1}: B operand of MMA1, K-major SWIZZLE_128B
+    unsigned char *slab = sVk + BW_TILE;    // 4 x [32][128] fp32: emission rows in, gamma_ref rows out
+    Bwd2Prep *prep = (Bwd2Prep *)(slab + 4 * BW_SLAB);
+    Bwd2Bars *bars = (Bwd2Bars *)(prep + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (B + 127) / 128;
+    const int M = ob.M;
+    const int Ti = (int)T;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->w_full, 1);
+        mbar_init(&bars->w_empty, 9);        // 8 compute warps + the commit of MMA2
+        mbar_init(&bars->v_ready, 256);
+        mbar_init(&bars->d1_full, 1);
+        for (int k = 0; k < 2; k++) {
+            mbar_init(&bars->prep_full[k], 1);
+            mbar_init(&bars->prep_empty[k], 13);   // 8 compute warps + 4 reduction warps + the gather warp
+        }
+        for (int k = 0; k < 4; k++) {
+            mbar_init(&bars->mma2_q[k], 1);
+            mbar_init(&bars->e_full[k], 1);
+            mbar_init(&bars->g_full[k], 128);
+            mbar_init(&bars->s_empty[k], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 8) {
+        // ------------------------------------------------ TMA producer: W_t tiles of the stash
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (elect_one()) {
+            tma_prefetch_desc(&mapStash);
+            uint32_t g = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int t = Ti - 1; t >= 0; t--, g++) {
+                    mbar_wait(&bars->w_empty, (g & 1) ^ 1);
+                    BW2_TRACE(0);
+                    mbar_arrive_expect_tx(&bars->w_full, BW_TILE);
+                    for (int c = 0; c < 4; c++)
+                        tma_load_3d(sW + c * BW_SUB, &mapStash, &bars->w_full, c * 32, 0, (int)(tile * T + t));
+                }
+        }
+    } else if (warp == 9) {
+        // ------------------------------------------------ MMA issuer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (elect_one()) {
+            const uint32_t idesc_k = make_idesc_tf32(128, 128);
+            const uint32_t idesc_mn = make_idesc_tf32(128, 128, false, true);
+            const uint64_t dW = make_mnmajor_sw128a32_desc(sW, BW_SUB, 512);
+            uint32_t nv = 0, g = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                g++;      // step t = T-1 has no MMA
+                for (int t = Ti - 2; t >= 0; t--, g++) {
+                    mbar_wait(&bars->v_ready, nv & 1);
+                    nv++;
+                    BW2_TRACE(4);
+                    tc_fence_after();
+                    // MMA1(t): D1^T = A . V_{t+1}^T
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        uint64_t db = make_kmajor_sw128_desc(sVk + (k >> 2) * BW_SUB);
+                        mma_tf32_ts(tmem + C2_D1, tmem + C2_A + k * 8, desc_advance(db, (k & 3) * 32), idesc_k, k != 0);
+                    }
+                    tc_commit(&bars->d1_full);
+                    BW2_TRACE(5);
+                    mbar_wait(&bars->w_full, g & 1);
+                    BW2_TRACE(6);
+                    tc_fence_after();
+                    // MMA2(t): Xi^T += V2^T_{t+1} . W_t, K = the 128 sequences in the order the compute warps overwrite
+                    // the V2^T columns (sequences 0-31 and 64-95 first); one commit per 32 sequences releases them
+#pragma unroll
+                    for (int grp = 0; grp < 4; grp++) {
+                        const int r0 = (grp & 1) * 64 + (grp >> 1) * 32;
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            const int k = r0 / 8 + kk;
+                            mma_tf32_ts(tmem + C2_XI, tmem + C2_V2T + k * 8, desc_advance(dW, k * 1024), idesc_mn,
+                                        (t != Ti - 2) || grp != 0 || kk != 0);
+                        }
+                        tc_commit(&bars->mma2_q[grp]);
+                    }
+                    tc_commit(&bars->w_empty);
+                    BW2_TRACE(7);
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ------------------------------------------------ prep: per-sequence scalars of the step, one step ahead
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        uint32_t g = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int64_t bc[4];
+            int len[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int64_t gb = tile * 128 + lane + 32 * k;
+                bc[k] = gb < B ? gb : B - 1;
+                len[k] = gb < B ? ob.len(gb) : 0;
+            }
+            for (int t = Ti - 1; t >= 0; t--, g++) {
+                const int buf = g & 1;
+                int sy[4];
+                float c1[4], cm[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int b = lane + 32 * k;
+                    sy[k] = ob.sym(bc[k], t);
+                    c1[k] = (t + 1 < Ti) ? scale[(tile * T + t + 1) * 128 + b] : 1.f;
+                    cm[k] = (t > 0) ? scale[(tile * T + t - 1) * 128 + b] : 1.f;
+                }
+                mbar_wait(&bars->prep_empty[buf], ((g >> 1) & 1) ^ 1);
+                Bwd2Prep &P = prep[buf];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int b = lane + 32 * k;
+                    const bool bone = (t == Ti - 1) || (t >= len[k] - 1);
+                    P.srow[b] = (sy[k] * BW_N) | (t < len[k] ? 0 : (int)0x80000000) | (t == len[k] - 1 ? SROW_LAST : 0);
+                    P.mulb[b] = bone ? 0.f : 1.0f / c1[k];
+                    P.rcm1[b] = (t > 0 && t < len[k]) ? 1.0f / cm[k] : 0.f;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->prep_full[buf]);
+            }
+        }
+    } else if (warp == 11) {
+        // ------------------------------------------------ gather: emission rows b(o_t[b]) -> slabs, 4 table rows per TMA
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (lane == 0) tma_prefetch_desc(&mapB);
+        uint32_t g = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            for (int t = Ti - 1; t >= 0; t--, g++) {
+                const int buf = g & 1;
+                mbar_wait(&bars->prep_full[buf], (g >> 1) & 1);
+                const Bwd2Prep &P = prep[buf];
+#pragma unroll 1
+                for (int s = 0; s < 4; s++) {
+                    mbar_wait(&bars->s_empty[s], (g & 1) ^ 1);     // the reduction warps have drained the previous step's rows
+                    if (lane == 0) mbar_arrive_expect_tx(&bars->e_full[s], BW_SLAB);
+                    __syncwarp();
+                    if (lane < 8) {
+                        const int b0 = (s & 1) * 64 + (s >> 1) * 32 + 4 * lane;
+                        const int4 r4 = *reinterpret_cast<const int4 *>(P.srow + b0);
+                        tma_gather4(slab + s * BW_SLAB + 4 * lane * 512, &mapB, &bars->e_full[s], 0, (r4.x & SROW_MASK) >> 7,
+                                    (r4.y & SROW_MASK) >> 7, (r4.z & SROW_MASK) >> 7, (r4.w & SROW_MASK) >> 7);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->prep_empty[buf]);
+            }
+    } else if (warp >= 12) {
+        // ------------------------------------------------ reduction warps: gamma_ref rows -> fp32 count table in L2
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        const int r = warp - 12;
+        float *tab0 = out.tab + (size_t)(blockIdx.x % BW_REPL) * (size_t)(M + 2) * BW_N + 4 * lane;
+        float *r_pi = tab0 + (size_t)M * BW_N;
+        float *r_last = tab0 + (size_t)(M + 1) * BW_N;
+        uint32_t g = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            for (int t = Ti - 1; t >= 0; t--, g++) {
+                const int buf = g & 1;
+                mbar_wait(&bars->prep_full[buf], (g >> 1) & 1);
+                const Bwd2Prep &P = prep[buf];
+#pragma unroll 1
+                for (int s = 0; s < 4; s++) {
+                    mbar_wait(&bars->g_full[s], g & 1);
+                    if (r == 0 && s == 0) BW2_TRACE(16);
+                    const int b0 = (s & 1) * 64 + (s >> 1) * 32 + 8 * r;
+                    const unsigned char *rows = slab + s * BW_SLAB + 8 * r * 512 + 16 * lane;
+                    if (t > 0) {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const float4 f = *reinterpret_cast<const float4 *>(rows + k * 512);
+                            const int sy = P.srow[b0 + k];
+                            // unconditional: a dead (row, step) pair holds an all-zero gamma row (zero stash row)
+                            red_add_v4_nc(tab0 + (sy & SROW_MASK), f.x, f.y, f.z, f.w);
+                            if (sy & SROW_LAST) red_add_v4_nc(r_last, f.x, f.y, f.z, f.w);
+                        }
+                    } else {
+                        // t = 0: pi_new = smooth1d(gamma[0]) per sequence (util.py:56-60); the smoothed row counts for pi AND
+                        // for the emission numerators (the reference overwrites gamma[0] in place, discrete_hmm.py:132)
+#pragma unroll 1
+                        for (int k = 0; k < 8; k++) {
+                            const float4 f = *reinterpret_cast<const float4 *>(rows + k * 512);
+                            const int sy = P.srow[b0 + k];
+                            const bool live = sy >= 0;
+                            int cnt = (f.x < 1e-10f) + (f.y < 1e-10f) + (f.z < 1e-10f) + (f.w < 1e-10f);
+                            cnt = __reduce_add_sync(0xffffffffu, cnt);
+                            if (cnt >= BW_N) {
+                                if (live && lane == 0) atomicAdd(out.flags, 1.0);
+                                cnt = BW_N - 1;
+                            }
+                            const float sub = (float)((double)cnt * 1e-10 / (double)(BW_N - cnt));
+                            const float floorv = 1e-10f;
+                            const float x0 = fmaxf(f.x - sub, floorv), x1 = fmaxf(f.y - sub, floorv),
+                                        x2 = fmaxf(f.z - sub, floorv), x3 = fmaxf(f.w - sub, floorv);
+                            const float inv = 1.0f / warp_sum((x0 + x1) + (x2 + x3));
+                            if (live) {
+                                red_add_v4_nc(tab0 + (sy & SROW_MASK), x0 * inv, x1 * inv, x2 * inv, x3 * inv);
+                                red_add_v4_nc(r_pi, x0 * inv, x1 * inv, x2 * inv, x3 * inv);
+                                if (sy & SROW_LAST) red_add_v4_nc(r_last, x0 * inv, x1 * inv, x2 * inv, x3 * inv);
+                            }
+                        }
+                    }
+                    fence_proxy_async();       // the slab is refilled through the async proxy (TMA gather)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->s_empty[s]);
+                    if (r == 0 && s == 3) BW2_TRACE(17);
+                }
+                if (lane == 0) mbar_arrive(&bars->prep_empty[buf]);
+            }
+    } else {
+        // ------------------------------------------------ compute warps: thread = state i, 64 sequences (half h)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+        const int q = warp & 3, h = warp >> 2;
+        const int i = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        // byte offset of element (b, i) inside a tile:
+        //   K-major SWIZZLE_128B (sVk):        b * 128 + (kbase ^ ((b & 7) << 4))     16-byte chunk (lane / 4) ^ (b & 7)
+        //   MN-major 32-byte atoms (sW):       b * 128 + (mbase ^ ((b & 3) << 5))     32-byte chunk (lane / 8) ^ (b & 3)
+        const uint32_t kbase = q * BW_SUB + ((lane >> 2) << 4) + ((lane & 3) << 2);
+        const uint32_t mbase = q * BW_SUB + ((lane >> 3) << 5) + ((lane & 7) << 2);
+        unsigned char *vk_h = sVk + 64 * h * 128;
+        const unsigned char *w_h = sW + 64 * h * 128;
+        if (h == 0) {
+            // the (tf32-rounded) transition matrix: row i -> TMEM lane i, resident for the whole kernel
+#pragma unroll 1
+            for (int c0 = 0; c0 < BW_N; c0 += 32) {
+                uint32_t a[32];
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    float4 f = ldg4(Ar + (size_t)i * BW_N + c0 + 4 * p);
+                    a[4 * p] = __float_as_uint(f.x); a[4 * p + 1] = __float_as_uint(f.y);
+                    a[4 * p + 2] = __float_as_uint(f.z); a[4 * p + 3] = __float_as_uint(f.w);
+                }
+                tmem_st_32x32(tmem + lane_base + C2_A + c0, a);
+            }
+            tmem_st_wait();
+        }
+        tc_fence_before();
+        uint32_t nd = 0, nm = 0, g = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int t = Ti - 1; t >= 0; t--, g++) {
+                const bool has_mma = (t <= Ti - 2);            // MMA1(t) / MMA2(t) exist
+                const int buf = g & 1;
+                const Bwd2Prep &P = prep[buf];
+                // W_t -> registers (64 values: this state, this half's sequences), then the tile goes back to the TMA producer.
+                // (Waiting for MMA1 first, so that these reads do not share the shared-memory port with its operand fetch,
+                // was measured slower: 9,300 against 8,300 cycles per step.)
+                mbar_wait(&bars->w_full, g & 1);
+                if (warp == 0) BW2_TRACE(8);
+                float gam[64];
+#pragma unroll
+                for (int k = 0; k < 64; k++) gam[k] = *reinterpret_cast<const float *>(w_h + k * 128 + (mbase ^ ((k & 3) << 5)));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->w_empty);
+                if (!has_mma && threadIdx.x == 0) mbar_arrive(&bars->w_empty);   // t = T-1: in place of MMA2's commit
+                mbar_wait(&bars->prep_full[buf], (g >> 1) & 1);
+                uint32_t d0[32], d1[32];
+                if (has_mma) {
+                    mbar_wait(&bars->d1_full, nd & 1);
+                    nd++;
+                    tc_fence_after();
+                    tmem_ld_32x32(tmem + lane_base + C2_D1 + 64 * h, d0);
+                    tmem_ld_32x32(tmem + lane_base + C2_D1 + 64 * h + 32, d1);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) d0[k] = d1[k] = 0u;      // t = T-1: beta = 0 * 0 + 1
+                }
+                if (warp == 0) BW2_TRACE(10);
+                const uint32_t mpar = nm & 1;
+                if (has_mma) nm++;
+                // one chunk = 32 sequences = one slab: emission rows in, gamma_ref rows out; V -> shared memory, V2 -> TMEM
+                auto chunk = [&](auto cc, uint32_t (&d)[32]) {
+                    constexpr int c = decltype(cc)::value;
+                    const int s = 2 * c + h;
+                    const int b0 = 64 * h + 32 * c;
+                    float *srows = reinterpret_cast<float *>(slab + s * BW_SLAB) + i;
+                    mbar_wait(&bars->e_full[s], g & 1);
+                    if (c == 0 && warp == 0) BW2_TRACE(13);
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; k4++) {
+                        const float4 m4 = *reinterpret_cast<const float4 *>(P.mulb + b0 + 4 * k4);
+                        const float4 r4 = *reinterpret_cast<const float4 *>(P.rcm1 + b0 + 4 * k4);
+                        const float mu4[4] = {m4.x, m4.y, m4.z, m4.w};
+                        const float rc4[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            const int k = 4 * k4 + kk;
+                            const float e = srows[k * BW_N];
+                            // beta = D1 / c_{t+1}, or 1 where mulb = 0 (the sequence's last step, its padding)
+                            const float beta = fmaf(__uint_as_float(d[k]), mu4[kk], mu4[kk] == 0.f ? 1.f : 0.f);
+                            srows[k * BW_N] = gam[32 * c + k] * beta;       // gamma_ref: 0 for dead (row, step) pairs
+                            const float v = e * beta;
+                            *reinterpret_cast<uint32_t *>(vk_h + (32 * c + k) * 128 + (kbase ^ ((k & 7) << 4))) = tf32_bits(v);
+                            d[k] = tf32_bits(v * rc4[kk]);
+                        }
+                    }
+                    mbar_arrive(&bars->g_full[s]);                 // the reduction warps may take the slab
+                };
+                if (has_mma) tmem_ld_wait();
+                chunk(std::integral_constant<int, 0>{}, d0);
+                if (warp == 0) BW2_TRACE(11);
+                chunk(std::integral_constant<int, 1>{}, d1);
+                if (t > 0) {
+                    // MMA2(t) reads the V2^T columns until its groups commit (long done by now: it started with this step's
+                    // compute); then this step's V2^T goes in
+                    if (has_mma) {
+                        mbar_wait(&bars->mma2_q[h], mpar);
+                        mbar_wait(&bars->mma2_q[2 + h], mpar);
+                    }
+                    if (warp == 0) BW2_TRACE(15);
+                    tc_fence_after();
+                    tmem_st_32x32(tmem + lane_base + C2_V2T + 64 * h, d0);
+                    tmem_st_32x32(tmem + lane_base + C2_V2T + 64 * h + 32, d1);
+                    tmem_st_wait();
+                    fence_proxy_async();          // V is read by the tensor core through the async proxy
+                    tc_fence_before();
+                    mbar_arrive(&bars->v_ready);
+                    if (warp == 0) BW2_TRACE(12);
+                } else if (Ti > 1) {
+                    mbar_wait(&bars->mma2_q[3], mpar);            // MMA2(0): the tile's Xi is complete
+                    tc_fence_after();
+                    if (h == 0) {
+                        // Xi^T[j][i'] (lane = j = this thread's state) -> float64 counts xi[i'][j]: coalesced over j
+#pragma unroll 1
+                        for (int c0 = 0; c0 < BW_N; c0 += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(tmem + lane_base + C2_XI + c0, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int x = 0; x < 32; x++)
+                                atomicAdd(out.xi + (c0 + x) * BW_N + i, (double)__uint_as_float(v[x]));
+                        }
+                        tc_fence_before();
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->prep_empty[buf]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
 // Fold the fp32 table replicas into the float64 count buffer:
 //   emis_num[k][i] += sum_r tab[r][k][i];  emis_den[i] += sum_k (that);  pi[i] += row M;
 //   gam[i] += emis_den part - row M+1 (gamma_ref summed over t < T-1);  loglik, nseq.
@@ -806,6 +1225,21 @@ struct BwWorkspace {
     size_t bytes;
 };
 
+// Which backward kernel: 1 = thread-per-sequence kernel (bw_backward_tc_kernel, the default), 2 = the transposed
+// thread-per-state kernel (bw_backward_tc2_kernel).  Both produce the same statistics and run within 3 % of each other at
+// config-4 size (17.0-17.7 against 17.2-17.5 ms; DESIGN.md 3.5 has the resource budgets that bound both), so the older,
+// longer-tested one stays the default; $KHMM_BW_BACKWARD=2 or khmm_debug_bw_backward_version(2) selects the other.
+static int g_bw_backward_override = 0;   // khmm_debug_bw_backward_version
+static int bw_backward_version() {
+    static int v = -1;
+    if (g_bw_backward_override) return g_bw_backward_override;
+    if (v < 0) {
+        const char *e = getenv("KHMM_BW_BACKWARD");
+        v = (e && e[0] == '2') ? 2 : 1;
+    }
+    return v;
+}
+
 static BwWorkspace bw_layout(void *ws, int64_t B, int64_t T, int M) {
     auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
     BwWorkspace w;
@@ -849,6 +1283,12 @@ extern "C" {
 // development hook: device buffer of 2*8*32 int64 for the backward + forward timelines (NULL disarms it)
 int khmm_debug_bw_trace(int64_t *dev_buf) {
     g_bw_trace = (long long *)dev_buf;
+    return KHMM_OK;
+}
+
+int khmm_debug_bw_backward_version(int version) {
+    KHMM_REQUIRE(version >= 0 && version <= 2, "debug_bw_backward_version: 0 (default), 1 or 2");
+    g_bw_backward_override = version;
     return KHMM_OK;
 }
 
@@ -958,8 +1398,40 @@ int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const 
         double *c_xi = counts + BW_N;
         double *c_tail = counts + BW_N + (size_t)BW_N * BW_N + BW_N + (size_t)M * BW_N + BW_N;
         BwdOut out{g_bw_trace, w.tab, c_xi, c_tail + 2};
-        bw_backward_tc_kernel<<<grid, 384, smem, st>>>(mapA, mapStash, Bsm, ob, B, T, w.scale, out);
-        KHMM_LAUNCH_CHECK("bw_backward_tc_kernel");
+        if (bw_backward_version() == 1) {
+            bw_backward_tc_kernel<<<grid, 384, smem, st>>>(mapA, mapStash, Bsm, ob, B, T, w.scale, out);
+            KHMM_LAUNCH_CHECK("bw_backward_tc_kernel");
+        } else {
+            KHMM_REQUIRE(M <= (1 << 22), "estep_tc: alphabet size %d exceeds 2^22", M);
+            // emission table rows for the TMA gather: [M][128] fp32, box = one full row (gather4 takes 4 row indices)
+            CUtensorMap mapB;
+            {
+                static PFN_encodeTiled encode = nullptr;
+                if (!encode) {
+                    void *fn = nullptr;
+                    cudaDriverEntryPointQueryResult q;
+                    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+                        set_error("estep_tc: cuTensorMapEncodeTiled is unavailable");
+                        return KHMM_ERR_CUDA;
+                    }
+                    encode = (PFN_encodeTiled)fn;
+                }
+                cuuint64_t dims[2] = {(cuuint64_t)BW_N, (cuuint64_t)M};
+                cuuint64_t strides[1] = {(cuuint64_t)BW_N * 4};
+                cuuint32_t box[2] = {(cuuint32_t)BW_N, 1};
+                cuuint32_t estr[2] = {1, 1};
+                if (encode(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)Bsm, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+                    set_error("estep_tc: tensor map creation for the emission table failed (is Bsm 16-byte aligned?)");
+                    return KHMM_ERR_CUDA;
+                }
+            }
+            size_t smem2 = 2 * (size_t)BW_TILE + 4 * (size_t)BW_SLAB + 2 * sizeof(Bwd2Prep) + sizeof(Bwd2Bars) + 1024;
+            KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_backward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            bw_backward_tc2_kernel<<<grid, 512, smem2, st>>>(mapStash, mapB, w.Ar, ob, B, T, w.scale, out);
+            KHMM_LAUNCH_CHECK("bw_backward_tc2_kernel");
+        }
         if (tev) KHMM_CUDA_CHECK(cudaEventRecord(tev[2], st));
     }
     bw_fold_kernel<<<64, 128, 0, st>>>(w.tab, M, counts, w.loglik, B);

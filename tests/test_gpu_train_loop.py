@@ -151,3 +151,42 @@ def test_comm_entry_points_single_rank(K):
     with pytest.raises(_lib.KhmmError):
         _lib.call("khmm_comm_init_rank", ctypes.create_string_buffer(128), 3, 2, 0, ctypes.byref(ctypes.c_void_p()))
     assert L.khmm_comm_destroy(None) == 0
+
+
+# ------------------------------------------------------- the two backward kernels of the fused E-step
+@pytest.mark.parametrize("M,B,T,ragged", [(16, 128, 1, False), (16, 128, 2, False), (16, 130, 8, False), (48, 300, 33, True),
+                                          (1024, 1000, 20, False), (24, 700, 64, True)])
+def test_transposed_backward_kernel_matches_the_default_one(K, M, B, T, ragged):
+    """bw_backward_tc2_kernel (thread = state, TMA-gathered emission rows, dedicated reduction warps) against
+    bw_backward_tc_kernel (thread = sequence) and the float64 oracle: same statistics on equal-length and ragged
+    batches, partial tiles, T = 1 and T = 2."""
+    from kerehmm_b200 import _lib, engine
+    N = 128
+    h, (pi, A, Bm) = random_discrete(K, N, M, seed=N + M + B + T)
+    rng = np.random.default_rng(B * T)
+    obs = rng.integers(0, M, size=(B, T))
+    lengths = rng.integers(1, T + 1, size=B) if ragged else None
+    ob = engine.prepare_obs(obs, symbols=True, lengths=lengths, alphabet=M)
+    p = h._params()
+    try:
+        _lib.call("khmm_debug_bw_backward_version", 1)
+        c1 = engine.estep_discrete_tc(p, ob).host()
+        _lib.call("khmm_debug_bw_backward_version", 2)
+        c2 = engine.estep_discrete_tc(p, ob).host()
+    finally:
+        _lib.call("khmm_debug_bw_backward_version", 0)
+    if lengths is None:
+        st = O.batch_stats_discrete(pi, A, Bm, obs)
+    else:
+        st = None
+        for b in range(B):
+            s1 = O.batch_stats_discrete(pi, A, Bm, obs[b:b + 1, :lengths[b]])
+            st = s1 if st is None else {k: st[k] + s1[k] for k in st}
+    assert c2["nseq"] == B and c2["flags"] == 0 and c2["loglik"] == c1["loglik"]
+    for key in ("pi", "emis_num", "emis_den"):
+        np.testing.assert_allclose(c2[key], c1[key], rtol=2e-5, atol=1e-6 * np.abs(c1[key]).max(), err_msg=key)
+        np.testing.assert_allclose(c2[key], st[key], rtol=5e-4, atol=1e-6 * np.abs(st[key]).max(), err_msg=key)
+    if T > 1:
+        np.testing.assert_allclose(c2["gam"], c1["gam"], rtol=2e-5, atol=1e-5 * np.abs(c1["gam"]).max())
+        np.testing.assert_allclose(c2["xi_raw"], c1["xi_raw"], rtol=1e-3, atol=1e-6 * c1["xi_raw"].max())
+        np.testing.assert_allclose(c2["xi_raw"] * A, st["xi"], rtol=1e-3, atol=1e-6 * st["xi"].max())
