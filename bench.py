@@ -277,15 +277,18 @@ def setup_c4(ctx, args):
         kdist.init_comm()
         w.nccl_ranks = kdist.comm_info()[2]
 
+    tc = {"default": True, "bf16x3": "bf16x3", "tf32": "tf32"}[args.precision]
+    prec_name = "bf16x3" if args.precision == "default" else args.precision
+
     def step(i):
-        trainer.step(ob, tensor_cores=True)
+        trainer.step(ob, tensor_cores=tc)
 
     # the class API takes a NumPy uint16 array; this one is a view of the page-locked copy (torch has no first-class uint16)
     host_np = w.host_input.numpy().view(np.uint16)
 
     def e2e_step(i):
         # public class API: host array in, one Baum-Welch iteration, re-estimated host parameters out
-        w.model.train_batch(host_np, iterations=1, tensor_cores=True)
+        w.model.train_batch(host_np, iterations=1, tensor_cores=tc)
         return w.model.transitionMatrix
 
     w.step, w.e2e_step = step, e2e_step
@@ -295,7 +298,8 @@ def setup_c4(ctx, args):
     w.h2d, w.d2h = B * T * 2, (N + N * N + N * M) * 8 + 8 + 8
     w.dominant = "bw_backward_tc_kernel (tcgen05, xi in TMEM, L2 count reductions)"
     w.l2_note = "forward stash of B*T*512 B per step (34 GB at B=131072, >> 126 MB L2): nothing survives between steps"
-    w.dtype = "tf32 multiply / f32 accumulate (float64 counts and M-step)"
+    w.dtype = ("split bf16 operands (hi + lo, 3 MMAs) / f32 accumulate" if prec_name == "bf16x3" else
+               "tf32 multiply / f32 accumulate") + " (float64 counts and M-step)"
     w.sharding = "sequences sharded across ranks, one count all-reduce per iteration (libkhmm communicator over NCCL)"
     w.scaling = "weak"
 
@@ -316,6 +320,18 @@ def setup_c4(ctx, args):
         # dram__bytes_read.sum + dram__bytes_write.sum of one backward launch (ncu --set full at B=18944, scaled to
         # this batch; profiles/): traffic ~ algorithmic bytes
         traffic = (5.037033e9 + 0.004398e9) * (B * T) / (18944.0 * 512.0)
+        # the other operand precision, 5 iterations of the same loop (secondary record)
+        other = "tf32" if prec_name == "bf16x3" else "bf16x3"
+        import torch as _t
+        for _ in range(2):
+            trainer.step(ob, tensor_cores=other)
+        e0, e1 = _t.cuda.Event(enable_timing=True), _t.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            trainer.step(ob, tensor_cores=other)
+        e1.record()
+        _t.cuda.synchronize()
+        other_ms = e0.elapsed_time(e1) / 5
         return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "traffic": traffic, "kernel": w.dominant, "peak_source": pk["hbm_source"],
                 "algorithmic_bytes_per_launch": bwd_bytes, "kernel_ms": bwd_ms,
@@ -330,8 +346,11 @@ def setup_c4(ctx, args):
                 "tensor": {"achieved_tflops": 4.0 * B * T * N * N / (bwd_ms * 1e-3) / 1e12,
                            "peak_tflops": pk["tf32_tflops"], "peak_source": pk["tf32_source"],
                            "note": "secondary roof: MMA1 + MMA2 of the backward kernel counted as 4 flop per transition"},
+                "operand_precision": {"this_run": prec_name, "other": other, "other_ms_per_step": other_ms,
+                                      "note": "bf16x3 (the API default): re-estimated pi/A/B within 1e-6/2e-6/1e-5 of the float64 "
+                                              "oracle at 4,096 sequences; tf32: 6e-5/7e-5/4e-4 (tests/test_gpu_train_loop.py)"},
                 "note": "binding roof = HBM (the stash is the only operand that does not fit on chip); the kernel is "
-                        "held below it by L2 count reductions sharing the LSU path (DESIGN.md 3.5)"}
+                        "held below it by the shared-memory port (512 KB per tile-step) and L2 count reductions (DESIGN.md 3.5)"}
 
     w.roofline = roofline
     w.trainer = trainer
@@ -830,6 +849,8 @@ def main():
     ap.add_argument("--operands", default="bf16", choices=["tf32", "bf16"],
                     help="c5: tensor-core operand precision (bf16: log-likelihoods within 7e-6 of float64 at c5's T=1024, "
                          "measured; tf32: 9e-7)")
+    ap.add_argument("--precision", default="default", choices=["default", "bf16x3", "tf32"],
+                    help="c4: operand precision of the fused tensor-core E-step (default = the API default, bf16x3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-cores", type=int, default=os.cpu_count() or 1)
     args = ap.parse_args()

@@ -296,6 +296,21 @@ int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const 
                                       void *workspace, size_t workspace_bytes, double *counts, float *alpha_out,
                                       float *scale_out, khmm_stream_t stream);
 
+/* The same with a choice of operand precision for the recursion's contraction (alpha_{t-1} A and A (b . beta_{t+1})):
+ *   KHMM_TC_TF32    one tf32 MMA (10-bit mantissa).  The rounding of A itself is a fixed perturbation of the model and
+ *                   leaves a systematic 1e-5 (median) ... 1e-4 (worst entry) relative error in the counts.
+ *   KHMM_TC_BF16X3  split operands: x = hi + lo with hi = bf16(x), lo = bf16(x - hi), three bf16 MMAs
+ *                   (hi hi + hi lo + lo hi) into the same fp32 accumulator: 2^-17 operand precision in the same 64 KB
+ *                   of shared memory, 1.5 x the tensor time of the contraction.  Counts and re-estimated parameters
+ *                   then agree with the float64 reference to float32 accuracy (tests state the bound).
+ * The accumulation of zi (the second contraction) stays tf32 in both modes: its per-term rounding errors are unbiased
+ * and average out over the B*T rows it sums. */
+#define KHMM_TC_BF16X3 2
+int khmm_estep_tc_discrete_ex_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *AT,
+                                  const float *Bsm, const void *obs, int obs_dtype, const int32_t *lengths,
+                                  void *workspace, size_t workspace_bytes, double *counts, float *alpha_out,
+                                  float *scale_out, int operand_precision, khmm_stream_t stream);
+
 /* Measurement hook (bench.py's roofline): khmm_estep_tc_timing(1) arms CUDA events on the launching stream around the
  * forward and the backward kernel of every following khmm_estep_tc_* call (per device, a ring of the last 64 calls;
  * nothing is created or recorded while disarmed).  khmm_estep_tc_kernel_ms(k, ...) returns the durations of the call

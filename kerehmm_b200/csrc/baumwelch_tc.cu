@@ -68,6 +68,17 @@ static __global__ void bw_round_matrix_kernel(const float *__restrict__ in, floa
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) out[k] = bw_round_tf32(in[k]);
 }
 
+// bf16 hi/lo split of a matrix for the split-operand mode: hi = bf16(x), lo = bf16(x - hi)
+static __global__ void bw_split_matrix_kernel(const float *__restrict__ in, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo,
+                                              int n) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        uint32_t h, l;
+        split_bf16x2(in[k], 0.f, h, l);
+        hi[k] = (uint16_t)(h & 0xffffu);
+        lo[k] = (uint16_t)(l & 0xffffu);
+    }
+}
+
 struct BwObs {
     const void *obs;
     int dtype, M;
@@ -133,10 +144,21 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // Warps: 0-7 epilogue (thread = sequence = TMEM lane; warps 0-3 own columns 0-63, warps 4-7 columns 64-127 of
 // the same rows, the two halves of a row sum meet in shared memory), 8 MMA issuer + TMEM allocator, 9-10 gather,
 // 11 storer.
+// SPLIT: the recursion's MMA takes bf16 hi/lo operand pairs (kind::f16) instead of tf32 -- W_hi, W_lo in TMEM (two
+// values per column), A^T_hi, A^T_lo in the same 64 KB of shared memory -- and adds the three products W_hi A_hi +
+// W_hi A_lo + W_lo A_hi (2^-17 operand precision against tf32's 2^-11, 1.5 x the tensor time): the rounding of the
+// transition matrix, which tf32 leaves as a SYSTEMATIC 1e-5 ... 1e-4 error in the counts, drops below 2e-6.
+template <int PREC>
 __global__ void __launch_bounds__(384, 1)
-bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_constant__ CUtensorMap mapStashSt,
+bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_constant__ CUtensorMap mapATlo,
+                     const __grid_constant__ CUtensorMap mapStashSt,
                      const float *__restrict__ pi, const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T,
                      float *__restrict__ scale, double *__restrict__ loglik, long long *trace) {
+    constexpr bool SPLIT = PREC != KHMM_TC_TF32;
+    // (Dropping the W_lo A_hi product -- two MMAs, the recursion vector rounded to bf16 -- was measured: the aggregate
+    // counts stay within 6e-6 but single emission counts scatter by up to 4e-3 at 4,096 sequences, and the kernels are
+    // no faster than with tf32 operands; not kept.)
+    constexpr int NPASS = 3;
 #define FW_TRACE(ev)                                                                                      \
     do {                                                                                                  \
         if (trace && blockIdx.x == 0 && tile == blockIdx.x && t >= 8 && t < 16 && (threadIdx.x & 31) == 0) \
@@ -174,9 +196,18 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
         if (elect_one()) {
             tma_prefetch_desc(&mapAT);
             mbar_arrive_expect_tx(&bars->mat_full, BW_TILE);
-            for (int kb = 0; kb < 4; kb++) tma_load_2d(tiles + kb * BW_SUB, &mapAT, &bars->mat_full, kb * 32, 0);
+            if (SPLIT) {
+                // A^T_hi | A^T_lo: bf16 [128][128] each, two sub-tiles of [128 rows][64 K elements = 128 B]
+                tma_prefetch_desc(&mapATlo);
+                for (int kb = 0; kb < 2; kb++) {
+                    tma_load_2d(tiles + kb * BW_SUB, &mapAT, &bars->mat_full, kb * 64, 0);
+                    tma_load_2d(tiles + 2 * BW_SUB + kb * BW_SUB, &mapATlo, &bars->mat_full, kb * 64, 0);
+                }
+            } else {
+                for (int kb = 0; kb < 4; kb++) tma_load_2d(tiles + kb * BW_SUB, &mapAT, &bars->mat_full, kb * 32, 0);
+            }
             mbar_wait(&bars->mat_full, 0);
-            const uint32_t idesc = make_idesc_tf32(128, 128);
+            const uint32_t idesc = SPLIT ? make_idesc_bf16(128, 128) : make_idesc_tf32(128, 128);
             uint32_t na = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
                 for (int64_t t = 1; t < T; t++) {
@@ -184,10 +215,24 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                     na++;
                     FW_TRACE(0);
                     tc_fence_after();
+                    if (SPLIT) {
+                        // (W_hi, A_hi), (W_hi, A_lo), (W_lo, A_hi): W_hi in TMEM columns [128,192), W_lo in [192,256)
 #pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        uint64_t db = make_kmajor_sw128_desc(tiles + (k >> 2) * BW_SUB);
-                        mma_tf32_ts(tmem, tmem + 128 + k * 8, desc_advance(db, (k & 3) * 32), idesc, k != 0);
+                        for (int pass = 0; pass < NPASS; pass++) {
+                            const uint32_t acol = tmem + 128 + (pass == 2 ? 64 : 0);
+                            const unsigned char *bt = tiles + (pass == 1 ? 2 * BW_SUB : 0);
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                uint64_t db = make_kmajor_sw128_desc(bt + (k >> 2) * BW_SUB);
+                                mma_bf16_ts(tmem, acol + k * 8, desc_advance(db, (k & 3) * 32), idesc, (pass | k) != 0);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            uint64_t db = make_kmajor_sw128_desc(tiles + (k >> 2) * BW_SUB);
+                            mma_tf32_ts(tmem, tmem + 128 + k * 8, desc_advance(db, (k & 3) * 32), idesc, k != 0);
+                        }
                     }
                     tc_commit(&bars->d_full);
                     FW_TRACE(1);
@@ -297,9 +342,20 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                         float v = __uint_as_float(acc[q]) * r * e[q];
                         rowsum += v;
                         e[q] = t < len_b ? v : 0.f;   // rows past the batch / steps past the sequence: zeros in the stash
-                        w[q] = tf32_bits(v);
+                        w[q] = SPLIT ? __float_as_uint(v) : tf32_bits(v);
                     }
-                    if (t + 1 < T) tmem_st_32x32(tmem + lane_base + 128 + c0, w);
+                    if (SPLIT) {
+                        if (t + 1 < T) {
+                            uint32_t hi[16], lo[16];
+#pragma unroll
+                            for (int m = 0; m < 16; m++)
+                                split_bf16x2(__uint_as_float(w[2 * m]), __uint_as_float(w[2 * m + 1]), hi[m], lo[m]);
+                            tmem_st_32x16(tmem + lane_base + 128 + c0 / 2, hi);
+                            if (NPASS == 3) tmem_st_32x16(tmem + lane_base + 192 + c0 / 2, lo);
+                        }
+                    } else if (t + 1 < T) {
+                        tmem_st_32x32(tmem + lane_base + 128 + c0, w);
+                    }
 #pragma unroll
                     for (int q = 0; q < 8; q++)
                         *reinterpret_cast<float4 *>(erow + ((q ^ sw7) << 4)) = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
@@ -367,10 +423,16 @@ struct BwdOut {
 // Warp roles (384 threads): warps 0-3 epilogue (setmaxnreg.inc 232), warps 4-7 count reductions (168),
 // warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator, warps 10-11 idle (96): three warps share one
 // SM sub-partition (16K registers), so the register file is re-split by role.
+// SPLIT: MMA1 on bf16 hi/lo pairs like the forward kernel (V_hi, V_lo in TMEM, A_hi, A_lo in shared memory); MMA2 stays tf32
+// (its rounding errors are unbiased and average out over the B*T rows it sums).
+template <int PREC>
 __global__ void __launch_bounds__(384, 1)
-bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapStash,
+bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+                      const __grid_constant__ CUtensorMap mapStash,
                       const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T, const float *__restrict__ scale,
                       BwdOut out) {
+    constexpr bool SPLIT = PREC != KHMM_TC_TF32;
+    constexpr int NPASS = 3;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sA = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // A, K-major SW128
     unsigned char *sW = sA + BW_TILE;      // W_t tile, MN-major (TMA, SWIZZLE_128B_ATOM_32B)
@@ -440,7 +502,15 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             tma_prefetch_desc(&mapA);
             tma_prefetch_desc(&mapStash);
             mbar_arrive_expect_tx(&bars->mat_full, BW_TILE);
-            for (int kb = 0; kb < 4; kb++) tma_load_2d(sA + kb * BW_SUB, &mapA, &bars->mat_full, kb * 32, 0);
+            if (SPLIT) {
+                tma_prefetch_desc(&mapAlo);
+                for (int kb = 0; kb < 2; kb++) {
+                    tma_load_2d(sA + kb * BW_SUB, &mapA, &bars->mat_full, kb * 64, 0);
+                    tma_load_2d(sA + 2 * BW_SUB + kb * BW_SUB, &mapAlo, &bars->mat_full, kb * 64, 0);
+                }
+            } else {
+                for (int kb = 0; kb < 4; kb++) tma_load_2d(sA + kb * BW_SUB, &mapA, &bars->mat_full, kb * 32, 0);
+            }
             uint32_t np = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
                 for (int64_t t = T - 1; t >= 0; t--) {
@@ -457,7 +527,7 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         if (elect_one()) {
             mbar_wait(&bars->mat_full, 0);
-            const uint32_t idesc_k = make_idesc_tf32(128, 128);
+            const uint32_t idesc_k = SPLIT ? make_idesc_bf16(128, 128) : make_idesc_tf32(128, 128);
             const uint32_t idesc_mn = make_idesc_tf32(128, 128, true, true);
             const uint64_t dW = make_mnmajor_sw128a32_desc(sW, BW_SUB, 512);
             const uint64_t dV = make_mnmajor_sw128a32_desc(sV, BW_SUB, 512);
@@ -469,10 +539,24 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                     nv++;
                     BW_TRACE(4);
                     tc_fence_after();
+                    if (SPLIT) {
+                        // (V_hi, A_hi), (V_hi, A_lo), (V_lo, A_hi): V_hi in TMEM columns [COL_V, +64), V_lo in [COL_V+64, +128)
 #pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        uint64_t db = make_kmajor_sw128_desc(sA + (k >> 2) * BW_SUB);
-                        mma_tf32_ts(tmem + COL_D1, tmem + COL_V + k * 8, desc_advance(db, (k & 3) * 32), idesc_k, k != 0);
+                        for (int pass = 0; pass < NPASS; pass++) {
+                            const uint32_t acol = tmem + COL_V + (pass == 2 ? 64 : 0);
+                            const unsigned char *bt = sA + (pass == 1 ? 2 * BW_SUB : 0);
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                uint64_t db = make_kmajor_sw128_desc(bt + (k >> 2) * BW_SUB);
+                                mma_bf16_ts(tmem + COL_D1, acol + k * 8, desc_advance(db, (k & 3) * 32), idesc_k, (pass | k) != 0);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            uint64_t db = make_kmajor_sw128_desc(sA + (k >> 2) * BW_SUB);
+                            mma_tf32_ts(tmem + COL_D1, tmem + COL_V + k * 8, desc_advance(db, (k & 3) * 32), idesc_k, k != 0);
+                        }
                     }
                     tc_commit(&bars->d1_full);
                     BW_TRACE(5);
@@ -603,14 +687,28 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll
                         for (int q = 0; q < 8; q++) {
                             float4 f = *reinterpret_cast<const float4 *>(erow + ((q ^ (row & 7)) << 4));
-                            u[4 * q] = tf32_bits(f.x * beta[4 * q]);
-                            u[4 * q + 1] = tf32_bits(f.y * beta[4 * q + 1]);
-                            u[4 * q + 2] = tf32_bits(f.z * beta[4 * q + 2]);
-                            u[4 * q + 3] = tf32_bits(f.w * beta[4 * q + 3]);
+                            if (SPLIT) {
+                                split_bf16x2(f.x * beta[4 * q], f.y * beta[4 * q + 1], u[2 * q], u[16 + 2 * q]);
+                                split_bf16x2(f.z * beta[4 * q + 2], f.w * beta[4 * q + 3], u[2 * q + 1], u[16 + 2 * q + 1]);
+                            } else {
+                                u[4 * q] = tf32_bits(f.x * beta[4 * q]);
+                                u[4 * q + 1] = tf32_bits(f.y * beta[4 * q + 1]);
+                                u[4 * q + 2] = tf32_bits(f.z * beta[4 * q + 2]);
+                                u[4 * q + 3] = tf32_bits(f.w * beta[4 * q + 3]);
+                            }
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars->e_free[buf]);
-                        tmem_st_32x32(tmem + lane_base + COL_V + c0, u);
+                        if (SPLIT) {
+                            // u[0..15] = hi pairs, u[16..31] = lo pairs of the 32 values of this chunk
+                            uint32_t hi[16], lo[16];
+#pragma unroll
+                            for (int m = 0; m < 16; m++) { hi[m] = u[m]; lo[m] = u[16 + m]; }
+                            tmem_st_32x16(tmem + lane_base + COL_V + c0 / 2, hi);
+                            tmem_st_32x16(tmem + lane_base + COL_V + 64 + c0 / 2, lo);
+                        } else {
+                            tmem_st_32x32(tmem + lane_base + COL_V + c0, u);
+                        }
                     }
                 }
                 // W_t has been read: hand the buffer back to the TMA producer (MMA2 adds its own arrival)
@@ -636,11 +734,23 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll 1
                     for (int c0 = 0; c0 < BW_N; c0 += 32) {
                         uint32_t v[32];
-                        tmem_ld_32x32(tmem + lane_base + COL_V + c0, v);
-                        tmem_ld_wait();
-                        unsigned char *vrow = sV + (c0 >> 5) * BW_SUB + row * 128;
+                        if (SPLIT) {
+                            uint32_t hi[16], lo[16];
+                            tmem_ld_32x16(tmem + lane_base + COL_V + c0 / 2, hi);
+                            tmem_ld_32x16(tmem + lane_base + COL_V + 64 + c0 / 2, lo);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int q = 0; q < 32; q++) v[q] = tf32_bits(__uint_as_float(v[q]) * rcm1);
+                            for (int m = 0; m < 16; m++) {
+                                v[2 * m] = tf32_bits(unsplit_lo(hi[m], lo[m]) * rcm1);
+                                v[2 * m + 1] = tf32_bits(unsplit_hi(hi[m], lo[m]) * rcm1);
+                            }
+                        } else {
+                            tmem_ld_32x32(tmem + lane_base + COL_V + c0, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int q = 0; q < 32; q++) v[q] = tf32_bits(__uint_as_float(v[q]) * rcm1);
+                        }
+                        unsigned char *vrow = sV + (c0 >> 5) * BW_SUB + row * 128;
 #pragma unroll
                         for (int c32 = 0; c32 < 4; c32++) {
                             const int q = c32 * 8;
@@ -1221,6 +1331,7 @@ static BwTiming g_bw_tm[BW_MAX_DEV];
 
 struct BwWorkspace {
     float *stash, *scale, *tab, *Ar, *ATr;
+    uint16_t *Ah, *Al, *ATh, *ATl;    // bf16 hi / lo halves of A and A^T (split-operand mode)
     double *loglik;
     size_t bytes;
 };
@@ -1250,6 +1361,10 @@ static BwWorkspace bw_layout(void *ws, int64_t B, int64_t T, int M) {
     w.tab = (float *)(p + o);    o += up((size_t)BW_REPL * (M + 2) * BW_N * 4);
     w.Ar = (float *)(p + o);     o += up((size_t)BW_N * BW_N * 4);
     w.ATr = (float *)(p + o);    o += up((size_t)BW_N * BW_N * 4);
+    w.Ah = (uint16_t *)(p + o);  o += up((size_t)BW_N * BW_N * 2);
+    w.Al = (uint16_t *)(p + o);  o += up((size_t)BW_N * BW_N * 2);
+    w.ATh = (uint16_t *)(p + o); o += up((size_t)BW_N * BW_N * 2);
+    w.ATl = (uint16_t *)(p + o); o += up((size_t)BW_N * BW_N * 2);
     w.loglik = (double *)(p + o); o += up((size_t)B * 8);
     w.bytes = o;
     return w;
@@ -1333,8 +1448,19 @@ int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const 
                                       const float *Bsm, const void *obs, int obs_dtype, const int32_t *lengths,
                                       void *workspace, size_t workspace_bytes, double *counts, float *alpha_out,
                                       float *scale_out, khmm_stream_t stream) {
+    return khmm_estep_tc_discrete_ex_f32(B, T, N, M, pi, A, AT, Bsm, obs, obs_dtype, lengths, workspace, workspace_bytes,
+                                         counts, alpha_out, scale_out, KHMM_TC_TF32, stream);
+}
+
+int khmm_estep_tc_discrete_ex_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *AT,
+                                  const float *Bsm, const void *obs, int obs_dtype, const int32_t *lengths,
+                                  void *workspace, size_t workspace_bytes, double *counts, float *alpha_out,
+                                  float *scale_out, int operand_precision, khmm_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     KHMM_REQUIRE(B >= 0 && T >= 1 && M >= 1, "estep_tc: bad shape");
+    KHMM_REQUIRE(operand_precision == KHMM_TC_TF32 || operand_precision == KHMM_TC_BF16X3,
+                 "estep_tc: operand_precision must be KHMM_TC_TF32 or KHMM_TC_BF16X3");
+    const bool split = operand_precision != KHMM_TC_TF32;
     if (N != BW_N) {
         set_error("estep_tc: the fused tensor-core E-step covers N = %d (got %d)", BW_N, N);
         return KHMM_ERR_UNSUPPORTED;
@@ -1354,12 +1480,22 @@ int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const 
     if (scale_out) w.scale = scale_out;
     KHMM_REQUIRE(((uintptr_t)w.stash & 15) == 0, "estep_tc: stash must be 16-byte aligned");
 
-    bw_round_matrix_kernel<<<16, 256, 0, st>>>(A, w.Ar, BW_N * BW_N);
-    bw_round_matrix_kernel<<<16, 256, 0, st>>>(AT, w.ATr, BW_N * BW_N);
+    CUtensorMap mapAT, mapATlo, mapA, mapAlo, mapStash, mapStashSt;
+    int maperr;
+    if (split) {
+        bw_split_matrix_kernel<<<16, 256, 0, st>>>(A, w.Ah, w.Al, BW_N * BW_N);
+        bw_split_matrix_kernel<<<16, 256, 0, st>>>(AT, w.ATh, w.ATl, BW_N * BW_N);
+        maperr = make_tmap_bf16_rowmajor(&mapAT, w.ATh, BW_N, BW_N, 128) || make_tmap_bf16_rowmajor(&mapATlo, w.ATl, BW_N, BW_N, 128) ||
+                 make_tmap_bf16_rowmajor(&mapA, w.Ah, BW_N, BW_N, 128) || make_tmap_bf16_rowmajor(&mapAlo, w.Al, BW_N, BW_N, 128);
+    } else {
+        bw_round_matrix_kernel<<<16, 256, 0, st>>>(A, w.Ar, BW_N * BW_N);
+        bw_round_matrix_kernel<<<16, 256, 0, st>>>(AT, w.ATr, BW_N * BW_N);
+        maperr = make_tmap_f32_rowmajor(&mapAT, w.ATr, BW_N, BW_N, 128) || make_tmap_f32_rowmajor(&mapA, w.Ar, BW_N, BW_N, 128);
+        mapATlo = mapAT;
+        mapAlo = mapA;
+    }
     KHMM_CUDA_CHECK(cudaMemsetAsync(w.tab, 0, (size_t)BW_REPL * (M + 2) * BW_N * 4, st));
-    CUtensorMap mapAT, mapA, mapStash, mapStashSt;
-    if (make_tmap_f32_rowmajor(&mapAT, w.ATr, BW_N, BW_N, 128) || make_tmap_f32_rowmajor(&mapA, w.Ar, BW_N, BW_N, 128) ||
-        make_tmap_stash(&mapStash, w.stash, B, T, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+    if (maperr || make_tmap_stash(&mapStash, w.stash, B, T, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
         make_tmap_stash(&mapStashSt, w.stash, B, T, CU_TENSOR_MAP_SWIZZLE_128B)) {
         set_error("estep_tc: tensor map creation failed");
         return KHMM_ERR_CUDA;
@@ -1370,7 +1506,8 @@ int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const 
     cudaEvent_t *tev = nullptr;   // timing events of this call (armed by khmm_estep_tc_timing)
     {
         size_t smem = BW_TILE + 2 * (size_t)FW_EBUF + 6 * 128 * sizeof(float) + sizeof(FwdBars) + 1024;
-        KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc_kernel<KHMM_TC_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc_kernel<KHMM_TC_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = (int)(ntiles < sms ? ntiles : sms);
         if (g_bw_timing) {
             int dev = 0;
@@ -1387,19 +1524,28 @@ int khmm_estep_tc_discrete_ragged_f32(int64_t B, int64_t T, int N, int M, const 
             }
         }
         if (tev) KHMM_CUDA_CHECK(cudaEventRecord(tev[0], st));
-        bw_forward_tc_kernel<<<grid, 384, smem, st>>>(mapAT, mapStashSt, pi, Bsm, ob, B, T, w.scale, w.loglik, g_bw_trace);
+        if (operand_precision == KHMM_TC_BF16X3)
+            bw_forward_tc_kernel<KHMM_TC_BF16X3><<<grid, 384, smem, st>>>(mapAT, mapATlo, mapStashSt, pi, Bsm, ob, B, T, w.scale,
+                                                                          w.loglik, g_bw_trace);
+        else
+            bw_forward_tc_kernel<KHMM_TC_TF32><<<grid, 384, smem, st>>>(mapAT, mapATlo, mapStashSt, pi, Bsm, ob, B, T, w.scale,
+                                                                        w.loglik, g_bw_trace);
         KHMM_LAUNCH_CHECK("bw_forward_tc_kernel");
         if (tev) KHMM_CUDA_CHECK(cudaEventRecord(tev[1], st));
     }
     {
         size_t smem = 3 * (size_t)BW_TILE + 2 * (size_t)BW_ECHUNK + sizeof(BwdBars) + 1024;
-        KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_backward_tc_kernel<KHMM_TC_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_backward_tc_kernel<KHMM_TC_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = (int)(ntiles < sms ? ntiles : sms);
         double *c_xi = counts + BW_N;
         double *c_tail = counts + BW_N + (size_t)BW_N * BW_N + BW_N + (size_t)M * BW_N + BW_N;
         BwdOut out{g_bw_trace, w.tab, c_xi, c_tail + 2};
-        if (bw_backward_version() == 1) {
-            bw_backward_tc_kernel<<<grid, 384, smem, st>>>(mapA, mapStash, Bsm, ob, B, T, w.scale, out);
+        if (operand_precision == KHMM_TC_BF16X3) {
+            bw_backward_tc_kernel<KHMM_TC_BF16X3><<<grid, 384, smem, st>>>(mapA, mapAlo, mapStash, Bsm, ob, B, T, w.scale, out);
+            KHMM_LAUNCH_CHECK("bw_backward_tc_kernel<bf16x3>");
+        } else if (bw_backward_version() == 1) {
+            bw_backward_tc_kernel<KHMM_TC_TF32><<<grid, 384, smem, st>>>(mapA, mapAlo, mapStash, Bsm, ob, B, T, w.scale, out);
             KHMM_LAUNCH_CHECK("bw_backward_tc_kernel");
         } else {
             KHMM_REQUIRE(M <= (1 << 22), "estep_tc: alphabet size %d exceeds 2^22", M);

@@ -415,7 +415,24 @@ def pad_states(p: ModelParams, multiple: int = 128) -> ModelParams:
     return ModelParams(kind="gauss", pi=pi, A=A, mean=mean, sd=sd)
 
 
-TC_TF32, TC_BF16 = 0, 1
+TC_TF32, TC_BF16, TC_BF16X3 = 0, 1, 2
+
+# Operand precision of the fused tensor-core E-step when the caller just says tensor_cores=True / "auto":
+# split bf16 operands (three MMAs, 2^-17) -- counts and re-estimated parameters then agree with the float64
+# reference to float32 accuracy; "tf32" (one MMA, 2^-11, ~8 % faster per iteration) stays available by name.
+ESTEP_TC_DEFAULT_PRECISION = TC_BF16X3
+
+
+def estep_precision(tensor_cores):
+    """tensor_cores argument of the Baum-Welch entry points -> (use the tensor-core path?, operand precision).
+    False | True | "auto" | "tf32" | "bf16x3"."""
+    if tensor_cores in ("tf32",):
+        return True, TC_TF32
+    if tensor_cores in ("bf16x3", "split"):
+        return True, TC_BF16X3
+    if tensor_cores in (True, False, "auto"):
+        return tensor_cores, ESTEP_TC_DEFAULT_PRECISION
+    raise ValueError('tensor_cores must be True, False, "auto", "tf32" or "bf16x3"')
 
 
 def fwdbwd_loglik_tc(p: ModelParams, ob: Obs, both=True, precision=TC_TF32):
@@ -586,12 +603,15 @@ def _pick_counts(big: "Counts", counts: "Counts", n: int):
     return counts
 
 
-def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=None, stash_out=False, operands=None):
+def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=None, stash_out=False, operands=None,
+                      precision=None):
     """Fused tensor-core E-step (khmm_estep_tc_discrete_f32).  With `stash_out` also returns the
     forward stash W[b][t][:] = c_t alpha_t and the scale factors of the LAST chunk (tests).
     `operands`: device-resident float32 operand set at 128 states (pi, A, AT, Bsm attributes -- the training loop's,
     `DiscreteTrainer`); `p` is then only consulted for its shape (N may be < 128: the operands are already padded)."""
     t = require_cuda()
+    if precision is None:
+        precision = ESTEP_TC_DEFAULT_PRECISION
     if p.N < 128:
         # pad to 128 states with unreachable ones (pad_states): their statistics are exactly zero; the real states'
         # counts are then picked out of the 128-state buffer.  (The per-sequence smoothing of gamma_0 floors the padded
@@ -601,9 +621,10 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
         n = p.N
         if operands is not None:
             big = estep_discrete_tc(ModelParams(kind="discrete", pi=np.empty(128), A=np.empty((128, 0)),
-                                                B=np.empty((128, p.M))), ob, chunk=chunk, operands=operands)
+                                                B=np.empty((128, p.M))), ob, chunk=chunk, operands=operands,
+                                    precision=precision)
         else:
-            big = estep_discrete_tc(pad_states(p), ob, chunk=chunk)
+            big = estep_discrete_tc(pad_states(p), ob, chunk=chunk, precision=precision)
         return _pick_counts(big, counts or Counts(n, p.M), n)
     dm = operands if operands is not None else DeviceModel(p, t.float32)
     N, M, dev = p.N, p.M, device()
@@ -632,8 +653,8 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
         nb = min(chunk, ob.B - b0)
         obs_c = ob.tensor[b0:b0 + nb]
         len_c = ob.lengths[b0:b0 + nb] if ob.lengths is not None else None
-        _lib.call("khmm_estep_tc_discrete_ragged_f32", nb, ob.T, N, M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.Bsm),
-                  ptr(obs_c), ob.code, ptr(len_c), wsp, nbytes, ptr(counts.buf), ptr(W), ptr(sc), stream_ptr())
+        _lib.call("khmm_estep_tc_discrete_ex_f32", nb, ob.T, N, M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.Bsm),
+                  ptr(obs_c), ob.code, ptr(len_c), wsp, nbytes, ptr(counts.buf), ptr(W), ptr(sc), int(precision), stream_ptr())
     if stash_out:
         W = W.permute(0, 2, 1, 3).reshape(-1, ob.T, N)[:nb0]     # -> [b][t][:]
         sc = sc.permute(0, 2, 1).reshape(-1, ob.T)[:nb0]
@@ -642,9 +663,10 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
 
 
 def estep_uses_tc(p: ModelParams, ob: Obs, real, tensor_cores="auto") -> bool:
-    if tensor_cores == "auto":
-        tensor_cores = ob.B * ob.T >= TC_AUTO_MIN_ROWS
-    return bool(tensor_cores) and estep_tc_supported(p, ob, real)
+    use, _ = estep_precision(tensor_cores)
+    if use == "auto":
+        use = ob.B * ob.T >= TC_AUTO_MIN_ROWS
+    return bool(use) and estep_tc_supported(p, ob, real)
 
 
 def estep_discrete(p: ModelParams, ob: Obs, real, counts: Counts = None, chunk=None, tensor_cores="auto", operands=None):
@@ -656,7 +678,8 @@ def estep_discrete(p: ModelParams, ob: Obs, real, counts: Counts = None, chunk=N
         raise NotImplementedError("Baum-Welch is defined for discrete emissions "
                                   "(GaussianHMM.do_pass is broken in the reference, SURVEY.md Q9)")
     if estep_uses_tc(p, ob, real, tensor_cores):
-        return estep_discrete_tc(p, ob, counts=counts, chunk=chunk, operands=operands)
+        return estep_discrete_tc(p, ob, counts=counts, chunk=chunk, operands=operands,
+                                 precision=estep_precision(tensor_cores)[1])
     dm = operands if operands is not None else DeviceModel(p, real)
     N, M, dev = p.N, p.M, device()
     counts = counts or Counts(N, M)
@@ -762,7 +785,9 @@ class DiscreteTrainer:
         Np = 128 if use_tc else self.N
         ops = self.operands(Np)
         self.counts.buf.zero_()
-        estep_discrete(self.shape, ob, self.real, counts=self.counts, chunk=chunk, tensor_cores=use_tc, operands=ops)
+        estep_discrete(self.shape, ob, self.real, counts=self.counts, chunk=chunk,
+                       tensor_cores=(tensor_cores if (use_tc and isinstance(tensor_cores, str) and tensor_cores != "auto")
+                                     else use_tc), operands=ops)
         kdist.all_reduce_counts(self.counts.buf, group=group)
         if self.iteration < self.history.numel():
             o = self.counts.sl["tail"].start
