@@ -77,22 +77,81 @@ class AbstractHMM(object):
     def compute_emission_mapping_score(self, to_hmm, mapping):
         raise NotImplementedError("AbstractHMM doesn't define emissions, override this for concrete implementations.")
 
-    def compute_mapping_to(self, to_hmm):
-        """Best state permutation from this HMM onto `to_hmm` (abstract_hmm.py:63-94): brute force
-        over permutations of initial + transition + normalised emission scores.  (The reference's
-        second loop iterates an exhausted generator and never adds the emission scores, and it is
-        py3-broken; this version does what its docstrings describe.  Off the hot path.)"""
-        from itertools import permutations
+    def _emission_pair_costs(self, to_hmm):
+        """(N, N) matrix c[k][m] = emission distance of this model's state m mapped onto `to_hmm`'s state k; the
+        emission mapping score of a permutation is the sum of c[k][mapping[k]].  Concrete classes override."""
+        raise NotImplementedError("AbstractHMM doesn't define emissions, override this for concrete implementations.")
+
+    def mapping_score(self, to_hmm, mapping, emission_total=None):
+        """The objective `compute_mapping_to` minimises (abstract_hmm.py:63-94 as its docstrings describe it): initial +
+        transition score of the permutation plus its emission score divided by the sum of the emission scores of ALL
+        N! permutations -- which has the closed form (N-1)! * sum(c), every (k, m) pair occurring in (N-1)! of them."""
+        from math import lgamma
+        mapping = list(mapping)
+        score = self.compute_initprob_mapping_score(to_hmm, mapping) + self.compute_transition_mapping_score(to_hmm, mapping)
+        emis = self.compute_emission_mapping_score(to_hmm, mapping)
+        if emission_total is None:
+            c = self._emission_pair_costs(to_hmm)
+            emission_total = (np.log(c.sum()) + lgamma(self.nStates)) if c.sum() > 0 else None
+        if emission_total is not None and emis > 0:
+            score += float(np.exp(np.log(emis) - emission_total))
+        return score
+
+    def compute_mapping_to(self, to_hmm, exact_max_states=8):
+        """Best state permutation from this HMM onto `to_hmm` (abstract_hmm.py:63-94): the permutation minimising
+        initial + transition + normalised emission scores.
+
+        The reference enumerates all N! permutations (and is broken at HEAD: its second loop iterates an exhausted
+        generator, so the emission scores are never added, and it does not run on Python 3).  Here: up to
+        `exact_max_states` states the same exhaustive search over the same objective (exact); above that the initial and
+        emission terms -- which are sums of per-state costs -- plus the diagonal of the transition term go to the
+        Hungarian algorithm (scipy.optimize.linear_sum_assignment, O(N^3)), followed for N <= 64 by pairwise-swap
+        descent on the full objective.  The transition term couples pairs of states (a quadratic assignment problem), so
+        beyond `exact_max_states` the result is a local optimum; it recovers a relabelled copy of a model exactly.
+        Off the hot path."""
+        from math import lgamma
         assert self.nStates == to_hmm.nStates
-        mappings = list(permutations(range(self.nStates)))
-        base = {m: self.compute_initprob_mapping_score(to_hmm, list(m)) +
-                self.compute_transition_mapping_score(to_hmm, list(m)) for m in mappings}
-        emis = np.array([self.compute_emission_mapping_score(to_hmm, list(m)) for m in mappings], dtype=np.float64)
-        total = emis.sum()
-        if total != 0:
-            emis = emis / total
-        scores = {m: base[m] + e for m, e in zip(mappings, emis)}
-        return min(mappings, key=lambda m: scores[m])
+        n = self.nStates
+        c_emis = np.asarray(self._emission_pair_costs(to_hmm), dtype=np.float64)
+        total = c_emis.sum()
+        log_z = (np.log(total) + lgamma(n)) if total > 0 else None          # log((N-1)! * sum(c))
+        if n <= exact_max_states:
+            from itertools import permutations
+            best, best_score = None, None
+            for m in permutations(range(n)):
+                sc = self.mapping_score(to_hmm, m, emission_total=log_z)
+                if best_score is None or sc < best_score:
+                    best, best_score = m, sc
+            return best
+        from scipy.optimize import linear_sum_assignment
+        pi_f, pi_t = np.asarray(self.initialProbabilities), np.asarray(to_hmm.initialProbabilities)
+        A_f, A_t = np.asarray(self.transitionMatrix), np.asarray(to_hmm.transitionMatrix)
+        cost = np.abs(pi_t[:, None] - pi_f[None, :]) / n
+        cost = cost + np.abs(np.diag(A_t)[:, None] - np.diag(A_f)[None, :]) / (n ** 2)
+        if log_z is not None:
+            with np.errstate(divide="ignore", under="ignore"):
+                cost = cost + np.exp(np.log(c_emis) - log_z)
+        # tie-break on the emission distances themselves: their normalised weight underflows for large N, yet they are
+        # what tells relabelled states apart when the initial probabilities are uniform
+        cost = cost + 1e-9 * c_emis / max(total, 1e-300) * n
+        rows, cols = linear_sum_assignment(cost)
+        mapping = [0] * n
+        for k, m in zip(rows, cols):
+            mapping[k] = int(m)
+        if n <= 64:
+            best = self.mapping_score(to_hmm, mapping, emission_total=log_z)
+            improved = True
+            while improved:
+                improved = False
+                for a in range(n):
+                    for b in range(a + 1, n):
+                        mapping[a], mapping[b] = mapping[b], mapping[a]
+                        sc = self.mapping_score(to_hmm, mapping, emission_total=log_z)
+                        if sc < best - 1e-15:
+                            best, improved = sc, True
+                        else:
+                            mapping[a], mapping[b] = mapping[b], mapping[a]
+        return tuple(mapping)
 
     def rearrange(self, mapping):
         mapping = list(mapping)

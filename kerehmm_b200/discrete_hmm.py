@@ -65,6 +65,13 @@ class DiscreteHMM(AbstractHMM):
             score += fro.b_distance(to)
         return score
 
+    def _emission_pair_costs(self, to_hmm):
+        """c[k][m] = Bhattacharyya distance (distribution.py:41-68: -log sqrt(sum p q)) between this model's state m and
+        `to_hmm`'s state k, all pairs at once."""
+        P, Q = self.emission_matrix(), to_hmm.emission_matrix()
+        with np.errstate(divide="ignore"):
+            return -np.log(np.sqrt(Q @ P.T))
+
     def initialize_parameters(self, observations):
         pass
 

@@ -603,6 +603,25 @@ def test_train_batch_matches_oracle_iterations(K):
     h.sanity_check()
 
 
+def test_config1_full_length_golden(K):
+    """BASELINE config 1 at full length (one sequence, T = 1000) through the reference-named single-sequence methods against
+    the real reference's outputs (tests/golden/c1_golden.npz): float64 recursions to 1e-9, Viterbi path and log-probability
+    bit-exact over 1000 steps, the bug-compatible forward_probability."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_golden.npz"))
+    h = discrete_model(K, g["pi"], g["A"], g["B"])
+    obs = g["obs"]
+    alpha, scale = h.forward(list(obs))
+    beta = h.backward(list(obs), scale)
+    np.testing.assert_allclose(alpha, g["alpha"], rtol=1e-9)
+    np.testing.assert_allclose(scale, g["scale"], rtol=1e-11)
+    np.testing.assert_allclose(beta, g["beta"], rtol=1e-8)
+    np.testing.assert_allclose(h.gamma(alpha, beta, scale), g["gamma"], rtol=1e-8)
+    assert np.isclose(h.forward_probability(list(obs)), g["forward_probability"], rtol=1e-11)
+    path, logp = h.viterbi_path(obs)
+    assert path.dtype == obs.dtype and np.array_equal(path, g["path"]) and logp == g["logp"]
+
+
 # ------------------------------------------------------------------------- errors / edges
 def test_error_behaviour(K):
     h, _ = random_discrete(K, 4, 5, seed=0)

@@ -207,3 +207,34 @@ def test_bench_reference_arm_under_torchrun_prints_once():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+
+
+def test_state_alignment_exact_and_assignment_based():
+    """compute_mapping_to: exhaustive search up to 8 states (the reference's own objective, abstract_hmm.py:63-94) and
+    the Hungarian + swap-descent path above it; both recover a relabelled copy of a model, and on small models the
+    assignment path reaches the exhaustive optimum."""
+    import kerehmm_b200 as K
+    rng = np.random.default_rng(11)
+    for n, m in ((5, 7), (12, 9), (40, 16)):
+        np.random.seed(100 + n)
+        a = K.DiscreteHMM(n, m, random_transitions=True, random_emissions=True)
+        perm = list(rng.permutation(n))
+        b = K.DiscreteHMM(n, m)
+        b.initialProbabilities = a.initialProbabilities[perm]
+        b.transitionMatrix = a.transitionMatrix[perm, :][:, perm]
+        b.emissionDistributions = a.emissionDistributions[perm]
+        mapping = a.compute_mapping_to(b)
+        assert list(mapping) == perm                      # b's state k is a's state perm[k]
+        a.rearrange_like(b)
+        assert np.allclose(a.transitionMatrix, b.transitionMatrix) and np.allclose(a.emission_matrix(), b.emission_matrix())
+    # two unrelated 6-state models: the transition term makes this a quadratic assignment problem, so the assignment path
+    # ends in a local optimum of the same objective -- close to, never below, the exhaustive optimum
+    np.random.seed(7)
+    x = K.DiscreteHMM(6, 5, random_transitions=True, random_emissions=True)
+    y = K.DiscreteHMM(6, 5, random_transitions=True, random_emissions=True)
+    exact = x.compute_mapping_to(y)
+    approx = x.compute_mapping_to(y, exact_max_states=0)
+    assert x.mapping_score(y, exact) - 1e-12 <= x.mapping_score(y, approx) <= 1.1 * x.mapping_score(y, exact)
+    # the emission score of a permutation is the sum of the pair costs
+    c = x._emission_pair_costs(y)
+    assert np.isclose(x.compute_emission_mapping_score(y, list(exact)), sum(c[k, mk] for k, mk in enumerate(exact)))

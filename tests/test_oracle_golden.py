@@ -258,3 +258,23 @@ def test_gaussian_viterbi_extension_is_the_best_path():
             best, best_path = s, cand
     assert tuple(path) == best_path
     np.testing.assert_allclose(logp, best, rtol=1e-12)
+
+
+def test_config1_full_length_golden():
+    """BASELINE config 1 at its full length (3 states x 4 symbols, ONE sequence of T = 1000; tests/golden/c1_golden.npz from
+    oracle/make_golden_c1.py): the oracle against the real reference's forward / backward / gamma / Viterbi outputs."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_golden.npz"))
+    pi, A, Bm, obs = g["pi"], g["A"], g["B"], g["obs"]
+    assert obs.shape == (1000,) and A.shape == (3, 3) and Bm.shape == (3, 4)
+    E = O.emissions_discrete(Bm, obs)
+    alpha, scale = O.forward(pi, A, E)
+    beta = O.backward(A, E, scale)
+    np.testing.assert_allclose(alpha, g["alpha"], rtol=1e-10)
+    np.testing.assert_allclose(scale, g["scale"], rtol=1e-12)
+    np.testing.assert_allclose(beta, g["beta"], rtol=1e-9)
+    np.testing.assert_allclose(O.gamma(alpha, beta, scale), g["gamma"], rtol=1e-9)
+    assert np.isclose(O.forward_probability(scale), g["forward_probability"], rtol=1e-12)
+    with np.errstate(divide="ignore"):
+        path, logp = O.viterbi(pi, A, Bm, obs)
+    assert np.array_equal(path, g["path"]) and logp == g["logp"]          # bit-exact, 1000 steps
