@@ -303,14 +303,20 @@ def setup_c4(ctx, args):
     w.sharding = "sequences sharded across ranks, one count all-reduce per iteration (libkhmm communicator over NCCL)"
     w.scaling = "weak"
 
-    def roofline(ms_per_step, steps, pk):
+    def collect(steps):
+        """Average device durations of the two E-step kernels over the timed steps (CUDA events inside libkhmm)."""
         n = max(1, min(steps, 32))
         f, b = ctypes.c_float(), ctypes.c_float()
         fs, bs = [], []
         for back in range(n):
             _lib.call("khmm_estep_tc_kernel_ms", back, ctypes.byref(f), ctypes.byref(b))
             fs.append(f.value); bs.append(b.value)
-        fwd_ms, bwd_ms = float(np.mean(fs)), float(np.mean(bs))
+        w.kernel_ms = (float(np.mean(fs)), float(np.mean(bs)))
+
+    w.collect = collect
+
+    def roofline(ms_per_step, steps, pk):
+        fwd_ms, bwd_ms = w.kernel_ms
         # algorithmic bytes of the backward kernel: the forward stash read once (512 B per (sequence, step)), two float32
         # scale factors and the 2-byte symbol twice (epilogue + reduction warps); of the forward kernel: stash + scale write, symbol
         bwd_bytes = B * T * (N * 4 + 8 + 4)
@@ -320,18 +326,7 @@ def setup_c4(ctx, args):
         # dram__bytes_read.sum + dram__bytes_write.sum of one backward launch (ncu --set full at B=18944, scaled to
         # this batch; profiles/): traffic ~ algorithmic bytes
         traffic = (5.037033e9 + 0.004398e9) * (B * T) / (18944.0 * 512.0)
-        # the other operand precision, 5 iterations of the same loop (secondary record)
-        other = "tf32" if prec_name == "bf16x3" else "bf16x3"
-        import torch as _t
-        for _ in range(2):
-            trainer.step(ob, tensor_cores=other)
-        e0, e1 = _t.cuda.Event(enable_timing=True), _t.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            trainer.step(ob, tensor_cores=other)
-        e1.record()
-        _t.cuda.synchronize()
-        other_ms = e0.elapsed_time(e1) / 5
+        other, other_ms = w.secondary_result
         return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "traffic": traffic, "kernel": w.dominant, "peak_source": pk["hbm_source"],
                 "algorithmic_bytes_per_launch": bwd_bytes, "kernel_ms": bwd_ms,
@@ -352,6 +347,21 @@ def setup_c4(ctx, args):
                 "note": "binding roof = HBM (the stash is the only operand that does not fit on chip); the kernel is "
                         "held below it by the shared-memory port (512 KB per tile-step) and L2 count reductions (DESIGN.md 3.5)"}
 
+    def secondary():
+        """The other operand precision, 5 iterations of the same loop (secondary record).  Runs on EVERY rank: the
+        iterations contain the count all-reduce."""
+        other = "tf32" if prec_name == "bf16x3" else "bf16x3"
+        for _ in range(2):
+            trainer.step(ob, tensor_cores=other)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            trainer.step(ob, tensor_cores=other)
+        e1.record()
+        torch.cuda.synchronize()
+        w.secondary_result = (other, e0.elapsed_time(e1) / 5)
+
+    w.secondary = secondary
     w.roofline = roofline
     w.trainer = trainer
     return w
@@ -614,6 +624,11 @@ def measure(w, ctx, steps, warmup, pk, sample_clocks):
     ms_per_step = float(t_ms.item()) / steps
     transitions = float(w.B) * w.T * w.N * w.N * world
     value = transitions / (ms_per_step * 1e-3)
+    if getattr(w, "collect", None) is not None:
+        w.collect(steps)
+    if getattr(w, "secondary", None) is not None:
+        w.secondary()                 # collective-bearing extra measurements: every rank takes part
+        barrier()
     roof = w.roofline(ms_per_step, steps, pk) if rank == 0 else None
 
     # ---- end-to-end through the public API with pinned host buffers
@@ -714,7 +729,9 @@ def run_ours(args):
     torch.cuda.set_device(ctx.local)
     ctx.dev = torch.device("cuda", ctx.local)
     if ctx.world > 1:
-        dist.init_process_group("nccl", device_id=ctx.dev)
+        import datetime
+        # a protocol bug must fail the run within minutes, not sit in a collective until the default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=ctx.dev, timeout=datetime.timedelta(seconds=180))
     engine.require_cuda()
     pk = peaks()
     check = multi_gpu_check(ctx) if ctx.world > 1 else None

@@ -320,6 +320,10 @@ int khmm_estep_tc_timing(int enable);
 int khmm_estep_tc_kernel_ms(int calls_back, float *forward_ms_host, float *backward_ms_host);
 int khmm_estep_tc_last_kernel_ms(float *forward_ms_host, float *backward_ms_host);
 
+/* Development switches: name = "KHMM_RC_MODE" | "KHMM_RC_BN" | "KHMM_VIT_SCREEN" | "KHMM_BW_BACKWARD" (DESIGN.md 4a), value -1
+ * restores the library's default.  The environment variable of the same name sets the initial value and is read once per
+ * process; no production call reads the environment. */
+int khmm_debug_switch(const char *name, int value);
 /* Development hook: which backward kernel the fused E-step uses -- 1 = thread per sequence (the default), 2 = the
  * transposed thread-per-state kernel, 0 = back to the default / $KHMM_BW_BACKWARD.  Both compute the same statistics
  * (tests/test_gpu_parity.py runs the tensor-core E-step tests on both). */

@@ -275,6 +275,8 @@ class AbstractHMM(object):
         """abstract_hmm.py:291-297: gamma[t] = alpha[t]*beta[t]*scale[t] (true gamma times c_t)."""
         t = engine.require_cuda()
         dev = engine.device()
+        if np.shape(alpha) != np.shape(beta) or np.ndim(alpha) != 2 or np.shape(scale) != (np.shape(alpha)[0],):
+            raise ValueError("gamma needs alpha and beta of shape (T, N) and scale of shape (T,)")
         a = t.as_tensor(np.ascontiguousarray(alpha, dtype=np.float64)).to(dev)
         b = t.as_tensor(np.ascontiguousarray(beta, dtype=np.float64)).to(dev)
         c = t.as_tensor(np.ascontiguousarray(scale, dtype=np.float64)).to(dev)

@@ -1,5 +1,6 @@
 // Error plumbing, device info and small utility kernels of libkhmm.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -32,6 +33,24 @@ int sm_count() {
     return cached;
 }
 
+static const char *kSwitchNames[SW_COUNT] = {"KHMM_RC_MODE", "KHMM_RC_BN", "KHMM_VIT_SCREEN", "KHMM_BW_BACKWARD"};
+static int g_switch[SW_COUNT];
+static bool g_switch_init = false;
+
+static void switches_init() {
+    if (g_switch_init) return;
+    for (int k = 0; k < SW_COUNT; k++) {
+        const char *e = getenv(kSwitchNames[k]);
+        g_switch[k] = (e && *e) ? atoi(e) : -1;
+    }
+    g_switch_init = true;
+}
+
+int dev_switch(DevSwitch which) {
+    switches_init();
+    return g_switch[which];
+}
+
 template <typename R>
 __global__ void transpose_kernel(int rows, int cols, const R *__restrict__ in, R *__restrict__ out) {
     __shared__ R tile[32][33];
@@ -62,7 +81,19 @@ extern "C" {
 
 const char *khmm_last_error(void) { return khmm::g_err; }
 
-int khmm_version(void) { return 100; }
+int khmm_version(void) { return 200; }
+
+int khmm_debug_switch(const char *name, int value) {
+    KHMM_REQUIRE(name, "debug_switch: NULL name");
+    khmm::switches_init();
+    for (int k = 0; k < khmm::SW_COUNT; k++)
+        if (strcmp(name, khmm::kSwitchNames[k]) == 0) {
+            khmm::g_switch[k] = value;
+            return KHMM_OK;
+        }
+    khmm::set_error("debug_switch: unknown switch %s", name);
+    return KHMM_ERR_INVALID;
+}
 
 int khmm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
     cudaDeviceProp p;

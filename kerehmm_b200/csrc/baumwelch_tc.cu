@@ -1340,16 +1340,7 @@ struct BwWorkspace {
 // thread-per-state kernel (bw_backward_tc2_kernel).  Both produce the same statistics and run within 3 % of each other at
 // config-4 size (17.0-17.7 against 17.2-17.5 ms; DESIGN.md 3.5 has the resource budgets that bound both), so the older,
 // longer-tested one stays the default; $KHMM_BW_BACKWARD=2 or khmm_debug_bw_backward_version(2) selects the other.
-static int g_bw_backward_override = 0;   // khmm_debug_bw_backward_version
-static int bw_backward_version() {
-    static int v = -1;
-    if (g_bw_backward_override) return g_bw_backward_override;
-    if (v < 0) {
-        const char *e = getenv("KHMM_BW_BACKWARD");
-        v = (e && e[0] == '2') ? 2 : 1;
-    }
-    return v;
-}
+static int bw_backward_version() { return dev_switch(SW_BW_BACKWARD) == 2 ? 2 : 1; }
 
 static BwWorkspace bw_layout(void *ws, int64_t B, int64_t T, int M) {
     auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
@@ -1403,8 +1394,7 @@ int khmm_debug_bw_trace(int64_t *dev_buf) {
 
 int khmm_debug_bw_backward_version(int version) {
     KHMM_REQUIRE(version >= 0 && version <= 2, "debug_bw_backward_version: 0 (default), 1 or 2");
-    g_bw_backward_override = version;
-    return KHMM_OK;
+    return khmm_debug_switch("KHMM_BW_BACKWARD", version == 0 ? -1 : version);
 }
 
 int khmm_estep_tc_timing(int enable) {

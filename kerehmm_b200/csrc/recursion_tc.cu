@@ -726,7 +726,7 @@ static long long *g_rc_trace = nullptr;
 
 template <bool GAUSS>
 static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, const float *AT, TcEmis em, void *ws,
-                  size_t ws_bytes, double *loglik, double *loglik_bwd, int precision, cudaStream_t st) {
+                  size_t ws_bytes, double *loglik, double *loglik_bwd, int precision, cudaStream_t st, bool no_pairs = false) {
     KHMM_REQUIRE(precision == KHMM_TC_TF32 || precision == KHMM_TC_BF16, "fwdbwd_loglik_tc: unknown operand precision %d", precision);
     const bool bf16 = precision == KHMM_TC_BF16;
     KHMM_REQUIRE(B >= 0 && T >= 1, "fwdbwd_loglik_tc: bad shape");
@@ -761,7 +761,8 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
     // kernel on single CTAs, 3 = on CTA pairs where the shape allows.  Measured at c5 (B = 4096, T = 1024, N = 1024): bf16 17.5 ms
     // single / 17.9 ms pairs; tf32 ~29 ms single / 25.8 ms pairs
     int rc_mode = KHMM_RC2 ? ((KHMM_RC2_PAIR && !bf16) ? 3 : 2) : 1;
-    if (const char *e = getenv("KHMM_RC_MODE")) rc_mode = atoi(e);
+    if (dev_switch(SW_RC_MODE) >= 0) rc_mode = dev_switch(SW_RC_MODE);
+    if (no_pairs && rc_mode == 3) rc_mode = 2;
     const bool use_rc2 = coop && rc_mode >= 2;         // any N % 128 == 0, any batch: one launch for all T-1 steps
     if (em.lengths && !use_rc2) {
         set_error("fwdbwd_loglik_tc: ragged batches need the whole-recursion kernel (cooperative launch)");
@@ -814,7 +815,7 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
     // 256-wide column tiles when N allows: 25 % less L2 operand traffic per MAC and half the CTAs
     // (small batches -- e.g. a strong-scaling shard -- keep 128-wide tiles so that more SMs get a CTA)
     int BN = (N % 256 == 0 && (Bp / TC_BM) * (N / 256) * ndir >= sm_count()) ? 256 : 128;
-    if (const char *e = getenv("KHMM_RC_BN")) { if (atoi(e) == 128) BN = 128; }      // development switch
+    if (dev_switch(SW_RC_BN) == 128) BN = 128;      // development switch
     // forward: out[j] = sum_i W[i] A[i][j]  -> B-operand rows j, K index i: AT[j][i]
     // backward: out[i] = sum_j A[i][j] w[j] -> B-operand rows i, K index j: A[i][j]
     if (bf16 ? (make_tmap_bf16_rowmajor(&mapM[0], ATr, N, N, BN) || make_tmap_bf16_rowmajor(&mapM[1], Ar, N, N, BN))
@@ -866,10 +867,11 @@ static int run_tc(int64_t B, int64_t T, int N, const float *pi, const float *A, 
                         &d[0], &d[1], &em, &Bv, &Tv, &Ni, &mt, &nd, &done, &g_rc_trace};
         cudaError_t le = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(320), args, smem, st);
         if (le != cudaSuccess && rpair) {
-            // cooperative launch of a cluster kernel refused: the grid is sized to the resident-cluster count, so a plain
-            // launch still has every CTA resident once the preceding kernels of this stream have drained
+            // cooperative launch of the cluster kernel refused: take the single-CTA whole-recursion kernel (also a
+            // cooperative launch: a plain launch of kernels that spin on each other's progress could hang when the
+            // CTAs are not all resident, e.g. under MPS or with other streams active)
             cudaGetLastError();
-            le = cudaLaunchKernel(kern, dim3(grid), dim3(320), args, smem, st);
+            return run_tc<GAUSS>(B, T, N, pi, A, AT, em, ws, ws_bytes, loglik, loglik_bwd, precision, st, true);
         }
         KHMM_CUDA_CHECK(le);
     } else {

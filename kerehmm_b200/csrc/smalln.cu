@@ -14,14 +14,14 @@
 //
 // Blackwell specifics: all FP32 work is issued as packed FFMA2/FMUL2/FADD2 (fma.rn.f32x2, two
 // states per instruction) -- the kernel is bound by FP32 issue, not by HBM; the
-// matrix-vector product pairs the INPUT states (even/odd partial sums, one scalar add per output)
-// so no broadcast moves are needed; exp2 and the reciprocal are single MUFU instructions
-// (ex2.approx / rcp.approx); observations are prefetched one 8-step block ahead so their latency
-// never sits on the recursion's dependency chain.
+// matrix-vector product keeps one accumulation chain per pair of OUTPUT states (broadcast input
+// state times a packed pair of matrix entries); exp2 is a single MUFU instruction (ex2.approx);
+// observations are prefetched one 8-step block ahead so their latency never sits on the
+// recursion's dependency chain.
 //
-// Scaling uses r_t ~ 1/c_t from the hardware reciprocal and accumulates log P from r_t itself
-// (exponent in an integer, mantissa product in fp32, renormalised every block), so the result
-// does not depend on the reciprocal's rounding and costs no transcendental per step.
+// Scaling (round 2): exact powers of two, taken from the exponent of the row sum every OTHER step and applied one step
+// late, off the recursion's dependency chain; log P = ln 2 * (sum of the exponents, an integer) + log(final sum).  No
+// reciprocal, no mantissa bookkeeping, and half the scale / row-sum arithmetic of scaling at every step.
 #include "common.cuh"
 
 namespace khmm {
@@ -31,31 +31,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-struct LogAccum {  // log2 of a product of positive normal floats
-    int esum = 0;      // sum of biased exponents
-    int n = 0;         // number of factors
-    float mant = 1.f;  // product of mantissas since the last fold, in [1, 2^8]
-    __device__ __forceinline__ void mul(float r) {
-        unsigned bits = __float_as_uint(r);
-        esum += (int)(bits >> 23);
-        n++;
-        mant *= __uint_as_float((bits & 0x7fffffu) | 0x3f800000u);
-    }
-    __device__ __forceinline__ void fold() {  // call at least every 100 factors
-        unsigned bits = __float_as_uint(mant);
-        esum += (int)(bits >> 23) - 127;
-        mant = __uint_as_float((bits & 0x7fffffu) | 0x3f800000u);
-    }
-    __device__ __forceinline__ double log2_total() const {
-        return (double)(esum - 127 * n) + (double)log2f(mant);
-    }
-};
 
 template <int NP, bool GAUSS, bool MX_SMEM>
 struct SmallStep {
@@ -87,39 +62,57 @@ struct SmallStep {
         }
     }
 
-    // One recursion step with the scale applied AFTER the matrix-vector product:
-    //     w_t = (w_{t-1} M) . (b_t * r_{t-1}),   r_t = 1 / sum(w_t)
-    // (w_t is the reference's unnormalised alpha_t; same arithmetic as normalising w_{t-1} first, but
-    // the sum -> reciprocal chain of step t-1 now runs in parallel with the matrix-vector product of
-    // step t instead of in front of it).  log P accumulates from the reciprocals themselves.
-    __device__ __forceinline__ void step(float2 (&w)[H], float &r, const float2 (&bv)[H], LogAccum &acc) const {
-        const float2 rr = make_float2(r, r);
-        float2 out[H];
+    // w M: input states in ONE accumulation chain per output pair (the four / eight chains of a step are independent,
+    // which is all the instruction-level parallelism a warp needs with packed FFMA2 issuing every other cycle; the
+    // round-1 version split even and odd inputs into two chains and paid a packed add per output pair to merge them)
+    __device__ __forceinline__ void matvec(const float2 (&w)[H], float2 (&out)[H]) const {
 #pragma unroll
         for (int k = 0; k < H; k++) {
-            // even / odd input states in two independent chains, scalar-broadcast operand form
-            float2 c0 = __fmul2_rn(make_float2(w[0].x, w[0].x), mat(0, k));
-            float2 c1 = __fmul2_rn(make_float2(w[0].y, w[0].y), mat(1, k));
+            float2 c = __fmul2_rn(make_float2(w[0].x, w[0].x), mat(0, k));
+            c = __ffma2_rn(make_float2(w[0].y, w[0].y), mat(1, k), c);
 #pragma unroll
             for (int y2 = 1; y2 < H; y2++) {
-                c0 = __ffma2_rn(make_float2(w[y2].x, w[y2].x), mat(2 * y2, k), c0);
-                c1 = __ffma2_rn(make_float2(w[y2].y, w[y2].y), mat(2 * y2 + 1, k), c1);
+                c = __ffma2_rn(make_float2(w[y2].x, w[y2].x), mat(2 * y2, k), c);
+                c = __ffma2_rn(make_float2(w[y2].y, w[y2].y), mat(2 * y2 + 1, k), c);
             }
-            out[k] = __fadd2_rn(c0, c1);
+            out[k] = c;
         }
-#pragma unroll
-        for (int k = 0; k < H; k++) w[k] = __fmul2_rn(out[k], __fmul2_rn(bv[k], rr));
-        r = recip_sum(w);
-        acc.mul(r);
     }
 
-    __device__ __forceinline__ float recip_sum(const float2 (&val)[H]) const {
+    // Steps come in pairs, and the scale factor is an exact POWER OF TWO applied one step late:
+    //     step A:  w = (w M) . b                       s = sum(w)  (off the dependency chain);  e = exponent(s)
+    //     step B:  w = (w M) . (b 2^-e)                log2 P accumulates e as an integer
+    // The recursion is linear, so any positive scale sequence gives the same likelihood; powers of two make the
+    // bookkeeping exact and free of MUFU work, and scaling every other step halves the scale and row-sum arithmetic
+    // (52 packed FMA-pipe instructions per step at N = 8 against 64 in round 1).  Between two rescalings the vector
+    // shrinks by at most three emission factors, far inside the fp32 range for any emission above 1e-12.
+    __device__ __forceinline__ void step_plain(float2 (&w)[H], const float2 (&bv)[H]) const {
+        float2 out[H];
+        matvec(w, out);
+#pragma unroll
+        for (int k = 0; k < H; k++) w[k] = __fmul2_rn(out[k], bv[k]);
+    }
+    __device__ __forceinline__ void step_scaled(float2 (&w)[H], const float2 (&bv)[H], float sc) const {
+        const float2 s2 = make_float2(sc, sc);
+        float2 out[H];
+        matvec(w, out);
+#pragma unroll
+        for (int k = 0; k < H; k++) w[k] = __fmul2_rn(out[k], __fmul2_rn(bv[k], s2));
+    }
+    __device__ __forceinline__ float hsum(const float2 (&val)[H]) const {
         float2 s2 = val[0];
         if constexpr (H >= 2) s2 = __fadd2_rn(s2, val[1]);
         if constexpr (H >= 4) s2 = __fadd2_rn(s2, __fadd2_rn(val[2], val[3]));
         if constexpr (H >= 8) s2 = __fadd2_rn(s2, __fadd2_rn(__fadd2_rn(val[4], val[5]), __fadd2_rn(val[6], val[7])));
-        return rcp_approx(s2.x + s2.y);
+        return s2.x + s2.y;
     }
+    // 2^-e with e = the exponent of s (s = 0 or subnormal: 2^127, the vector is zero anyway); esum += e
+    __device__ __forceinline__ float pow2_rescale(float s, int &esum) const {
+        const int e = (int)((__float_as_uint(s) >> 23) & 0xffu) - 127;
+        esum += e;
+        return __uint_as_float((uint32_t)(127 - e) << 23);
+    }
+
 };
 
 constexpr int kBlk = 8;  // steps per observation prefetch block
@@ -203,8 +196,8 @@ fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict_
     };
 
     float2 u[Q][H];
-    float r[Q];
-    LogAccum acc[Q];
+    float sc[Q];        // pending power-of-two scale factor (applied by the next scaled step)
+    int esum[Q];        // log2 of the product of the scale factors taken out so far, negated
 #pragma unroll
     for (int q = 0; q < Q; q++) {   // step 0: start vector (pi forward, ones backward) times the first emission
         float2 bv[H];
@@ -215,8 +208,8 @@ fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict_
             float2 st = dir ? make_float2(2 * k < N ? 1.f : 0.f, 2 * k + 1 < N ? 1.f : 0.f) : pv[k];
             u[q][k] = __fmul2_rn(st, bv[k]);
         }
-        r[q] = S.recip_sum(u[q]);
-        acc[q].mul(r[q]);
+        esum[q] = 0;
+        sc[q] = S.pow2_rescale(S.hsum(u[q]), esum[q]);
     }
     float xs[Q][kBlk], xn[Q][kBlk];
 #pragma unroll
@@ -233,12 +226,16 @@ fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict_
         for (int q = 0; q < Q; q++) full = full && (s0 + kBlk <= len[q]);
         if (full) {
 #pragma unroll
-            for (int i = 0; i < kBlk; i++) {
+            for (int i = 0; i < kBlk; i += 2) {
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
                     float2 bv[H];
+                    // scaled step (takes the pending factor), then a plain step whose row sum gives the next factor
                     S.emis(xs[q][i], __float_as_int(xs[q][i]), bv);
-                    S.step(u[q], r[q], bv, acc[q]);
+                    S.step_scaled(u[q], bv, sc[q]);
+                    S.emis(xs[q][i + 1], __float_as_int(xs[q][i + 1]), bv);
+                    S.step_plain(u[q], bv);
+                    sc[q] = S.pow2_rescale(S.hsum(u[q]), esum[q]);
                 }
             }
         } else {
@@ -246,17 +243,17 @@ fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict_
             for (int i = 0; i < kBlk; i++) {
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
-                    if (s0 + i < len[q]) {
+                    if (s0 + i < len[q]) {      // the ragged tail rescales at every step
                         float2 bv[H];
                         S.emis(xs[q][i], __float_as_int(xs[q][i]), bv);
-                        S.step(u[q], r[q], bv, acc[q]);
+                        S.step_scaled(u[q], bv, sc[q]);
+                        sc[q] = S.pow2_rescale(S.hsum(u[q]), esum[q]);
                     }
                 }
             }
         }
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            acc[q].fold();
 #pragma unroll
             for (int i = 0; i < kBlk; i++) xs[q][i] = xn[q][i];
         }
@@ -265,15 +262,16 @@ fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict_
     for (int q = 0; q < Q; q++) {
         int64_t b = bfirst + 32 * q;
         if (b >= B) continue;
-        // closing dot product: forward sum(u) r (= 1 up to rounding), backward (pi . w_0) r
+        // closing dot product: forward sum(u), backward pi . w_0 -- of the vector as it stands (the pending factor was
+        // counted in esum but not applied yet, so it is applied here)
         float2 f2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < H; k++) {
             float2 w = dir ? pv[k] : make_float2(2 * k < N ? 1.f : 0.f, 2 * k + 1 < N ? 1.f : 0.f);
             f2 = __ffma2_rn(u[q][k], w, f2);
         }
-        const float fin = (f2.x + f2.y) * r[q];   // u is unnormalised by the last reciprocal
-        double ll = (-acc[q].log2_total()) * 0.6931471805599453 + log((double)fin);
+        const float fin = (f2.x + f2.y) * sc[q];
+        double ll = (double)esum[q] * 0.6931471805599453 + log((double)fin);
         if (!(fin > 0.f) || !(fin < INFINITY)) ll = __longlong_as_double(0x7ff8000000000000ll);  // underflow -> NaN (Q15)
         (dir ? loglik_bwd : loglik)[b] = ll;
     }

@@ -624,8 +624,7 @@ static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, 
     size_t off = (((size_t)B * sizeof(int32_t)) + 255) / 256 * 256;
     PSI *psi = reinterpret_cast<PSI *>(reinterpret_cast<unsigned char *>(backptr) + off);
     int rc_tile = -1;
-    const char *vs_env = getenv("KHMM_VIT_SCREEN");      // development / cross-check switch, read on every call
-    const bool use_screen = !(vs_env && atoi(vs_env) == 0);
+    const bool use_screen = dev_switch(SW_VIT_SCREEN) != 0;      // development / cross-check switch (khmm_debug_switch)
     // N <= 64: from one sequence up (T = 4096: 3.2 ms against 6.3 ms on the generic kernel at N = 64, 2.2 against 4.2 ms
     // at N = 32); N = 128: from 64 sequences (every CTA first copies 192 KB of logA into shared memory: 14.2 against
     // 10.7 ms at B = 8)

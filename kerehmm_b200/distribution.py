@@ -120,3 +120,14 @@ class GaussianDistribution(Distribution):
             self.dimensions, self.mean, self.variance)
 
     __repr__ = __str__
+
+
+class GaussianMixture(Distribution):
+    """kerehmm/distribution.py:173-219 declares a mixture-of-Gaussians emission that no HMM class of the reference uses
+    and whose constructor does not run on Python 3 (`distribution.py:202`); it is off the hot path
+     and not provided -- the name exists so that code importing it fails with an explanation rather than
+    an ImportError."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("GaussianMixture is unused by the reference's HMM classes and outside this engine's "
+                                  "scope (SURVEY.md 2); GaussianDistribution covers Gaussian emissions")

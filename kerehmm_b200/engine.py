@@ -289,6 +289,10 @@ def backward(p: ModelParams, ob: Obs, real, scale, alpha=None, want_beta=True, w
              gamma_kind=_lib.GAMMA_REFERENCE):
     """Scaled backward (+ optional fused gamma) -> (beta|None, gamma|None)."""
     t = require_cuda()
+    if tuple(scale.shape) != (ob.B, ob.T):
+        raise ValueError("scale must have shape (B, T) = %s, got %s" % ((ob.B, ob.T), tuple(scale.shape)))
+    if alpha is not None and tuple(alpha.shape) != (ob.B, ob.T, p.N):
+        raise ValueError("alpha must have shape (B, T, N)")
     dm = DeviceModel(p, real)
     N, dev = p.N, device()
     beta = t.empty((ob.B, ob.T, N), dtype=real, device=dev) if want_beta else None
@@ -482,6 +486,11 @@ def viterbi(p: ModelParams, ob: Obs, path_dtype=None):
     d_logpi, d_logA = _dev(logpi, t.float64), _dev(logA, t.float64)
     path_dtype = path_dtype or t.int64
     pname = str(path_dtype).replace("torch.", "")
+    if pname not in _PATH_CODES:
+        raise ValueError("path_dtype must be uint8, int16, int32 or int64")
+    capacity = {"uint8": 256, "int16": 32768}.get(pname)
+    if capacity is not None and N > capacity:
+        raise ValueError("path_dtype %s cannot hold the states of a %d-state model" % (pname, N))
     path = t.zeros((ob.B, ob.T), dtype=path_dtype, device=dev)
     logp = t.empty((ob.B,), dtype=t.float64, device=dev)
     ws_bytes = _lib.lib().khmm_viterbi_workspace_bytes(ob.B, ob.T, N)
@@ -571,18 +580,26 @@ def estep_tc_supported(p: ModelParams, ob: Obs, real) -> bool:
 _ws_cache = {}
 
 
+def _ws_key():
+    """Scratch buffers are per (device, stream): kernels queued on different streams must not share scratch, and a
+    block allocated under one stream is only ever reused by work on that stream (the caching allocator's contract)."""
+    t = torch()
+    return (t.cuda.current_device(), t.cuda.current_stream().cuda_stream)
+
+
 def workspace(nbytes: int, align: int = 1024):
-    """A cached, aligned device scratch buffer of at least `nbytes` (one per device, grown on demand).
+    """A cached, aligned device scratch buffer of at least `nbytes` (one per device and stream, grown on demand).
     The tensor-core E-step stash is tens of GB: re-allocating it every iteration costs a cudaMalloc of
     that size whenever the caching allocator has let the block go."""
     t = torch()
     dev = device()
-    buf = _ws_cache.get(dev.index)
+    key = _ws_key()
+    buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes + align:
-        _ws_cache.pop(dev.index, None)
+        _ws_cache.pop(key, None)
         buf = None
         buf = t.empty((nbytes + align,), dtype=t.uint8, device=dev)
-        _ws_cache[dev.index] = buf
+        _ws_cache[key] = buf
     return buf, buf.data_ptr() + (-buf.data_ptr()) % align
 
 
@@ -631,7 +648,7 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
     counts = counts or Counts(N, M)
     L = _lib.lib()
     if chunk is None:
-        cached = _ws_cache.get(dev.index)
+        cached = _ws_cache.get(_ws_key())
         if cached is not None and cached.numel() >= L.khmm_estep_tc_workspace_bytes(ob.B, ob.T, N, M) + 1024:
             chunk = ob.B                      # the whole batch fits the scratch buffer we already hold
         else:

@@ -50,6 +50,17 @@ class GaussianHMM(AbstractHMM):
         pi_new[:] = gamma[0, :]
         return pi_new
 
+    def estimate_transition_probabilities(self, *args, **kwargs):
+        """gaussian_hmm.py:34-45 is part of the reference's stale log-space training code (it is only reachable from
+        `do_pass`, which fails before calling it); the working path is `do_pass_batch` / `train_batch`."""
+        raise NotImplementedError("GaussianHMM.estimate_transition_probabilities belongs to the reference's broken "
+                                  "log-space do_pass; use do_pass_batch / train_batch")
+
+    def estimate_emission_distributions(self, *args, **kwargs):
+        """See `estimate_transition_probabilities` (gaussian_hmm.py:47-53)."""
+        raise NotImplementedError("GaussianHMM.estimate_emission_distributions belongs to the reference's broken "
+                                  "log-space do_pass; use do_pass_batch / train_batch")
+
     def do_pass(self, observations, verbose=False):
         """The reference's GaussianHMM.do_pass is stale log-space code that fails at its first
         lines at HEAD (`backward()` without the scale argument -> TypeError, gaussian_hmm.py:55-56;

@@ -689,17 +689,14 @@ def test_viterbi_config3_full_size_two_kernels_agree(K):
     N, M, B, T = 64, 256, 65536, 4096
     h, (pi, A, Bm) = random_discrete(K, N, M, seed=3)
     obs = torch.from_numpy(np.random.default_rng(1003).integers(0, M, size=(B, T)).astype(np.uint8)).cuda()
-    old = os.environ.get("KHMM_VIT_SCREEN")
+    from kerehmm_b200 import _lib
     try:
-        os.environ["KHMM_VIT_SCREEN"] = "1"
+        _lib.call("khmm_debug_switch", b"KHMM_VIT_SCREEN", 1)
         p1, l1 = h.viterbi_batch(obs, path_dtype=torch.uint8)
-        os.environ["KHMM_VIT_SCREEN"] = "0"
+        _lib.call("khmm_debug_switch", b"KHMM_VIT_SCREEN", 0)
         p0, l0 = h.viterbi_batch(obs, path_dtype=torch.uint8)
     finally:
-        if old is None:
-            os.environ.pop("KHMM_VIT_SCREEN", None)
-        else:
-            os.environ["KHMM_VIT_SCREEN"] = old
+        _lib.call("khmm_debug_switch", b"KHMM_VIT_SCREEN", -1)
     assert torch.equal(p1, p0) and torch.equal(l1, l0)
     with np.errstate(divide="ignore"):
         rp, rl = O.viterbi(pi, A, Bm, obs[:4].cpu().numpy().astype(np.int64))
