@@ -1281,6 +1281,501 @@ bw_backward_tc2_kernel(const __grid_constant__ CUtensorMap mapStash, const __gri
     if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------- backward, transposed, four quarter-tile pipelines in flight (round 2)
+// Both kernels above run ONE tile per CTA, and a step of a tile is a serial chain -- MMA1 -> thread work -> MMA1 --
+// whose links use different resources: their step period (8,100 / 8,300 cycles) is the SUM of the links.  This kernel keeps
+// the transposed formulation (TMEM lane = state: every thread access is contiguous across the warp, the transition matrix
+// is a resident TMEM operand) and splits the tile into two HALVES of 64 sequences that run as independent pipelines:
+//     MMA1(t, h)  D1^T[i][b] = sum_j A[i][j] V_{t+1}[b][j]      M = 128 states, N = 64 sequences: a transposed MMA loses
+//                                                               nothing at N = 64 (a thread-per-sequence M = 64 MMA would
+//                                                               run at half rate)
+//     MMA2(t, h)  Xi^T[j][i] += sum_b V2^T_{t+1}[j][b] W_t[b][i]  K = the 64 sequences of the half, one accumulator
+// so the tensor pipe, the compute warps of the other half, the TMA stream and the L2 reductions overlap.  What the threads do
+// per (sequence b, state i = thread), all warp-contiguous:
+//     e   = Bsm[o_t(b)][i]            coalesced 128-byte read of a table row through L1/L2, prefetched one step ahead
+//     w   = W_t[b][i]                 shared memory (the TMA tile, read in place; two buffers per half)
+//     beta = D1^T[i][b] / c_{t+1}(b);  gamma_ref = w beta  -> red.global.add.f32 into row o_t(b) of the count table:
+//                                     one coalesced 128-byte reduction per warp instruction, straight from registers
+//     V   = e beta -> shared memory (K-major operand of MMA1(t-1)),  V2 = V / c_{t-1}(b) -> TMEM (operand of MMA2(t-1))
+// SIXTEEN compute warps, warp (q, h, c) = states 32q..32q+31, sequences 32c..32c+31 of half h: four warps per scheduler (the
+// eight-warp version ran each warp at 0.25 instructions per clock on its own dependency chains -- 5,000 cycles per
+// half-step whatever was switched off).  The loop body is straight-line: unconditional reductions (a dead (sequence, step)
+// pair adds the zero of its zero stash row), the rows of a sequence's last step summed in a register.
+// No staging of gamma or of the emission rows in shared memory.  Shared memory: W 2 halves x 2 buffers x 32 KB, V 2 x 32 KB.
+// TMEM: A (or A_hi | A_lo), D1^T (2 x 64 columns), Xi^T, V2^T (2 x 64 columns) = 512 columns.
+// SPLIT (bf16x3): MMA1 = A_hi V_hi + A_lo V_hi + A_hi V_lo on bf16 hi/lo pairs (kind::f16), A_hi/A_lo resident in TMEM, V_hi/V_lo
+// in the same 32 KB; MMA2 stays tf32 (its rounding errors are unbiased and average out over the B*T rows it sums).
+constexpr uint32_t C3_A = 0, C3_R0 = 128, C3_XI = 256, C3_R1 = 384;   // R0 / R1: D1^T of one step, V2^T of the other (ping-pong)
+constexpr int BW_HSUB = 64 * 128;       // one [64 sequences][128 B] sub-tile of a half (8 KB)
+constexpr int BW_HTILE = 4 * BW_HSUB;   // one half: [64 sequences][128 states] fp32 (32 KB)
+constexpr int BW3_PREP = 4;             // prep ring depth: the prep warps run up to three steps ahead of the compute warps
+constexpr int BW3_THREADS = 640;        // 16 compute warps + TMA + MMA + 2 prep warps
+
+struct __align__(8) Bwd3Bars {
+    uint64_t w_full[2][2], w_empty[2][2], v_ready[4], d1_full[4], prep_full[2][BW3_PREP], prep_empty[2][BW3_PREP],
+        xi_done, xi_free;
+    uint32_t tmem_base;
+};
+struct __align__(16) Bwd3Prep {   // per-sequence scalars of one step of one half
+    uint32_t roff[64]; // 128 * clamped symbol: float offset of the table row o_t(b)
+    float mulb[64];    // c_t / c_{t+1}, or 0 where beta_t = 1 (t >= len - 1: the sequence's last step or its padding):
+                       // MMA1 runs on V2_{t+1} = V_{t+1} / c_t, so D1 = (A V_{t+1}) / c_t and beta_t = D1 c_t / c_{t+1}
+    float addb[64];    // 1 where mulb = 0, else 0:  beta = D1 * mulb + addb
+    float rcm1[64];    // 1 / c_{t-1} for 0 < t < len, else 0 (V2_t = 0: the pair (t-1, t) does not count)
+    float lastf[64];   // 1 on the sequence's last step (t = len - 1), else 0
+    int flag[64];      // bit 0: (sequence, step) not live (a row past the batch, a step of the padding); bit 1: last step
+};
+// base + off floats in one IMAD.WIDE (the compiler's LEA / IADD.X pair costs two issue slots per address)
+__device__ __forceinline__ float *addr_f32(const float *base, uint32_t off) {
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(off), "l"(base));
+    return reinterpret_cast<float *>(a);
+}
+__device__ __forceinline__ void red_add_f32_nc(float *p, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a));
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(BW3_THREADS, 1)
+bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const float *__restrict__ Amat,
+                       const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T, const float *__restrict__ scale,
+                       BwdOut out) {
+    constexpr bool SPLIT = PREC != KHMM_TC_TF32;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *sW = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [half][buffer][BW_HTILE]
+    unsigned char *sV = sW + 4 * BW_HTILE;                                              // [half][BW_HTILE]
+    Bwd3Prep *prep = (Bwd3Prep *)(sV + 2 * BW_HTILE);                                   // [half][BW3_PREP]
+    Bwd3Bars *bars = (Bwd3Bars *)(prep + 2 * BW3_PREP);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (B + 127) / 128;
+    const int M = ob.M;
+    const int Ti = (int)T;
+    const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const uint32_t gtotal = (uint32_t)(my_tiles * Ti);     // steps of this CTA (all its tiles)
+
+    if (threadIdx.x == 0) {
+        for (int h = 0; h < 2; h++) {
+            for (int k = 0; k < 2; k++) {
+                mbar_init(&bars->w_full[h][k], 1);
+                mbar_init(&bars->w_empty[h][k], 10);     // 8 compute warps + the commits of the two quarters' MMA2
+            }
+            for (int k = 0; k < BW3_PREP; k++) {
+                mbar_init(&bars->prep_full[h][k], 1);
+                mbar_init(&bars->prep_empty[h][k], 8);
+            }
+        }
+        for (int pq = 0; pq < 4; pq++) {
+            mbar_init(&bars->v_ready[pq], 128);
+            mbar_init(&bars->d1_full[pq], 1);
+        }
+        mbar_init(&bars->xi_done, 1);
+        mbar_init(&bars->xi_free, 256);
+        fence_barrier_init();
+    }
+    if (warp == 17) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    if (warp < 8) {
+        // the transition matrix, row i -> TMEM lane i, resident for the whole kernel: warp (q, hh) stores columns [64hh, 64hh+64)
+        const int q = warp & 3, hh = warp >> 2;
+        const int i = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        if (SPLIT) {
+            // A_hi -> columns [0, 64), A_lo -> [64, 128): two consecutive K elements per 32-bit column
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int p = 0; p < 16; p++) {
+                float4 f = ldg4(Amat + (size_t)i * BW_N + 64 * hh + 4 * p);
+                split_bf16x2(f.x, f.y, hi[2 * p], lo[2 * p]);
+                split_bf16x2(f.z, f.w, hi[2 * p + 1], lo[2 * p + 1]);
+            }
+            tmem_st_32x32(tmem + lane_base + C3_A + 32 * hh, hi);
+            tmem_st_32x32(tmem + lane_base + C3_A + 64 + 32 * hh, lo);
+        } else {
+#pragma unroll 1
+            for (int c0 = 64 * hh; c0 < 64 * hh + 64; c0 += 32) {
+                uint32_t a[32];
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    float4 f = ldg4(Amat + (size_t)i * BW_N + c0 + 4 * p);
+                    a[4 * p] = __float_as_uint(f.x); a[4 * p + 1] = __float_as_uint(f.y);
+                    a[4 * p + 2] = __float_as_uint(f.z); a[4 * p + 3] = __float_as_uint(f.w);
+                }
+                tmem_st_32x32(tmem + lane_base + C3_A + c0, a);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 16) {
+        // ------------------------------------------------ TMA producer: W_t half-tiles of the stash, two buffers per half
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (elect_one()) {
+            tma_prefetch_desc(&mapStashH);
+            uint32_t g = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int t = Ti - 1; t >= 0; t--, g++) {
+                    const int buf = g & 1;
+                    const uint32_t par = ((g >> 1) & 1) ^ 1;
+                    for (int h = 0; h < 2; h++) {
+                        mbar_wait(&bars->w_empty[h][buf], par);
+                        if (h == 0) BW2_TRACE(0);
+                        mbar_arrive_expect_tx(&bars->w_full[h][buf], BW_HTILE);
+                        unsigned char *dst = sW + (h * 2 + buf) * BW_HTILE;
+                        for (int c = 0; c < 4; c++)
+                            tma_load_3d(dst + c * BW_HSUB, &mapStashH, &bars->w_full[h][buf], c * 32, 64 * h, (int)(tile * T + t));
+                    }
+                }
+        }
+    } else if (warp == 17) {
+        // ------------------------------------------------ MMA issuer: the two halves alternate
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (elect_one()) {
+            const uint32_t idesc1 = SPLIT ? make_idesc_bf16(128, 32) : make_idesc_tf32(128, 32);
+            const uint32_t idesc2 = make_idesc_tf32(128, 128, false, true);
+            uint32_t nv = 0, g = 0, ntile = 0;
+            // operand descriptors: one base per half / per (half, buffer); a K step is a constant added to the address field
+            // (no dynamically indexed arrays here: they would live in local memory, whose loads miss L1 in this kernel)
+            const uint64_t dV0 = make_kmajor_sw128_desc(sV), dV1 = make_kmajor_sw128_desc(sV + BW_HTILE);
+            const uint64_t dW0 = make_mnmajor_sw128a32_desc(sW, BW_HSUB, 512),
+                           dW1 = make_mnmajor_sw128a32_desc(sW + 2 * BW_HTILE, BW_HSUB, 512);
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ntile++) {
+                g++;      // step t = T-1 has no MMA
+                for (int t = Ti - 2; t >= 0; t--, g++, nv++) {
+                    const int buf = g & 1;
+                    const uint32_t wpar = (g >> 1) & 1;
+#pragma unroll
+                    for (int pq = 0; pq < 4; pq++) {
+                        // pipeline pq = 2h + c: the 32 sequences [32c, 32c + 32) of half h -- rows 32c.. of the half's V and W
+                        // tiles (4 KB further into every sub-tile), columns 32c.. of its D1^T and V2^T
+                        const int h = pq >> 1, c = pq & 1;
+                        mbar_wait(&bars->v_ready[pq], nv & 1);
+                        BW2_TRACE(pq == 0 ? 4 : (pq == 2 ? 20 : 31));
+                        tc_fence_after();
+                        const uint32_t dcol = tmem + ((g & 1) ? C3_R1 : C3_R0) + 64 * h + 32 * c;     // D1^T of this step
+                        const uint32_t vcol = tmem + ((g & 1) ? C3_R0 : C3_R1) + 64 * h + 32 * c;     // V2^T of the previous step
+                        // opaque to the optimiser: it would otherwise hoist all 80 per-instruction descriptors out of the time
+                        // loop, spill them, and put local-memory loads (L2 latency here) in front of every MMA
+                        uint64_t dvb = h ? dV1 : dV0, dwb = desc_advance(h ? dW1 : dW0, buf * BW_HTILE);
+                        asm volatile("" : "+l"(dvb), "+l"(dwb));
+                        // MMA1(t, pq): D1^T = A . V_{t+1}^T
+                        if (SPLIT) {
+                            // (A_hi, V_hi), (A_lo, V_hi), (A_hi, V_lo)
+#pragma unroll
+                            for (int pass = 0; pass < 3; pass++) {
+                                const uint32_t acol = tmem + C3_A + (pass == 1 ? 64 : 0);
+#pragma unroll
+                                for (int k = 0; k < 8; k++)
+                                    mma_bf16_ts(dcol, acol + k * 8,
+                                                desc_advance(dvb, 4096 * c + (pass == 2 ? 2 * BW_HSUB : 0) + (k >> 2) * BW_HSUB + (k & 3) * 32),
+                                                idesc1, (pass | k) != 0);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; k++)
+                                mma_tf32_ts(dcol, tmem + C3_A + k * 8,
+                                            desc_advance(dvb, 4096 * c + (k >> 2) * BW_HSUB + (k & 3) * 32), idesc1, k != 0);
+                        }
+                        tc_commit(&bars->d1_full[pq]);
+                        BW2_TRACE(pq == 0 ? 5 : (pq == 2 ? 21 : 31));
+                        if (c == 0) mbar_wait(&bars->w_full[h][buf], wpar);
+                        // the previous tile's Xi must have been flushed before this tile's first MMA2 overwrites it
+                        if (t == Ti - 2 && pq == 0 && ntile > 0) mbar_wait(&bars->xi_free, (ntile - 1) & 1);
+                        BW2_TRACE(pq == 0 ? 6 : (pq == 2 ? 22 : 31));
+                        tc_fence_after();
+                        // MMA2(t, pq): Xi^T += V2^T_{t+1} . W_t over the 32 sequences of the quarter
+                        const uint64_t dW = dwb;
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            mma_tf32_ts(tmem + C3_XI, vcol + k * 8, desc_advance(dW, 4096 * c + k * 1024), idesc2,
+                                        (t != Ti - 2) || pq != 0 || k != 0);
+                        tc_commit(&bars->w_empty[h][buf]);
+                        if (t == 0 && pq == 3) tc_commit(&bars->xi_done);
+                        BW2_TRACE(pq == 0 ? 7 : (pq == 2 ? 23 : 31));
+                    }
+                }
+            }
+        }
+    } else if (warp >= 18) {
+        // ------------------------------------------------ prep (one warp per half): per-sequence scalars, up to three steps ahead.
+        // The symbol and scale loads of step g+1 are in flight while step g is written.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        const int h = warp - 18;
+        int64_t bc[2] = {0, 0};
+        int len[2] = {0, 0};
+        int syn[2] = {0, 0}, lenn[2] = {0, 0};
+        float c1n[2] = {1.f, 1.f}, c0n[2] = {1.f, 1.f}, cmn[2] = {1.f, 1.f};
+        auto issue = [&](uint32_t gg) {      // the loads of step gg
+            const int64_t tile = blockIdx.x + (int64_t)(gg / Ti) * gridDim.x;
+            const int t = Ti - 1 - (int)(gg % Ti);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int b = 64 * h + lane + 32 * k;
+                if (t == Ti - 1) {      // first step of a tile: this lane's sequences change
+                    const int64_t gb = tile * 128 + b;
+                    bc[k] = gb < B ? gb : B - 1;
+                    len[k] = gb < B ? ob.len(gb) : 0;
+                }
+                syn[k] = ob.sym(bc[k], t);
+                c1n[k] = (t + 1 < Ti) ? scale[(tile * T + t + 1) * 128 + b] : 1.f;
+                c0n[k] = scale[(tile * T + t) * 128 + b];
+                cmn[k] = (t > 0) ? scale[(tile * T + t - 1) * 128 + b] : 1.f;
+                lenn[k] = len[k];
+            }
+        };
+        if (gtotal) issue(0);
+        for (uint32_t g = 0; g < gtotal; g++) {
+            const int t = Ti - 1 - (int)(g % Ti);
+            int sy[2], lenc[2];
+            float c1[2], c0[2], cm[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) { sy[k] = syn[k]; c1[k] = c1n[k]; c0[k] = c0n[k]; cm[k] = cmn[k]; lenc[k] = lenn[k]; }
+            if (g + 1 < gtotal) issue(g + 1);
+            const int buf = g % BW3_PREP;
+            mbar_wait(&bars->prep_empty[h][buf], ((g / BW3_PREP) & 1) ^ 1);
+            Bwd3Prep &P = prep[h * BW3_PREP + buf];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int b = lane + 32 * k;
+                const bool bone = (t == Ti - 1) || (t >= lenc[k] - 1);
+                P.roff[b] = (uint32_t)(sy[k] * BW_N);
+                P.flag[b] = (t < lenc[k] ? 0 : 1) | (t == lenc[k] - 1 ? 2 : 0);
+                P.mulb[b] = bone ? 0.f : c0[k] / c1[k];
+                P.addb[b] = bone ? 1.f : 0.f;
+                P.rcm1[b] = (t > 0 && t < lenc[k]) ? 1.0f / cm[k] : 0.f;
+                P.lastf[b] = (t == lenc[k] - 1) ? 1.f : 0.f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->prep_full[h][buf]);
+        }
+    } else {
+        // ------------------------------------------------ compute warps (q, h, c): thread = state i, 32 sequences
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int q = warp & 3, h = (warp >> 2) & 1, c = warp >> 3;
+        const int pq = 2 * h + c;       // this warp's pipeline
+        const int i = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        // byte offset of element (b, i) inside a half (b = sequence within the half, b = 32c + k):
+        //   W, MN-major 32-byte atoms:            b * 128 + (mbase ^ ((b & 3) << 5))
+        //   V tf32, K-major SWIZZLE_128B:         b * 128 + (kbase ^ ((b & 7) << 4))
+        //   V bf16 pair (i even, i + 1), K-major: b * 128 + ((c16 ^ (b & 7)) << 4) + hbase   (+ 2 * BW_HSUB for the lo half)
+        const uint32_t mbase = q * BW_HSUB + ((lane >> 3) << 5) + ((lane & 7) << 2);
+        const uint32_t kbase = q * BW_HSUB + ((lane >> 2) << 4) + ((lane & 3) << 2);
+        const uint32_t c16 = 4 * (q & 1) + (lane >> 3);
+        const uint32_t hbase = (q >> 1) * BW_HSUB + 2 * (lane & 6);
+        unsigned char *vk_c = sV + h * BW_HTILE + 32 * c * 128;       // this warp's 32 sequences of the V tile
+        float *tabr = out.tab + (size_t)(blockIdx.x % BW_REPL) * (size_t)(M + 2) * BW_N;
+        float *tab0 = tabr + i;
+        const float *Bi = Bsm + i;
+        float e[32];
+        if (gtotal) {
+            mbar_wait(&bars->prep_full[h][0], 0);
+            const Bwd3Prep &P0 = prep[h * BW3_PREP];
+#pragma unroll
+            for (int k4 = 0; k4 < 8; k4++) {
+                const uint4 s4 = *reinterpret_cast<const uint4 *>(P0.roff + 32 * c + 4 * k4);
+                e[4 * k4] = __ldg(addr_f32(Bi, s4.x));
+                e[4 * k4 + 1] = __ldg(addr_f32(Bi, s4.y));
+                e[4 * k4 + 2] = __ldg(addr_f32(Bi, s4.z));
+                e[4 * k4 + 3] = __ldg(addr_f32(Bi, s4.w));
+            }
+        }
+        uint32_t nd = 0, g = 0, ntile = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ntile++) {
+            float glast = 0.f;     // gamma_ref[i] summed over the (sequence, last step) pairs of this tile with t > 0
+            for (int t = Ti - 1; t >= 0; t--, g++) {
+                const bool has_mma = (t <= Ti - 2);
+                const int buf = g & 1;
+                const int pb = g % BW3_PREP, pbn = (g + 1) % BW3_PREP;
+                const Bwd3Prep &P = prep[h * BW3_PREP + pb];
+                const Bwd3Prep &Pn = prep[h * BW3_PREP + pbn];
+                const bool has_next = g + 1 < gtotal;
+                mbar_wait(&bars->prep_full[h][pb], (g / BW3_PREP) & 1);
+                if (warp == 0) BW2_TRACE(8);
+                if (has_mma) {
+                    mbar_wait(&bars->d1_full[pq], nd & 1);
+                    nd++;
+                    tc_fence_after();
+                }
+                if (warp == 0) BW2_TRACE(10);
+                if (warp == 4) BW2_TRACE(24);
+                mbar_wait(&bars->w_full[h][buf], (g >> 1) & 1);
+                if (warp == 0) BW2_TRACE(9);
+                if (has_next) mbar_wait(&bars->prep_full[h][pbn], ((g + 1) / BW3_PREP) & 1);   // long complete: three steps of slack
+                if (warp == 0) BW2_TRACE(11);
+                const unsigned char *w_c = sW + (h * 2 + buf) * BW_HTILE + 32 * c * 128;
+                // D1^T of this step comes out of region R[g & 1] and V2^T of this step goes back IN PLACE, four columns at a time;
+                // MMA2 of this step reads the other region (the previous step's V2^T), so no write-after-read wait is needed
+                const uint32_t t_d1 = tmem + lane_base + ((g & 1) ? C3_R1 : C3_R0) + 64 * h + 32 * c;
+                // Straight-line body over 8 groups of four sequences.  D1 comes out of TMEM and V2 goes back four columns at
+                // a time: holding all 32 of each in registers spilled (ncu: the local-memory reloads missed L1 -- shared memory
+                // takes it all -- and their L2 latency sat on every warp's dependency chain, 7,000 cycles per step).
+                auto body = [&](auto t0c, auto mmac) {
+                    constexpr bool T0 = decltype(t0c)::value;
+                    constexpr bool MMA = decltype(mmac)::value;
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; k4++) {
+                        const int bq = 32 * c + 4 * k4;
+                        uint32_t d4[4] = {0u, 0u, 0u, 0u};      // t = T-1: beta = 0 * 0 + 1
+                        if (MMA) tmem_ld_32x4(t_d1 + 4 * k4, d4);
+                        const float4 m4 = *reinterpret_cast<const float4 *>(P.mulb + bq);
+                        const float4 a4 = *reinterpret_cast<const float4 *>(P.addb + bq);
+                        const float4 r4 = *reinterpret_cast<const float4 *>(P.rcm1 + bq);
+                        const float4 l4 = *reinterpret_cast<const float4 *>(P.lastf + bq);
+                        const uint4 s4 = *reinterpret_cast<const uint4 *>(P.roff + bq);
+                        const float mu4[4] = {m4.x, m4.y, m4.z, m4.w};
+                        const float ad4[4] = {a4.x, a4.y, a4.z, a4.w};
+                        const float rc4[4] = {r4.x, r4.y, r4.z, r4.w};
+                        const float lf4[4] = {l4.x, l4.y, l4.z, l4.w};
+                        const uint32_t sy4[4] = {s4.x, s4.y, s4.z, s4.w};
+                        float w4[4], v4[4];
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            const int kb = 4 * k4 + kk;       // sequence within this warp's 32 (kb & 7 == b & 7, kb & 3 == b & 3)
+                            w4[kk] = *reinterpret_cast<const float *>(w_c + kb * 128 + (mbase ^ ((kb & 3) << 5)));
+                        }
+                        if (MMA) tmem_ld_wait();
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            const int kb = 4 * k4 + kk;
+                            // beta = D1 / c_{t+1}, or 1 on the sequence's last step and in its padding
+                            const float beta = fmaf(__uint_as_float(d4[kk]), mu4[kk], ad4[kk]);
+                            const float gm = w4[kk] * beta;       // gamma_ref: 0 for dead (sequence, step) pairs (zero stash row)
+                            // V2_t = b(o_t) beta_t / c_{t-1}: the operand of MMA1(t-1) (shared memory) AND of MMA2(t-1) (TMEM)
+                            const float v = (e[kb] * beta) * rc4[kk];
+                            v4[kk] = v;
+                            d4[kk] = tf32_bits(v);
+                            if (!T0) {
+                                red_add_f32_nc(addr_f32(tab0, sy4[kk]), gm);
+                                glast = fmaf(gm, lf4[kk], glast);
+                                if (!SPLIT) *reinterpret_cast<uint32_t *>(vk_c + kb * 128 + (kbase ^ ((kb & 7) << 4))) = d4[kk];
+                            } else {
+                                // t = 0: gamma_ref goes where V would (this quarter's own rows of the tile, fp32, the
+                                // tf32 tile's addressing) for the smoothing pass below
+                                *reinterpret_cast<float *>(vk_c + kb * 128 + (kbase ^ ((kb & 7) << 4))) = gm;
+                            }
+                        }
+                        if (!T0) tmem_st_32x4(t_d1 + 4 * k4, d4);
+                        if (SPLIT && !T0) {
+                            // even lanes take the state pair (i, i+1) of sequence b, odd lanes the pair (i-1, i) of sequence b+1
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk += 2) {
+                                const int kb = 4 * k4 + kk;
+                                const float mine = (lane & 1) ? v4[kk] : v4[kk + 1];
+                                const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                                const float p0 = (lane & 1) ? other : v4[kk];
+                                const float p1 = (lane & 1) ? v4[kk + 1] : other;
+                                uint32_t hi, lo;
+                                split_bf16x2(p0, p1, hi, lo);
+                                const uint32_t offA = kb * 128 + ((c16 ^ (kb & 7)) << 4);
+                                const uint32_t offB = (kb + 1) * 128 + ((c16 ^ ((kb + 1) & 7)) << 4);
+                                unsigned char *dst = vk_c + hbase + ((lane & 1) ? offB : offA);
+                                *reinterpret_cast<uint32_t *>(dst) = hi;
+                                *reinterpret_cast<uint32_t *>(dst + 2 * BW_HSUB) = lo;
+                            }
+                        }
+                        // the emission values of the next step (the next tile's first step after t = 0), these 4 sequences
+                        if (has_next) {
+                            const uint4 n4 = *reinterpret_cast<const uint4 *>(Pn.roff + bq);
+                            e[4 * k4] = __ldg(addr_f32(Bi, n4.x));
+                            e[4 * k4 + 1] = __ldg(addr_f32(Bi, n4.y));
+                            e[4 * k4 + 2] = __ldg(addr_f32(Bi, n4.z));
+                            e[4 * k4 + 3] = __ldg(addr_f32(Bi, n4.w));
+                        }
+                    }
+                };
+                const bool t0 = (t == 0);
+                if (!t0) {
+                    if (has_mma) body(std::false_type{}, std::true_type{});
+                    else body(std::false_type{}, std::false_type{});
+                } else {
+                    if (has_mma) body(std::true_type{}, std::true_type{});
+                    else body(std::true_type{}, std::false_type{});
+                }
+                if (warp == 0) BW2_TRACE(14);
+                // W_t has been read: hand the buffer back (t = T-1 has no MMA2: its arrival is made here as well)
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&bars->w_empty[h][buf]);
+                    if (!has_mma && q == 0) mbar_arrive(&bars->w_empty[h][buf]);
+                }
+                if (!t0) {
+                    tmem_st_wait();
+                    fence_proxy_async();          // V is read by the tensor core through the async proxy
+                    tc_fence_before();
+                    mbar_arrive(&bars->v_ready[pq]);
+                    if (warp == 0) BW2_TRACE(12);
+                    if (warp == 4) BW2_TRACE(26);
+                } else {
+                    // t = 0: pi_new = smooth1d(gamma[0]) per sequence (util.py:56-60); the smoothed row counts for pi AND for
+                    // the emission numerators (the reference overwrites gamma[0] in place, discrete_hmm.py:132).  The gamma
+                    // rows of the half sit in its V buffer (no V_0 is formed); warp (q, c) takes 8 sequences.
+                    named_bar_sync(1 + h, 256);
+                    const unsigned char *scr = sV + h * BW_HTILE + (lane >> 3) * BW_HSUB;     // states 4 lane .. 4 lane + 3
+#pragma unroll 1
+                    for (int k = 0; k < 8; k++) {
+                        const int b = 8 * (q + 4 * c) + k;
+                        const float4 f = *reinterpret_cast<const float4 *>(scr + b * 128 + (((lane & 7) ^ (b & 7)) << 4));
+                        const uint32_t sy = P.roff[b];
+                        const int fl = P.flag[b];
+                        const bool live = !(fl & 1);
+                        const bool lastrow = (fl & 2) != 0;
+                        int cnt = (f.x < 1e-10f) + (f.y < 1e-10f) + (f.z < 1e-10f) + (f.w < 1e-10f);
+                        cnt = __reduce_add_sync(0xffffffffu, cnt);
+                        if (cnt >= BW_N) {
+                            if (live && lane == 0) atomicAdd(out.flags, 1.0);
+                            cnt = BW_N - 1;
+                        }
+                        const float sub = (float)((double)cnt * 1e-10 / (double)(BW_N - cnt));
+                        const float floorv = 1e-10f;
+                        const float x0 = fmaxf(f.x - sub, floorv), x1 = fmaxf(f.y - sub, floorv),
+                                    x2 = fmaxf(f.z - sub, floorv), x3 = fmaxf(f.w - sub, floorv);
+                        const float inv = 1.0f / warp_sum((x0 + x1) + (x2 + x3));
+                        if (live) {
+                            float *row = tabr + 4 * lane;
+                            red_add_v4_nc(row + sy, x0 * inv, x1 * inv, x2 * inv, x3 * inv);
+                            red_add_v4_nc(row + (size_t)M * BW_N, x0 * inv, x1 * inv, x2 * inv, x3 * inv);
+                            if (lastrow) red_add_v4_nc(row + (size_t)(M + 1) * BW_N, x0 * inv, x1 * inv, x2 * inv, x3 * inv);
+                        }
+                    }
+                    red_add_f32_nc(tab0 + (size_t)(M + 1) * BW_N, glast);
+                    named_bar_sync(1 + h, 256);     // the next tile's first step writes V into this buffer
+                    if (Ti > 1 && h == 0) {
+                        // tile done: Xi^T[j][i'] (lane = j = this thread's state) -> float64 counts xi[i'][j], coalesced over j;
+                        // warp (q, c) takes the columns i' in [64c, 64c + 64)
+                        mbar_wait(&bars->xi_done, ntile & 1);
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int c0 = 64 * c; c0 < 64 * c + 64; c0 += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(tmem + lane_base + C3_XI + c0, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int x = 0; x < 32; x++)
+                                atomicAdd(out.xi + (c0 + x) * BW_N + i, (double)__uint_as_float(v[x]));
+                        }
+                        tc_fence_before();
+                        mbar_arrive(&bars->xi_free);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->prep_empty[h][pb]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) tmem_dealloc(tmem, 512);
+}
+
 // Fold the fp32 table replicas into the float64 count buffer:
 //   emis_num[k][i] += sum_r tab[r][k][i];  emis_den[i] += sum_k (that);  pi[i] += row M;
 //   gam[i] += emis_den part - row M+1 (gamma_ref summed over t < T-1);  loglik, nseq.
@@ -1340,7 +1835,10 @@ struct BwWorkspace {
 // thread-per-state kernel (bw_backward_tc2_kernel).  Both produce the same statistics and run within 3 % of each other at
 // config-4 size (17.0-17.7 against 17.2-17.5 ms; DESIGN.md 3.5 has the resource budgets that bound both), so the older,
 // longer-tested one stays the default; $KHMM_BW_BACKWARD=2 or khmm_debug_bw_backward_version(2) selects the other.
-static int bw_backward_version() { return dev_switch(SW_BW_BACKWARD) == 2 ? 2 : 1; }
+static int bw_backward_version() {
+    const int v = dev_switch(SW_BW_BACKWARD);
+    return (v == 2 || v == 3) ? v : 1;
+}
 
 static BwWorkspace bw_layout(void *ws, int64_t B, int64_t T, int M) {
     auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
@@ -1361,7 +1859,8 @@ static BwWorkspace bw_layout(void *ws, int64_t B, int64_t T, int M) {
     return w;
 }
 
-static int make_tmap_stash(CUtensorMap *map, const float *stash, int64_t B, int64_t T, CUtensorMapSwizzle swz) {
+static int make_tmap_stash(CUtensorMap *map, const float *stash, int64_t B, int64_t T, CUtensorMapSwizzle swz,
+                           uint32_t box_rows = 128) {
     static PFN_encodeTiled encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -1372,7 +1871,7 @@ static int make_tmap_stash(CUtensorMap *map, const float *stash, int64_t B, int6
     // tile-major stash [ntiles * T][128 rows][128]
     cuuint64_t dims[3] = {(cuuint64_t)BW_N, 128, (cuuint64_t)((B + 127) / 128 * T)};
     cuuint64_t strides[2] = {(cuuint64_t)BW_N * 4, (cuuint64_t)128 * BW_N * 4};
-    cuuint32_t box[3] = {32, 128, 1};
+    cuuint32_t box[3] = {32, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)stash, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -1393,7 +1892,7 @@ int khmm_debug_bw_trace(int64_t *dev_buf) {
 }
 
 int khmm_debug_bw_backward_version(int version) {
-    KHMM_REQUIRE(version >= 0 && version <= 2, "debug_bw_backward_version: 0 (default), 1 or 2");
+    KHMM_REQUIRE(version >= 0 && version <= 3, "debug_bw_backward_version: 0 (default), 1, 2 or 3");
     return khmm_debug_switch("KHMM_BW_BACKWARD", version == 0 ? -1 : version);
 }
 
@@ -1531,7 +2030,23 @@ int khmm_estep_tc_discrete_ex_f32(int64_t B, int64_t T, int N, int M, const floa
         double *c_xi = counts + BW_N;
         double *c_tail = counts + BW_N + (size_t)BW_N * BW_N + BW_N + (size_t)M * BW_N + BW_N;
         BwdOut out{g_bw_trace, w.tab, c_xi, c_tail + 2};
-        if (operand_precision == KHMM_TC_BF16X3) {
+        if (bw_backward_version() == 3) {
+            KHMM_REQUIRE(M <= (1 << 22), "estep_tc: alphabet size %d exceeds 2^22", M);
+            CUtensorMap mapStashH;
+            if (make_tmap_stash(&mapStashH, w.stash, B, T, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 64)) {
+                set_error("estep_tc: tensor map creation failed");
+                return KHMM_ERR_CUDA;
+            }
+            size_t smem3 = 6 * (size_t)BW_HTILE + 2 * BW3_PREP * sizeof(Bwd3Prep) + sizeof(Bwd3Bars) + 1024;
+            if (split) {
+                KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_backward_tc3_kernel<KHMM_TC_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                bw_backward_tc3_kernel<KHMM_TC_BF16X3><<<grid, BW3_THREADS, smem3, st>>>(mapStashH, A, Bsm, ob, B, T, w.scale, out);
+            } else {
+                KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_backward_tc3_kernel<KHMM_TC_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                bw_backward_tc3_kernel<KHMM_TC_TF32><<<grid, BW3_THREADS, smem3, st>>>(mapStashH, w.Ar, Bsm, ob, B, T, w.scale, out);
+            }
+            KHMM_LAUNCH_CHECK("bw_backward_tc3_kernel");
+        } else if (operand_precision == KHMM_TC_BF16X3) {
             bw_backward_tc_kernel<KHMM_TC_BF16X3><<<grid, 384, smem, st>>>(mapA, mapAlo, mapStash, Bsm, ob, B, T, w.scale, out);
             KHMM_LAUNCH_CHECK("bw_backward_tc_kernel<bf16x3>");
         } else if (bw_backward_version() == 1) {

@@ -157,6 +157,16 @@ __device__ __forceinline__ float unsplit_hi(uint32_t hi, uint32_t lo) {   // ele
     return __uint_as_float(hi & 0xffff0000u) + __uint_as_float(lo & 0xffff0000u);
 }
 
+// 32 lanes x 4 consecutive columns <-> 4 registers per thread
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread i = lane base + i)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
