@@ -1320,10 +1320,11 @@ struct __align__(16) Bwd3Prep {   // per-sequence scalars of one step of one hal
     uint32_t roff[64]; // 128 * clamped symbol: float offset of the table row o_t(b)
     float mulb[64];    // c_t / c_{t+1}, or 0 where beta_t = 1 (t >= len - 1: the sequence's last step or its padding):
                        // MMA1 runs on V2_{t+1} = V_{t+1} / c_t, so D1 = (A V_{t+1}) / c_t and beta_t = D1 c_t / c_{t+1}
-    float addb[64];    // 1 where mulb = 0, else 0:  beta = D1 * mulb + addb
     float rcm1[64];    // 1 / c_{t-1} for 0 < t < len, else 0 (V2_t = 0: the pair (t-1, t) does not count)
     float lastf[64];   // 1 on the sequence's last step (t = len - 1), else 0
     int flag[64];      // bit 0: (sequence, step) not live (a row past the batch, a step of the padding); bit 1: last step
+    int anylast;       // some sequence of the half has its last step here (the compute warps then read lastf)
+    int pad[3];
 };
 // base + off floats in one IMAD.WIDE (the compiler's LEA / IADD.X pair costs two issue slots per address)
 __device__ __forceinline__ float *addr_f32(const float *base, uint32_t off) {
@@ -1549,9 +1550,12 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
                 P.roff[b] = (uint32_t)(sy[k] * BW_N);
                 P.flag[b] = (t < lenc[k] ? 0 : 1) | (t == lenc[k] - 1 ? 2 : 0);
                 P.mulb[b] = bone ? 0.f : c0[k] / c1[k];
-                P.addb[b] = bone ? 1.f : 0.f;
                 P.rcm1[b] = (t > 0 && t < lenc[k]) ? 1.0f / cm[k] : 0.f;
                 P.lastf[b] = (t == lenc[k] - 1) ? 1.f : 0.f;
+            }
+            {
+                const unsigned any = __ballot_sync(0xffffffffu, (t == lenc[0] - 1) || (t == lenc[1] - 1));
+                if (lane == 0) P.anylast = any != 0u;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->prep_full[h][buf]);
@@ -1618,21 +1622,21 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
                 // Straight-line body over 8 groups of four sequences.  D1 comes out of TMEM and V2 goes back four columns at
                 // a time: holding all 32 of each in registers spilled (ncu: the local-memory reloads missed L1 -- shared memory
                 // takes it all -- and their L2 latency sat on every warp's dependency chain, 7,000 cycles per step).
-                auto body = [&](auto t0c, auto mmac) {
+                auto body = [&](auto t0c, auto mmac, auto lastc) {
                     constexpr bool T0 = decltype(t0c)::value;
                     constexpr bool MMA = decltype(mmac)::value;
+                    constexpr bool LAST = decltype(lastc)::value;     // some sequence of the half ends at this step
 #pragma unroll
                     for (int k4 = 0; k4 < 8; k4++) {
                         const int bq = 32 * c + 4 * k4;
                         uint32_t d4[4] = {0u, 0u, 0u, 0u};      // t = T-1: beta = 0 * 0 + 1
                         if (MMA) tmem_ld_32x4(t_d1 + 4 * k4, d4);
                         const float4 m4 = *reinterpret_cast<const float4 *>(P.mulb + bq);
-                        const float4 a4 = *reinterpret_cast<const float4 *>(P.addb + bq);
                         const float4 r4 = *reinterpret_cast<const float4 *>(P.rcm1 + bq);
-                        const float4 l4 = *reinterpret_cast<const float4 *>(P.lastf + bq);
+                        float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (LAST) l4 = *reinterpret_cast<const float4 *>(P.lastf + bq);
                         const uint4 s4 = *reinterpret_cast<const uint4 *>(P.roff + bq);
                         const float mu4[4] = {m4.x, m4.y, m4.z, m4.w};
-                        const float ad4[4] = {a4.x, a4.y, a4.z, a4.w};
                         const float rc4[4] = {r4.x, r4.y, r4.z, r4.w};
                         const float lf4[4] = {l4.x, l4.y, l4.z, l4.w};
                         const uint32_t sy4[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -1647,7 +1651,7 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
                         for (int kk = 0; kk < 4; kk++) {
                             const int kb = 4 * k4 + kk;
                             // beta = D1 / c_{t+1}, or 1 on the sequence's last step and in its padding
-                            const float beta = fmaf(__uint_as_float(d4[kk]), mu4[kk], ad4[kk]);
+                            const float beta = fmaf(__uint_as_float(d4[kk]), mu4[kk], mu4[kk] == 0.f ? 1.f : 0.f);
                             const float gm = w4[kk] * beta;       // gamma_ref: 0 for dead (sequence, step) pairs (zero stash row)
                             // V2_t = b(o_t) beta_t / c_{t-1}: the operand of MMA1(t-1) (shared memory) AND of MMA2(t-1) (TMEM)
                             const float v = (e[kb] * beta) * rc4[kk];
@@ -1655,7 +1659,7 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
                             d4[kk] = tf32_bits(v);
                             if (!T0) {
                                 red_add_f32_nc(addr_f32(tab0, sy4[kk]), gm);
-                                glast = fmaf(gm, lf4[kk], glast);
+                                if (LAST) glast = fmaf(gm, lf4[kk], glast);
                                 if (!SPLIT) *reinterpret_cast<uint32_t *>(vk_c + kb * 128 + (kbase ^ ((kb & 7) << 4))) = d4[kk];
                             } else {
                                 // t = 0: gamma_ref goes where V would (this quarter's own rows of the tile, fp32, the
@@ -1694,11 +1698,15 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
                 };
                 const bool t0 = (t == 0);
                 if (!t0) {
-                    if (has_mma) body(std::false_type{}, std::true_type{});
-                    else body(std::false_type{}, std::false_type{});
+                    if (P.anylast) {
+                        if (has_mma) body(std::false_type{}, std::true_type{}, std::true_type{});
+                        else body(std::false_type{}, std::false_type{}, std::true_type{});
+                    } else {
+                        body(std::false_type{}, std::true_type{}, std::false_type{});    // no last step here implies t < T-1
+                    }
                 } else {
-                    if (has_mma) body(std::true_type{}, std::true_type{});
-                    else body(std::true_type{}, std::false_type{});
+                    if (has_mma) body(std::true_type{}, std::true_type{}, std::false_type{});
+                    else body(std::true_type{}, std::false_type{}, std::false_type{});
                 }
                 if (warp == 0) BW2_TRACE(14);
                 // W_t has been read: hand the buffer back (t = T-1 has no MMA2: its arrival is made here as well)
@@ -1831,13 +1839,13 @@ struct BwWorkspace {
     size_t bytes;
 };
 
-// Which backward kernel: 1 = thread-per-sequence kernel (bw_backward_tc_kernel, the default), 2 = the transposed
-// thread-per-state kernel (bw_backward_tc2_kernel).  Both produce the same statistics and run within 3 % of each other at
-// config-4 size (17.0-17.7 against 17.2-17.5 ms; DESIGN.md 3.5 has the resource budgets that bound both), so the older,
-// longer-tested one stays the default; $KHMM_BW_BACKWARD=2 or khmm_debug_bw_backward_version(2) selects the other.
+// Which backward kernel: 3 = the transposed kernel with four quarter-tile pipelines (bw_backward_tc3_kernel, the default, both
+// operand precisions); 1 = the round-1 thread-per-sequence kernel (bw_backward_tc_kernel, both precisions); 2 = the first
+// transposed kernel (bw_backward_tc2_kernel, tf32 only).  All three produce the same statistics to rounding; the older ones
+// stay as cross-checks ($KHMM_BW_BACKWARD or khmm_debug_bw_backward_version select them).
 static int bw_backward_version() {
     const int v = dev_switch(SW_BW_BACKWARD);
-    return (v == 2 || v == 3) ? v : 1;
+    return (v == 1 || v == 2) ? v : 3;
 }
 
 static BwWorkspace bw_layout(void *ws, int64_t B, int64_t T, int M) {
