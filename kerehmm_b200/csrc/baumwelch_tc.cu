@@ -1784,6 +1784,426 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
     if (warp == 17) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------- forward, transposed, four quarter-tile pipelines (round 2)
+// The forward kernel above has the same weakness as the first backward kernels: one tile per CTA, MMA -> epilogue -> MMA in
+// series (3,700 cycles per step with tf32 operands, 5,000 with bf16 hi/lo pairs, against 2,600 for the stash write at the HBM
+// rate).  This kernel applies the structure of bw_backward_tc3_kernel to the forward recursion: TMEM lane = state, A^T a
+// resident TMEM operand, four quarter-tiles of 32 sequences as independent pipelines, sixteen compute warps,
+// emission values read straight from the table (coalesced, one step ahead).  Per quarter and step t:
+//     MMA_f(t)    D^T[j][b] = sum_i A^T[j][i] W_{t-1}[b][i]        M = 128 states, N = 32 sequences
+//     MMA_S(t-1)  S[.][b]   = sum_i 1 * W_{t-1}[b][i]              the row sum c_{t-1}(b), on EVERY TMEM lane: a thread owns
+//                                                                 one state, so the sum over states is a cross-thread
+//                                                                 reduction -- the tensor core does it with an all-ones A
+//                                                                 operand, and every thread reads c_{t-1} of its 32
+//                                                                 sequences next to D (no shuffles, no shared memory)
+//     threads     W_t[b][j] = D^T[j][b] b_j(o_t(b)) / c_{t-1}(b)   (t = 0: pi_j b_j(o_0)); row sum = c_t as before
+//                 -> operand tile in shared memory (K-major, tf32-rounded or bf16 hi/lo) for MMA_f(t+1) and MMA_S(t)
+//                 -> fp32 stash tile in shared memory (zeros for t >= len) -> TMA tensor store, two buffers per quarter
+// c_{t-1} is the sum of the operand the recursion actually multiplies (rounded), i.e. the exact normaliser of what the
+// tensor core sees.  The scale factors go to HBM from one thread per quarter (16-byte stores); log P is summed from them
+// afterwards by bw_loglik_kernel (mantissa product + exponent sum, no log per step).
+// TMEM: A^T (tf32 128 columns / bf16 hi | lo 2 x 64), ones (128 / 64), D^T 4 x 32, S 4 x 32.
+constexpr uint32_t F3_AT = 0, F3_ONE = 128, F3_D = 256, F3_S = 384;
+struct __align__(8) Fwd3Bars {
+    uint64_t v_ready[4], d_full[4], s_full[4], s_free[4][2], prep_full[2][BW3_PREP], prep_empty[2][BW3_PREP];
+    uint32_t tmem_base;
+};
+struct __align__(16) Fwd3Prep {   // per-sequence scalars of one step of one half
+    uint32_t roff[64];  // 128 * clamped symbol: float offset of the table row o_t(b)
+    float livef[64];    // 1 for t < len (a live (sequence, step) pair), else 0: the stash row is zero there
+    int alllive;        // every sequence of the half is live at this step (the compute warps then skip livef)
+    int pad[3];
+};
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void bulk_wait_read4() { asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); }
+
+template <int PREC>
+__global__ void __launch_bounds__(BW3_THREADS, 1)
+bw_forward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashQ, const float *__restrict__ ATmat,
+                      const float *__restrict__ pi, const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T,
+                      float *__restrict__ scale, long long *trace) {
+    constexpr bool SPLIT = PREC != KHMM_TC_TF32;
+#define F3_TRACE(ev)                                                                                      \
+    do {                                                                                                  \
+        if (trace && blockIdx.x == 0 && tile == blockIdx.x && t >= 8 && t < 16 && (threadIdx.x & 31) == 0) \
+            trace[256 + (t - 8) * 32 + (ev)] = clock64();                                                 \
+    } while (0)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *sOp = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [half][BW_HTILE] operand tiles
+    unsigned char *sSt = sOp + 2 * BW_HTILE;                                             // [half][buffer][BW_HTILE] stash tiles
+    Fwd3Prep *prep = (Fwd3Prep *)(sSt + 4 * BW_HTILE);                                   // [half][BW3_PREP]
+    Fwd3Bars *bars = (Fwd3Bars *)(prep + 2 * BW3_PREP);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (B + 127) / 128;
+    const int Ti = (int)T;
+    const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const uint32_t gtotal = (uint32_t)(my_tiles * Ti);     // compute steps of this CTA (all its tiles)
+
+    if (threadIdx.x == 0) {
+        for (int h = 0; h < 2; h++)
+            for (int k = 0; k < BW3_PREP; k++) {
+                mbar_init(&bars->prep_full[h][k], 1);
+                mbar_init(&bars->prep_empty[h][k], 8);
+            }
+        for (int pq = 0; pq < 4; pq++) {
+            mbar_init(&bars->v_ready[pq], 128);
+            mbar_init(&bars->d_full[pq], 1);
+            mbar_init(&bars->s_full[pq], 128);
+            mbar_init(&bars->s_free[pq][0], 1);
+            mbar_init(&bars->s_free[pq][1], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 17) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    if (warp < 8) {
+        // A^T, row j -> TMEM lane j, resident for the whole kernel: warp (q, hh) stores columns [64hh, 64hh+64)
+        const int q = warp & 3, hh = warp >> 2;
+        const int j = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        if (SPLIT) {
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int p = 0; p < 16; p++) {
+                float4 f = ldg4(ATmat + (size_t)j * BW_N + 64 * hh + 4 * p);
+                split_bf16x2(f.x, f.y, hi[2 * p], lo[2 * p]);
+                split_bf16x2(f.z, f.w, hi[2 * p + 1], lo[2 * p + 1]);
+            }
+            tmem_st_32x32(tmem + lane_base + F3_AT + 32 * hh, hi);
+            tmem_st_32x32(tmem + lane_base + F3_AT + 64 + 32 * hh, lo);
+        } else {
+#pragma unroll 1
+            for (int c0 = 64 * hh; c0 < 64 * hh + 64; c0 += 32) {
+                uint32_t a[32];
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    float4 f = ldg4(ATmat + (size_t)j * BW_N + c0 + 4 * p);
+                    a[4 * p] = __float_as_uint(f.x); a[4 * p + 1] = __float_as_uint(f.y);
+                    a[4 * p + 2] = __float_as_uint(f.z); a[4 * p + 3] = __float_as_uint(f.w);
+                }
+                tmem_st_32x32(tmem + lane_base + F3_AT + c0, a);
+            }
+        }
+        tmem_st_wait();
+    } else if (warp < 12) {
+        // the all-ones operand of the row-sum MMA (tf32: 128 columns of 1.0f; bf16: 64 columns of the pair (1.0, 1.0))
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t o[32];
+#pragma unroll
+        for (int p = 0; p < 32; p++) o[p] = SPLIT ? 0x3f803f80u : 0x3f800000u;
+#pragma unroll 1
+        for (int c0 = 0; c0 < (SPLIT ? 64 : 128); c0 += 32) tmem_st_32x32(tmem + lane_base + F3_ONE + c0, o);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 16) {
+        // ------------------------------------------------ stash storer: one thread, the four quarters in turn.  (A compute
+        // thread issuing its quarter's stores held its whole warp -- and with it the quarter -- for 2,500 cycles per step.)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (elect_one()) {
+            tma_prefetch_desc(&mapStashQ);
+            uint32_t g = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int t = 0; t < Ti; t++, g++) {
+                    const int sbuf = g & 1;
+#pragma unroll 1
+                    for (int pq = 0; pq < 4; pq++) {
+                        const int h = pq >> 1, c = pq & 1;
+                        mbar_wait(&bars->s_full[pq], g & 1);
+                        // the quarter's stash tile is complete: four TMA tensor stores (one per 32-column sub-tile)
+                        const unsigned char *src = sSt + (h * 2 + sbuf) * BW_HTILE + 4096 * c;
+                        for (int cc = 0; cc < 4; cc++)
+                            tma_store_3d(&mapStashQ, src + cc * BW_HSUB, cc * 32, 64 * h + 32 * c, (int)(tile * T + t));
+                        bulk_commit();
+                        if (pq == 0) F3_TRACE(13);
+                        if (g >= 1) {
+                            bulk_wait_read4();      // all but the last four groups (one per quarter) have read their buffers:
+                            mbar_arrive(&bars->s_free[pq][sbuf ^ 1]);      // this quarter's store of step g-1 among them
+                        }
+                    }
+                }
+            bulk_wait0();
+        }
+    } else if (warp == 17) {
+        // ------------------------------------------------ MMA issuer: the four quarters in turn
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (elect_one()) {
+            const uint32_t idesc = SPLIT ? make_idesc_bf16(128, 32) : make_idesc_tf32(128, 32);
+            const uint64_t dV0 = make_kmajor_sw128_desc(sOp), dV1 = make_kmajor_sw128_desc(sOp + BW_HTILE);
+            uint32_t nv = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int t = 0; t < Ti; t++, nv++) {
+#pragma unroll
+                    for (int pq = 0; pq < 4; pq++) {
+                        const int h = pq >> 1, c = pq & 1;
+                        mbar_wait(&bars->v_ready[pq], nv & 1);
+                        F3_TRACE(pq == 0 ? 0 : (pq == 2 ? 2 : 31));
+                        tc_fence_after();
+                        uint64_t dvb = desc_advance(h ? dV1 : dV0, 4096 * c);     // rows 32c.. of the half's operand tile
+                        asm volatile("" : "+l"(dvb));      // keeps the per-instruction descriptors out of registers across steps
+                        const uint32_t scol = tmem + F3_S + 32 * pq, dcol = tmem + F3_D + 32 * pq;
+                        // MMA_S(t): c_t = the row sums of W_t
+                        if (SPLIT) {
+#pragma unroll
+                            for (int pass = 0; pass < 2; pass++)
+#pragma unroll
+                                for (int k = 0; k < 8; k++)
+                                    mma_bf16_ts(scol, tmem + F3_ONE + k * 8,
+                                                desc_advance(dvb, (pass ? 2 * BW_HSUB : 0) + (k >> 2) * BW_HSUB + (k & 3) * 32), idesc,
+                                                (pass | k) != 0);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; k++)
+                                mma_tf32_ts(scol, tmem + F3_ONE + k * 8, desc_advance(dvb, (k >> 2) * BW_HSUB + (k & 3) * 32), idesc,
+                                            k != 0);
+                        }
+                        // MMA_f(t+1): D^T = A^T . W_t^T
+                        if (t + 1 < Ti) {
+                            if (SPLIT) {
+                                // (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo)
+#pragma unroll
+                                for (int pass = 0; pass < 3; pass++) {
+                                    const uint32_t acol = tmem + F3_AT + (pass == 1 ? 64 : 0);
+#pragma unroll
+                                    for (int k = 0; k < 8; k++)
+                                        mma_bf16_ts(dcol, acol + k * 8,
+                                                    desc_advance(dvb, (pass == 2 ? 2 * BW_HSUB : 0) + (k >> 2) * BW_HSUB + (k & 3) * 32),
+                                                    idesc, (pass | k) != 0);
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 16; k++)
+                                    mma_tf32_ts(dcol, tmem + F3_AT + k * 8, desc_advance(dvb, (k >> 2) * BW_HSUB + (k & 3) * 32), idesc,
+                                                k != 0);
+                            }
+                        }
+                        tc_commit(&bars->d_full[pq]);
+                        F3_TRACE(pq == 0 ? 1 : (pq == 2 ? 3 : 31));
+                    }
+                }
+        }
+    } else if (warp >= 18) {
+        // ------------------------------------------------ prep (one warp per half): table row and liveness, up to three steps ahead
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        const int h = warp - 18;
+        int64_t bc[2] = {0, 0};
+        int len[2] = {0, 0};
+        int syn[2] = {0, 0}, lenn[2] = {0, 0};
+        auto issue = [&](uint32_t gg) {      // the symbol loads of step gg
+            const int64_t tile = blockIdx.x + (int64_t)(gg / Ti) * gridDim.x;
+            const int t = (int)(gg % Ti);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                if (t == 0) {      // first step of a tile: this lane's sequences change
+                    const int64_t gb = tile * 128 + 64 * h + lane + 32 * k;
+                    bc[k] = gb < B ? gb : B - 1;
+                    len[k] = gb < B ? ob.len(gb) : 0;
+                }
+                syn[k] = ob.sym(bc[k], t);
+                lenn[k] = len[k];
+            }
+        };
+        if (gtotal) issue(0);
+        for (uint32_t g = 0; g < gtotal; g++) {
+            const int t = (int)(g % Ti);
+            int sy[2], lenc[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) { sy[k] = syn[k]; lenc[k] = lenn[k]; }
+            if (g + 1 < gtotal) issue(g + 1);
+            const int buf = g % BW3_PREP;
+            mbar_wait(&bars->prep_empty[h][buf], ((g / BW3_PREP) & 1) ^ 1);
+            Fwd3Prep &P = prep[h * BW3_PREP + buf];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int b = lane + 32 * k;
+                P.roff[b] = (uint32_t)(sy[k] * BW_N);
+                P.livef[b] = t < lenc[k] ? 1.f : 0.f;
+            }
+            {
+                const unsigned dead = __ballot_sync(0xffffffffu, (t >= lenc[0]) || (t >= lenc[1]));
+                if (lane == 0) P.alllive = dead == 0u;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->prep_full[h][buf]);
+        }
+    } else {
+        // ------------------------------------------------ compute warps (q, h, c): thread = state j, 32 sequences
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int q = warp & 3, h = (warp >> 2) & 1, c = warp >> 3;
+        const int pq = 2 * h + c;
+        const int j = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        // byte offsets inside a half tile as in bw_backward_tc3_kernel (element (b, j), b = 32c + kb)
+        const uint32_t kbase = q * BW_HSUB + ((lane >> 2) << 4) + ((lane & 3) << 2);
+        const uint32_t c16 = 4 * (q & 1) + (lane >> 3);
+        const uint32_t hbase = (q >> 1) * BW_HSUB + 2 * (lane & 6);
+        unsigned char *op_c = sOp + h * BW_HTILE + 32 * c * 128;        // this warp's 32 rows of the operand tile
+        const float *Bj = Bsm + j;
+        const float pij = __ldg(pi + j);
+        const uint32_t t_d = tmem + lane_base + F3_D + 32 * pq, t_s = tmem + lane_base + F3_S + 32 * pq;
+        const bool issuer = (q == 0 && lane == 0);       // this quarter's TMA-store and scale-factor thread
+        float e[32];
+        if (gtotal) {
+            mbar_wait(&bars->prep_full[h][0], 0);
+            const Fwd3Prep &P0 = prep[h * BW3_PREP];
+#pragma unroll
+            for (int k4 = 0; k4 < 8; k4++) {
+                const uint4 s4 = *reinterpret_cast<const uint4 *>(P0.roff + 32 * c + 4 * k4);
+                e[4 * k4] = __ldg(addr_f32(Bj, s4.x));
+                e[4 * k4 + 1] = __ldg(addr_f32(Bj, s4.y));
+                e[4 * k4 + 2] = __ldg(addr_f32(Bj, s4.z));
+                e[4 * k4 + 3] = __ldg(addr_f32(Bj, s4.w));
+            }
+        }
+        uint32_t nd = 0, g = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int t = 0; t <= Ti; t++) {
+                const bool has_prev = t >= 1;           // S(t-1) -- and D(t) for t < T -- are due
+                float *sc_out = scale + (tile * T + (t - 1)) * 128 + 64 * h + 32 * c;
+                if (t == Ti) {
+                    // after the last step: only the scale factors c_{T-1}
+                    mbar_wait(&bars->d_full[pq], nd & 1);
+                    nd++;
+                    tc_fence_after();
+                    if (q == 0) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 8; k4++) {
+                            uint32_t s4[4];
+                            tmem_ld_32x4(t_s + 4 * k4, s4);
+                            tmem_ld_wait();
+                            if (lane == 0)
+                                *reinterpret_cast<uint4 *>(sc_out + 4 * k4) = make_uint4(s4[0], s4[1], s4[2], s4[3]);
+                        }
+                    }
+                    tc_fence_before();
+                    break;
+                }
+                const int pb = g % BW3_PREP, pbn = (g + 1) % BW3_PREP;
+                const Fwd3Prep &P = prep[h * BW3_PREP + pb];
+                const Fwd3Prep &Pn = prep[h * BW3_PREP + pbn];
+                const bool has_next = g + 1 < gtotal;
+                const int sbuf = g & 1;
+                mbar_wait(&bars->prep_full[h][pb], (g / BW3_PREP) & 1);
+                if (warp == 0) F3_TRACE(8);
+                if (has_prev) {
+                    mbar_wait(&bars->d_full[pq], nd & 1);
+                    nd++;
+                    tc_fence_after();
+                }
+                if (warp == 0) F3_TRACE(9);
+                if (warp == 4) F3_TRACE(14);
+                mbar_wait(&bars->s_free[pq][sbuf], ((g >> 1) & 1) ^ 1);     // the store of step g-2 has read this buffer
+                if (warp == 0) F3_TRACE(10);
+                if (has_next) mbar_wait(&bars->prep_full[h][pbn], ((g + 1) / BW3_PREP) & 1);
+                unsigned char *st_c = sSt + (h * 2 + sbuf) * BW_HTILE + 32 * c * 128;   // this warp's 32 rows of the stash tile
+                auto body = [&](auto firstc, auto livec) {
+                    constexpr bool FIRST = decltype(firstc)::value;       // t = 0: W_0 = pi . b(o_0)
+                    constexpr bool ALLLIVE = decltype(livec)::value;
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; k4++) {
+                        const int bq = 32 * c + 4 * k4;
+                        uint32_t d4[4], s4[4];
+                        if (!FIRST) {
+                            tmem_ld_32x4(t_d + 4 * k4, d4);
+                            tmem_ld_32x4(t_s + 4 * k4, s4);
+                        }
+                        float4 l4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (!ALLLIVE) l4 = *reinterpret_cast<const float4 *>(P.livef + bq);
+                        const float lf4[4] = {l4.x, l4.y, l4.z, l4.w};
+                        if (!FIRST) tmem_ld_wait();
+                        float x4[4];
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            const int kb = 4 * k4 + kk;
+                            const float x = FIRST ? pij * e[kb] : (__uint_as_float(d4[kk]) * e[kb]) * rcp_approx(__uint_as_float(s4[kk]));
+                            x4[kk] = x;
+                            const uint32_t off = kb * 128 + (kbase ^ ((kb & 7) << 4));
+                            if (!SPLIT) *reinterpret_cast<uint32_t *>(op_c + off) = tf32_bits(x);
+                            // the stash row of a dead (sequence, step) pair is zero (the recursion itself runs on)
+                            *reinterpret_cast<float *>(st_c + off) = ALLLIVE ? x : x * lf4[kk];
+                        }
+                        if (SPLIT) {
+                            // even lanes take the state pair (j, j+1) of sequence b, odd lanes the pair (j-1, j) of sequence b+1
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk += 2) {
+                                const int kb = 4 * k4 + kk;
+                                const float mine = (lane & 1) ? x4[kk] : x4[kk + 1];
+                                const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                                const float p0 = (lane & 1) ? other : x4[kk];
+                                const float p1 = (lane & 1) ? x4[kk + 1] : other;
+                                uint32_t hi, lo;
+                                split_bf16x2(p0, p1, hi, lo);
+                                const uint32_t offA = kb * 128 + ((c16 ^ (kb & 7)) << 4);
+                                const uint32_t offB = (kb + 1) * 128 + ((c16 ^ ((kb + 1) & 7)) << 4);
+                                unsigned char *dst = op_c + hbase + ((lane & 1) ? offB : offA);
+                                *reinterpret_cast<uint32_t *>(dst) = hi;
+                                *reinterpret_cast<uint32_t *>(dst + 2 * BW_HSUB) = lo;
+                            }
+                        }
+                        if (!FIRST && issuer) *reinterpret_cast<uint4 *>(sc_out + 4 * k4) = make_uint4(s4[0], s4[1], s4[2], s4[3]);
+                        // the emission values of the next step (the next tile's first step after t = T-1), these 4 sequences
+                        if (has_next) {
+                            const uint4 n4 = *reinterpret_cast<const uint4 *>(Pn.roff + bq);
+                            e[4 * k4] = __ldg(addr_f32(Bj, n4.x));
+                            e[4 * k4 + 1] = __ldg(addr_f32(Bj, n4.y));
+                            e[4 * k4 + 2] = __ldg(addr_f32(Bj, n4.z));
+                            e[4 * k4 + 3] = __ldg(addr_f32(Bj, n4.w));
+                        }
+                    }
+                };
+                if (!has_prev) {
+                    if (P.alllive) body(std::true_type{}, std::true_type{});
+                    else body(std::true_type{}, std::false_type{});
+                } else {
+                    if (P.alllive) body(std::false_type{}, std::true_type{});
+                    else body(std::false_type{}, std::false_type{});
+                }
+                if (warp == 0) F3_TRACE(11);
+                fence_proxy_async();          // both tiles are read through the async proxy (tensor core, TMA store)
+                tc_fence_before();
+                mbar_arrive(&bars->v_ready[pq]);
+                mbar_arrive(&bars->s_full[pq]);
+                if (warp == 0) F3_TRACE(12);
+                if (warp == 4) F3_TRACE(15);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->prep_empty[h][pb]);
+                __syncwarp();       // the tcgen05 loads of the next step are warp-collective
+                g++;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) tmem_dealloc(tmem, 512);
+}
+
+// log P of every sequence from the stored scale factors (tile-major [tile][t][row]): mantissa product + exponent sum, one
+// log per sequence
+static __global__ void bw_loglik_kernel(const float *__restrict__ scale, BwObs ob, int64_t B, int64_t T, double *__restrict__ loglik) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float *sc = scale + (b >> 7) * T * 128 + (b & 127);
+    const int len = ob.len(b);
+    float prod = 1.f;
+    int esum = 0;
+    for (int t = 0; t < len; t++) {
+        int ex;
+        prod = frexpf(prod * sc[(int64_t)t * 128], &ex);
+        esum += ex;
+    }
+    loglik[b] = (double)esum * 0.6931471805599453 + log((double)prod);
+}
+
 // Fold the fp32 table replicas into the float64 count buffer:
 //   emis_num[k][i] += sum_r tab[r][k][i];  emis_den[i] += sum_k (that);  pi[i] += row M;
 //   gam[i] += emis_den part - row M+1 (gamma_ref summed over t < T-1);  loglik, nseq.
@@ -2021,7 +2441,24 @@ int khmm_estep_tc_discrete_ex_f32(int64_t B, int64_t T, int N, int M, const floa
             }
         }
         if (tev) KHMM_CUDA_CHECK(cudaEventRecord(tev[0], st));
-        if (operand_precision == KHMM_TC_BF16X3)
+        if (dev_switch(SW_BW_FORWARD) == 3) {
+            KHMM_REQUIRE(M <= (1 << 22), "estep_tc: alphabet size %d exceeds 2^22", M);
+            CUtensorMap mapStashQ;
+            if (make_tmap_stash(&mapStashQ, w.stash, B, T, CU_TENSOR_MAP_SWIZZLE_128B, 32)) {
+                set_error("estep_tc: tensor map creation failed");
+                return KHMM_ERR_CUDA;
+            }
+            size_t smem3 = 6 * (size_t)BW_HTILE + 2 * BW3_PREP * sizeof(Fwd3Prep) + sizeof(Fwd3Bars) + 1024;
+            if (split) {
+                KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc3_kernel<KHMM_TC_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                bw_forward_tc3_kernel<KHMM_TC_BF16X3><<<grid, BW3_THREADS, smem3, st>>>(mapStashQ, AT, pi, Bsm, ob, B, T, w.scale, g_bw_trace);
+            } else {
+                KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc3_kernel<KHMM_TC_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                bw_forward_tc3_kernel<KHMM_TC_TF32><<<grid, BW3_THREADS, smem3, st>>>(mapStashQ, w.ATr, pi, Bsm, ob, B, T, w.scale, g_bw_trace);
+            }
+            KHMM_LAUNCH_CHECK("bw_forward_tc3_kernel");
+            bw_loglik_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(w.scale, ob, B, T, w.loglik);
+        } else if (operand_precision == KHMM_TC_BF16X3)
             bw_forward_tc_kernel<KHMM_TC_BF16X3><<<grid, 384, smem, st>>>(mapAT, mapATlo, mapStashSt, pi, Bsm, ob, B, T, w.scale,
                                                                           w.loglik, g_bw_trace);
         else
