@@ -117,7 +117,7 @@ __device__ __forceinline__ uint32_t tf32_bits(float x) { return (__float_as_uint
 constexpr int FW_EBUF = BW_TILE;   // one emission / stash staging buffer: 4 sub-tiles [128 rows][128 B], SWIZZLE_128B
 
 struct __align__(8) FwdBars {
-    uint64_t mat_full, a_ready, d_full, e_full[2], w_ready[2], buf_free[2];
+    uint64_t mat_full, a_ready, d_full[2], e_full[2], w_ready[2], buf_free[2];
     uint32_t tmem_base;
 };
 
@@ -178,7 +178,8 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
     if (threadIdx.x == 0) {
         mbar_init(&bars->mat_full, 1);
         mbar_init(&bars->a_ready, 256);
-        mbar_init(&bars->d_full, 1);
+        mbar_init(&bars->d_full[0], 1);
+        mbar_init(&bars->d_full[1], 1);
         for (int k = 0; k < 2; k++) {
             mbar_init(&bars->e_full[k], 64);
             mbar_init(&bars->w_ready[k], 256);
@@ -207,7 +208,9 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                 for (int kb = 0; kb < 4; kb++) tma_load_2d(tiles + kb * BW_SUB, &mapAT, &bars->mat_full, kb * 32, 0);
             }
             mbar_wait(&bars->mat_full, 0);
-            const uint32_t idesc = SPLIT ? make_idesc_bf16(128, 128) : make_idesc_tf32(128, 128);
+            // the MMA of a step is issued as two column halves (N = 64) with a commit each: the epilogue warps of columns
+            // 0-63 start while the tensor core still works on columns 64-127
+            const uint32_t idesc = SPLIT ? make_idesc_bf16(128, 64) : make_idesc_tf32(128, 64);
             uint32_t na = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
                 for (int64_t t = 1; t < T; t++) {
@@ -215,26 +218,30 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                     na++;
                     FW_TRACE(0);
                     tc_fence_after();
-                    if (SPLIT) {
-                        // (W_hi, A_hi), (W_hi, A_lo), (W_lo, A_hi): W_hi in TMEM columns [128,192), W_lo in [192,256)
 #pragma unroll
-                        for (int pass = 0; pass < NPASS; pass++) {
-                            const uint32_t acol = tmem + 128 + (pass == 2 ? 64 : 0);
-                            const unsigned char *bt = tiles + (pass == 1 ? 2 * BW_SUB : 0);
+                    for (int nh = 0; nh < 2; nh++) {
+                        // output columns [64nh, 64nh + 64) = rows 64nh.. of the K-major A^T tile (8 KB into every sub-tile)
+                        if (SPLIT) {
+                            // (W_hi, A_hi), (W_hi, A_lo), (W_lo, A_hi): W_hi in TMEM columns [128,192), W_lo in [192,256)
 #pragma unroll
-                            for (int k = 0; k < 8; k++) {
-                                uint64_t db = make_kmajor_sw128_desc(bt + (k >> 2) * BW_SUB);
-                                mma_bf16_ts(tmem, acol + k * 8, desc_advance(db, (k & 3) * 32), idesc, (pass | k) != 0);
+                            for (int pass = 0; pass < NPASS; pass++) {
+                                const uint32_t acol = tmem + 128 + (pass == 2 ? 64 : 0);
+                                const unsigned char *bt = tiles + (pass == 1 ? 2 * BW_SUB : 0) + nh * 8192;
+#pragma unroll
+                                for (int k = 0; k < 8; k++) {
+                                    uint64_t db = make_kmajor_sw128_desc(bt + (k >> 2) * BW_SUB);
+                                    mma_bf16_ts(tmem + 64 * nh, acol + k * 8, desc_advance(db, (k & 3) * 32), idesc, (pass | k) != 0);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; k++) {
+                                uint64_t db = make_kmajor_sw128_desc(tiles + (k >> 2) * BW_SUB + nh * 8192);
+                                mma_tf32_ts(tmem + 64 * nh, tmem + 128 + k * 8, desc_advance(db, (k & 3) * 32), idesc, k != 0);
                             }
                         }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            uint64_t db = make_kmajor_sw128_desc(tiles + (k >> 2) * BW_SUB);
-                            mma_tf32_ts(tmem, tmem + 128 + k * 8, desc_advance(db, (k & 3) * 32), idesc, k != 0);
-                        }
+                        tc_commit(&bars->d_full[nh]);
                     }
-                    tc_commit(&bars->d_full);
                     FW_TRACE(1);
                 }
         }
@@ -306,7 +313,7 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
                 const int cur = (int)(t & 1);
                 unsigned char *myrow = ebuf + cur * FW_EBUF + row * 128;
                 if (t > 0) {
-                    mbar_wait(&bars->d_full, nd & 1);
+                    mbar_wait(&bars->d_full[half], nd & 1);
                     nd++;
                     tc_fence_after();
                 }
