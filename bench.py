@@ -728,6 +728,9 @@ def run_ours(args):
     ctx.local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(ctx.local)
     ctx.dev = torch.device("cuda", ctx.local)
+    # the end-to-end leg copies from page-locked host buffers: keep them on the GPU's own NUMA node
+    from kerehmm_b200 import dist as _kdist
+    ctx.cpus = _kdist.bind_to_device_cpus(ctx.local)
     if ctx.world > 1:
         import datetime
         # a protocol bug must fail the run within minutes, not sit in a collective until the default 10-minute watchdog
@@ -741,6 +744,7 @@ def run_ours(args):
     steps = args.steps
     out = measure(w, ctx, steps, args.warmup, pk, sample_clocks=True)
     if out is not None:
+        out["e2e"]["host_cpu_binding"] = ("%d cores local to the GPU (NVML affinity)" % len(ctx.cpus)) if ctx.cpus else "none"
         if check is not None:
             out["multi_gpu_check"] = check
         if kind == "c4":

@@ -43,6 +43,36 @@ def shard_bounds(n_sequences: int, rank: int = None, world_size: int = None):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def bind_to_device_cpus(device: int = None):
+    """Pin this process to the CPU cores NVML reports as local to `device` (its NUMA node), so that page-locked host
+    buffers allocated afterwards -- first touch -- sit next to the GPU's PCIe root.  With 4-8 ranks per box the pinned
+    host -> device copy of an unbound process ran at half rate (2.4 -> 4.6 ms for 134 MB, round-1 scaling run): half
+    the ranks' buffers were on the other socket.  Returns the core list, or None when NVML / the affinity call is
+    unavailable (nothing is changed then).  Call it before allocating pinned memory."""
+    import os
+    try:
+        import pynvml
+        import torch
+        if device is None:
+            device = torch.cuda.current_device()
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:          # no NVML, no permission, a container that hides the topology: leave the process as it is
+        return None
+
+
 def unique_id() -> bytes:
     """A fresh NCCL rendezvous id (rank 0 calls this and ships the 128 bytes to the other ranks)."""
     buf = ctypes.create_string_buffer(128)
