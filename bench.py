@@ -296,7 +296,7 @@ def setup_c4(ctx, args):
     # (+ one torch fill of the 1.2 MB count buffer and, for N > 1, NCCL's all-reduce kernel: not counted)
     w.launches_per_step = 7
     w.h2d, w.d2h = B * T * 2, (N + N * N + N * M) * 8 + 8 + 8
-    w.dominant = "bw_backward_tc_kernel (tcgen05, xi in TMEM, L2 count reductions)"
+    w.dominant = "bw_backward_tc3_kernel (tcgen05, thread = state, four quarter-tile pipelines per CTA, xi in TMEM, L2 count reductions)"
     w.l2_note = "forward stash of B*T*512 B per step (34 GB at B=131072, >> 126 MB L2): nothing survives between steps"
     w.dtype = ("split bf16 operands (hi + lo, 3 MMAs) / f32 accumulate" if prec_name == "bf16x3" else
                "tf32 multiply / f32 accumulate") + " (float64 counts and M-step)"
@@ -345,7 +345,9 @@ def setup_c4(ctx, args):
                                       "note": "bf16x3 (the API default): re-estimated pi/A/B within 1e-6/2e-6/1e-5 of the float64 "
                                               "oracle at 4,096 sequences; tf32: 6e-5/7e-5/4e-4 (tests/test_gpu_train_loop.py)"},
                 "note": "binding roof = HBM (the stash is the only operand that does not fit on chip); the kernel is "
-                        "held below it by the shared-memory port (512 KB per tile-step) and L2 count reductions (DESIGN.md 3.5)"}
+                        "held below it by the L1 / shared-memory data pipe (ncu: LSU wavefronts 87 % of peak -- 4 coalesced "
+                        "128-byte accesses per (sequence, 32 states) plus the per-sequence scalars) and runs power-capped "
+                        "(clocks.reasons) (DESIGN.md 3.5)"}
 
     def secondary():
         """The other operand precision, 5 iterations of the same loop (secondary record).  Runs on EVERY rank: the

@@ -198,14 +198,18 @@ int khmm_fwdbwd_loglik_discrete_f32(int64_t B, int64_t T, int N, int M,
                                     double *loglik, double *loglik_bwd, khmm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
- * Tensor-core forward-backward log-likelihood for large state spaces: N a multiple of 128,
- * 128 <= N <= 1024, all sequences of length T.  One tcgen05 (kind::tf32, fp32 accumulation in
- * TMEM, TMA-staged operands) launch per time step computes (B x N) x (N x N) for the forward
- * (abstract_hmm.py:266-270) and the self-scaled backward (:339-349) recursion together, with the
- * emission evaluation, scaling and row sums fused in the epilogue.  A and AT: the transition
- * matrix and its transpose.  workspace: khmm_fwdbwd_loglik_tc_workspace_bytes(B, N) bytes,
- * 256-byte aligned.  loglik_bwd may be NULL (forward only).  tf32 multiplies: log-likelihoods
- * agree with the float64 reference to ~1e-6 relative (stated bound 2e-5 in the tests).
+ * Tensor-core forward-backward log-likelihood for large state spaces: N a multiple of 128, 128 <= N <= 1024
+ * (the Python layer pads any 65 <= N <= 1024 with unreachable states), any batch size; the *_ragged_* entry
+ * points below take per-sequence lengths.  ALL T-1 steps of the forward (abstract_hmm.py:266-270) and of the
+ * self-scaled backward (:339-349) recursion run in ONE cooperative launch of a persistent tcgen05 kernel
+ * (kind::tf32 or kind::f16 with bf16 operands, fp32 accumulation in TMEM, TMA-staged operands): the work is a
+ * set of (128-sequence row tile, direction) chains of column-tile jobs that wait for their inputs on per-chain
+ * counters in global memory instead of on a kernel boundary; the emission evaluation, the deferred scaling and the
+ * row sums are fused in the epilogue.  Where a cooperative launch is unavailable the same
+ * arithmetic runs with one launch per step.  A and AT: the transition matrix and its transpose.  workspace:
+ * khmm_fwdbwd_loglik_tc_workspace_bytes(B, N) bytes, 256-byte aligned.  loglik_bwd may be NULL (forward only).
+ * tf32 multiplies: log-likelihoods agree with the float64 reference to ~1e-6 relative (stated bound 2e-5 in the
+ * tests); bf16: 7e-6 at T = 1024.
  */
 /* operand_precision */
 #define KHMM_TC_TF32 0 /* tf32 operands (10-bit mantissa), fp32 accumulation */
@@ -266,20 +270,26 @@ int khmm_xi_accumulate_f64(int64_t B, int64_t T, int N, const int32_t *lengths,
                            const double *alpha, const double *V, double *xi_raw, khmm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
- * Fused tensor-core E-step for N = 128 states, equal-length sequences (config 4).  One call does,
- * for a batch chunk, what the three calls above do -- forward (abstract_hmm.py:250-285), backward
- * (:327-351), gamma (:291-297), zi summed over t (:299-325, discrete_hmm.py:155) and the count sums of
- * DiscreteHMM.do_pass (discrete_hmm.py:117-159) with the same reference weighting -- in two persistent
- * tcgen05 kernels (kind::tf32, fp32 accumulation in TMEM): the forward rows stay in tensor memory as
- * the next step's A operand and are stashed once in HBM; the backward kernel consumes the stash by
- * TMA, accumulates zi in TMEM and scatters the emission counts with sector-wide L2 reductions.
- * Adds into `counts` (same layout as above).  workspace: khmm_estep_tc_workspace_bytes(B,T,N,M)
- * bytes, 1024-byte aligned (holds the fp32 stash).  alpha_out / scale_out (may be NULL): caller-visible
- * copies of the stash -- tile-major [ceil(B/128)][T][128][128] floats, W[b/128][t][b%128][:] = c_t * alpha_t,
- * one contiguous 64 KB block per (tile of 128 sequences, step) -- and of the scale factors, tile-major
- * [ceil(B/128)][T][128], c[b/128][t][b%128] (used by the tests).
- * tf32 multiplies: statistics agree with the float64 reference to ~1e-3 relative per (sequence, step)
- * term, unbiased, so re-estimated parameters converge as 1/sqrt(rows) (tests state the bound).
+ * Fused tensor-core E-step for N = 128 states (config 4; the Python layer pads 8 <= N < 128 with unreachable
+ * states; per-sequence lengths: the *_ragged_* entry point below).  One call does, for a batch chunk, what the
+ * three calls above do -- forward (abstract_hmm.py:250-285), backward (:327-351), gamma (:291-297), zi summed
+ * over t (:299-325, discrete_hmm.py:155) and the count sums of DiscreteHMM.do_pass (discrete_hmm.py:117-159)
+ * with the same reference weighting -- in two persistent tcgen05 kernels (fp32 accumulation in TMEM):
+ *   forward   thread = sequence; the row W_t = c_t alpha_t stays in tensor memory as the next step's A operand
+ *             and is stashed once in HBM (TMA tensor stores);
+ *   backward  thread = state, four quarter-tiles of 32 sequences per CTA as independent pipelines: the stash
+ *             comes back by TMA, zi accumulates in TMEM over the whole tile, emission values are read and the
+ *             emission counts reduced (red.global.add) straight from registers, one coalesced 128-byte row per
+ *             warp instruction.
+ * Adds into `counts` (same layout as above).  workspace: khmm_estep_tc_workspace_bytes(B,T,N,M) bytes,
+ * 1024-byte aligned (holds the fp32 stash).  alpha_out / scale_out (may be NULL): caller-visible copies of the
+ * stash -- tile-major [ceil(B/128)][T][128][128] floats, W[b/128][t][b%128][:] = c_t * alpha_t, one contiguous
+ * 64 KB block per (tile of 128 sequences, step) -- and of the scale factors, tile-major [ceil(B/128)][T][128],
+ * c[b/128][t][b%128] (used by the tests).
+ * This entry point multiplies in tf32: statistics agree with the float64 reference to ~1e-3 relative per
+ * (sequence, step) term, unbiased, so re-estimated parameters converge as 1/sqrt(rows) down to the systematic
+ * 1e-5 ... 1e-4 left by the rounding of A (tests state the bounds); khmm_estep_tc_discrete_ex_f32 below takes the
+ * operand precision (the Python layer's default is KHMM_TC_BF16X3).
  */
 size_t khmm_estep_tc_workspace_bytes(int64_t B, int64_t T, int N, int M);
 int khmm_estep_tc_discrete_f32(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *AT,
@@ -324,12 +334,12 @@ int khmm_estep_tc_last_kernel_ms(float *forward_ms_host, float *backward_ms_host
  * restores the library's default.  The environment variable of the same name sets the initial value and is read once per
  * process; no production call reads the environment. */
 int khmm_debug_switch(const char *name, int value);
-/* Development hook: which backward kernel the fused E-step uses -- 1 = thread per sequence (the default), 2 = the
- * transposed thread-per-state kernel, 0 = back to the default / $KHMM_BW_BACKWARD.  Both compute the same statistics
- * (tests/test_gpu_parity.py runs the tensor-core E-step tests on both). */
+/* Development hook: which backward kernel the fused E-step uses -- 3 = thread per state, four quarter-tile pipelines per
+ * CTA (the default), 1 = the round-1 thread-per-sequence kernel, 0 = back to the default / $KHMM_BW_BACKWARD.  Both compute
+ * the same statistics in both operand precisions (tests/test_gpu_train_loop.py runs them against each other). */
 int khmm_debug_bw_backward_version(int version);
 /* Development hook: arm (device buffer of 2*8*32 int64) or disarm (NULL) a clock64 timeline of the warp roles
- * of the backward and forward kernels (block 0, steps 8..15; tools/dbg_bw_trace.py prints it). */
+ * of the backward and forward kernels (block 0, steps 8..15; tools/estep_forward_timeline.py prints it). */
 int khmm_debug_bw_trace(int64_t *dev_buf);
 /* Same for the whole-recursion kernel (device buffer of 4*2*16 int64: block 0, steps 8..11, its two lanes). */
 int khmm_debug_rc_trace(int64_t *dev_buf);

@@ -4,29 +4,25 @@
 // (:327-351), gamma (:291-297), zi (:299-325) and the count sums of DiscreteHMM.do_pass
 // (discrete_hmm.py:117-159):
 //
-//   bw_forward_tc_kernel   CTA = one tile of 128 sequences, whole time loop inside the kernel.  The row
+//   bw_forward_tc_kernel   thread = sequence.  CTA = one tile of 128 sequences, whole time loop inside the kernel.  The row
 //       W_t = c_t alpha_t (unnormalised: its row sum IS the scale factor c_t) stays in TENSOR MEMORY as
 //       the A operand of the next step's MMA (tcgen05.mma with A in TMEM, A^T as a K-major B operand in
-//       shared memory, loaded once by TMA); the epilogue (thread = sequence = TMEM lane) multiplies the
-//       accumulator by the gathered emission row and by 1/c_{t-1}, writes W_t back to TMEM (tf32-rounded)
-//       and to the HBM stash [B][T][128] (fp32), and keeps c_t / log P.  Two CTAs per SM interleave
-//       their MMAs and epilogues.
-//   bw_backward_tc_kernel  CTA = one tile, time loop backwards, one CTA per SM.  Per step:
-//         MMA1  D1 = V_{t+1} . A^T          (A operand = V in TMEM, B operand = A in shared memory)
-//         MMA2  Xi += W_t^T . V2_{t+1}      (both operands MN-major in shared memory: W_t straight from
-//                                            the stash by TMA, V2 = V / c_t written by the epilogue;
-//                                            Xi accumulates in TMEM over the whole tile = zi summed over t)
-//         epilogue  beta_t = D1 / c_{t+1};  gamma_ref = W_t . beta_t  (= alpha beta c_t, abstract_hmm.py:294);
-//                   V_t = b(o_t) . beta_t -> TMEM (next MMA1) and shared memory (next MMA2);
-//                   gamma_ref row -> TMEM staging;  t = 0: smooth1d(gamma[0]) (discrete_hmm.py:132).
-//         RED warps read the staging area back with the 16x256b shape (a quad of lanes = one 32-byte sector
-//         of a row) and add it into row o_t of an fp32 [M+2][128] table in L2 with red.global.add.v2.f32
-//         (rows M, M+1 collect pi and the t = T-1 rows).  Measured: L2 reductions cost ~0.6 sector-ops per
-//         clock per SM whatever the vector width, so full-sector quads are the cheapest form.
+//       shared memory, loaded once by TMA); the epilogue multiplies the accumulator by the gathered emission row and by
+//       1/c_{t-1}, writes W_t back to TMEM and to the HBM stash [tile][T][128][128] (fp32, TMA tensor stores), and keeps
+//       c_t / log P.  The MMA of a step is issued as two column halves so that the epilogue of the first overlaps the second.
+//   bw_backward_tc3_kernel  thread = STATE (the default backward kernel, round 2).  A tile is four quarter-tiles of 32
+//       sequences that run as independent pipelines (sixteen compute warps):
+//         MMA1  D1^T = A . V2_{t+1}^T        (A resident in TMEM, V2 K-major in shared memory, N = 32)
+//         MMA2  Xi^T += V2_{t+1}^T . W_t     (V2^T in TMEM, W_t straight from the stash by TMA; Xi = zi summed over t, in TMEM)
+//         threads: beta_t = D1 c_t / c_{t+1}; gamma_ref = W_t . beta_t -> red.global.add into row o_t of the fp32 count
+//                  table, one coalesced 128-byte row per warp instruction straight from registers; V2_t = b(o_t) . beta_t /
+//                  c_{t-1} -> shared memory and TMEM; emission values read from the table one step ahead (coalesced).
+//   bw_backward_tc_kernel  thread = sequence (round 1): the independent cross-check of the kernel above (development switch).
 //   bw_fold_kernel adds the fp32 table replicas into the float64 count buffer (include/khmm.h layout).
 //
 // HBM traffic per (sequence, step): 512 B stash write + 512 B stash read + 6 B observations/scales
-// (the generic path moves 2.5 KB).  Precision: tf32 multiplies, fp32 accumulation; tests state the bound.
+// (the generic path moves 2.5 KB).  Operand precision of the recursion's contraction: tf32, or bf16 hi/lo pairs with
+// three MMAs (KHMM_TC_BF16X3, fp32-class parity; the API default); fp32 accumulation; tests state the bounds.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -138,7 +134,7 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // the gather warps copy the emission rows b(o_t) of the tile into it one step ahead (cp.async, lane = 16-byte
 // piece, 4 rows per instruction), the epilogue overwrites them IN PLACE with W_t, and ONE thread sends the
 // whole 64 KB tile to the tile-major stash with four TMA tensor stores (plus one 512-byte bulk store for c_t).
-// Measured history of this kernel (clock64 timeline, tools/dbg_bw_trace.py): thread-per-row LDG/STG 12,000
+// Measured history of this kernel (clock64 timeline, tools/estep_forward_timeline.py): thread-per-row LDG/STG 12,000
 // cycles per step (32 L1 wavefronts per instruction); per-thread bulk copies 10,000 (UBLKCP serialises 32 per
 // warp); a storer warp doing LDS+STG per row 5,200 (the storer alone took 4,500).
 // Warps: 0-7 epilogue (thread = sequence = TMEM lane; warps 0-3 own columns 0-63, warps 4-7 columns 64-127 of
@@ -592,7 +588,6 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t b = tile * 128 + row;
             const bool live = b < B;
-            const int64_t bc = live ? b : B - 1;
             const int len_b = live ? ob.len(b) : 0;
             for (int64_t t = T - 1; t >= 0; t--) {
                 const bool last = (t == T - 1);
@@ -873,55 +868,10 @@ bw_backward_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
-// ---------------------------------------------------------------- backward, transposed (round 2)
-// The round-1 kernel above has thread = sequence (TMEM lane = sequence).  Its timeline (profiles/r2_trace_c4_backward_v1.txt)
-// shows a serial chain MMA1 (2,100 cycles) -> epilogue pass (3,400) -> V2 pass (1,600) per step, all three bound by the
-// 64 B/clk TMEM READ port: D1 is read once, V is read back for the shared-memory copy, the gamma staging area is read
-// back by the reduction warps, and MMA1's A operand (V) comes from TMEM as well -- 256 KB of TMEM reads per step.
-//
-// This kernel transposes the problem: TMEM lane = STATE.  Per step t (one tile of 128 sequences):
-//     MMA1  D1^T[i][b]  = sum_j A[i][j] V_{t+1}[b][j]      A operand = the transition matrix, resident in TMEM for the
-//                                                          whole kernel; B operand = V (K-major, written by the compute warps)
-//     MMA2  Xi^T[j][i] += sum_b V2_{t+1}[b][j] W_t[b][i]   A operand = V2^T in TMEM -- the compute thread of state j OWNS
-//                                                          row j of V2^T, so it stores it with tcgen05.st; B operand =
-//                                                          the W_t tile exactly as TMA delivers it (MN-major)
-//     compute warps (8), thread = state i, 64 sequences each (4 lane quadrants x 2 sequence halves):
-//         beta_t[b] = D1^T[i][b] / c_{t+1}[b];  gamma_ref = W_t[b][i] beta;  V_t[b][i] = b_i(o_t[b]) beta -> shared memory
-//         (MMA1's operand) and, divided by c_{t-1}, -> TMEM (MMA2's).  Every access is contiguous across the warp.
-//     slabs: four 16 KB buffers [32 sequences][128 states], one per (half, chunk).  A TMA gather4 (4 table rows per
-//         instruction, no LSU involvement) fills a slab with the emission rows b(o_t[b]) one step ahead; the compute warps
-//         read them and overwrite them IN PLACE with gamma_ref; four reduction warps then stream each row into row o_t[b]
-//         of the fp32 count table with one coalesced red.global.add.v4.f32 per row (the L2 atomic rate, ~0.6 sector-ops
-//         per clock per SM, is the floor of this kernel) and hand the slab back to the gather.  At t = 0 they apply
-//         smooth1d(gamma[0]) per sequence with warp-wide reductions (discrete_hmm.py:132, util.py:56-60).
-// TMEM is read exactly once per step by the threads (D1); the W tile is read into registers at the start of the step and
-// released at once, so ONE buffer gives the TMA producer a whole step of prefetch distance.  Per-sequence scalars (table
-// row, 1/c_{t+1}, 1/c_{t-1}, ragged-batch switches) are staged one step ahead by a helper warp.
-constexpr uint32_t C2_A = 0, C2_D1 = 128, C2_XI = 256, C2_V2T = 384;
-constexpr int BW_SLAB = 32 * 128 * 4;   // [32 sequences][128 states] fp32
-
-struct __align__(8) Bwd2Bars {
-    uint64_t w_full, w_empty, v_ready, d1_full, mma2_q[4], prep_full[2], prep_empty[2], e_full[4], g_full[4], s_empty[4];
-    uint32_t tmem_base;
-};
-struct __align__(16) Bwd2Prep {
-    int srow[128];     // 128 * clamped symbol (float offset of the table row) | bit 31: (row, step) not live (t >= len, or a
-                       // row past the batch) | bit 30: t == len - 1
-    float mulb[128];   // 1 / c_{t+1}, or 0 where beta_t = 1 (t >= len - 1: the sequence's last step or its padding)
-    float rcm1[128];   // 1 / c_{t-1} for 0 < t < len, else 0 (V2_t = 0: the pair (t-1, t) does not count)
-};
-constexpr int SROW_MASK = 0x3fffffff, SROW_LAST = 0x40000000;
-
 // No "memory" clobber: nothing in the kernel reads the count table, and the clobber would pin every shared-memory access
 // between two reductions.
 __device__ __forceinline__ void red_add_v4_nc(float *p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
-}
-__device__ __forceinline__ void tma_gather4(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int r0, int r1,
-                                            int r2, int r3) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 
 #define BW2_TRACE(ev)                                                                                  \
@@ -930,363 +880,6 @@ __device__ __forceinline__ void tma_gather4(void *smem_dst, const CUtensorMap *m
             (threadIdx.x & 31) == 0)                                                                   \
             out.trace[((Ti - 1 - t) - 8) * 32 + (ev)] = clock64();                                      \
     } while (0)
-
-__global__ void __launch_bounds__(512, 1)
-bw_backward_tc2_kernel(const __grid_constant__ CUtensorMap mapStash, const __grid_constant__ CUtensorMap mapB,
-                       const float *__restrict__ Ar, BwObs ob, int64_t B, int64_t T, const float *__restrict__ scale,
-                       BwdOut out) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *sW = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // W_t tile (TMA, MN-major 32 B atoms)
-    unsigned char *sVk = sW + BW_TILE;      // V_{t+1}: B operand of MMA1, K-major SWIZZLE_128B
-    unsigned char *slab = sVk + BW_TILE;    // 4 x [32][128] fp32: emission rows in, gamma_ref rows out
-    Bwd2Prep *prep = (Bwd2Prep *)(slab + 4 * BW_SLAB);
-    Bwd2Bars *bars = (Bwd2Bars *)(prep + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t ntiles = (B + 127) / 128;
-    const int M = ob.M;
-    const int Ti = (int)T;
-
-    if (threadIdx.x == 0) {
-        mbar_init(&bars->w_full, 1);
-        mbar_init(&bars->w_empty, 9);        // 8 compute warps + the commit of MMA2
-        mbar_init(&bars->v_ready, 256);
-        mbar_init(&bars->d1_full, 1);
-        for (int k = 0; k < 2; k++) {
-            mbar_init(&bars->prep_full[k], 1);
-            mbar_init(&bars->prep_empty[k], 13);   // 8 compute warps + 4 reduction warps + the gather warp
-        }
-        for (int k = 0; k < 4; k++) {
-            mbar_init(&bars->mma2_q[k], 1);
-            mbar_init(&bars->e_full[k], 1);
-            mbar_init(&bars->g_full[k], 128);
-            mbar_init(&bars->s_empty[k], 4);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 9) tmem_alloc(&bars->tmem_base, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-
-    if (warp == 8) {
-        // ------------------------------------------------ TMA producer: W_t tiles of the stash
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (elect_one()) {
-            tma_prefetch_desc(&mapStash);
-            uint32_t g = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-                for (int t = Ti - 1; t >= 0; t--, g++) {
-                    mbar_wait(&bars->w_empty, (g & 1) ^ 1);
-                    BW2_TRACE(0);
-                    mbar_arrive_expect_tx(&bars->w_full, BW_TILE);
-                    for (int c = 0; c < 4; c++)
-                        tma_load_3d(sW + c * BW_SUB, &mapStash, &bars->w_full, c * 32, 0, (int)(tile * T + t));
-                }
-        }
-    } else if (warp == 9) {
-        // ------------------------------------------------ MMA issuer
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (elect_one()) {
-            const uint32_t idesc_k = make_idesc_tf32(128, 128);
-            const uint32_t idesc_mn = make_idesc_tf32(128, 128, false, true);
-            const uint64_t dW = make_mnmajor_sw128a32_desc(sW, BW_SUB, 512);
-            uint32_t nv = 0, g = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                g++;      // step t = T-1 has no MMA
-                for (int t = Ti - 2; t >= 0; t--, g++) {
-                    mbar_wait(&bars->v_ready, nv & 1);
-                    nv++;
-                    BW2_TRACE(4);
-                    tc_fence_after();
-                    // MMA1(t): D1^T = A . V_{t+1}^T
-#pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        uint64_t db = make_kmajor_sw128_desc(sVk + (k >> 2) * BW_SUB);
-                        mma_tf32_ts(tmem + C2_D1, tmem + C2_A + k * 8, desc_advance(db, (k & 3) * 32), idesc_k, k != 0);
-                    }
-                    tc_commit(&bars->d1_full);
-                    BW2_TRACE(5);
-                    mbar_wait(&bars->w_full, g & 1);
-                    BW2_TRACE(6);
-                    tc_fence_after();
-                    // MMA2(t): Xi^T += V2^T_{t+1} . W_t, K = the 128 sequences in the order the compute warps overwrite
-                    // the V2^T columns (sequences 0-31 and 64-95 first); one commit per 32 sequences releases them
-#pragma unroll
-                    for (int grp = 0; grp < 4; grp++) {
-                        const int r0 = (grp & 1) * 64 + (grp >> 1) * 32;
-#pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            const int k = r0 / 8 + kk;
-                            mma_tf32_ts(tmem + C2_XI, tmem + C2_V2T + k * 8, desc_advance(dW, k * 1024), idesc_mn,
-                                        (t != Ti - 2) || grp != 0 || kk != 0);
-                        }
-                        tc_commit(&bars->mma2_q[grp]);
-                    }
-                    tc_commit(&bars->w_empty);
-                    BW2_TRACE(7);
-                }
-            }
-        }
-    } else if (warp == 10) {
-        // ------------------------------------------------ prep: per-sequence scalars of the step, one step ahead
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        uint32_t g = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            int64_t bc[4];
-            int len[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int64_t gb = tile * 128 + lane + 32 * k;
-                bc[k] = gb < B ? gb : B - 1;
-                len[k] = gb < B ? ob.len(gb) : 0;
-            }
-            for (int t = Ti - 1; t >= 0; t--, g++) {
-                const int buf = g & 1;
-                int sy[4];
-                float c1[4], cm[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int b = lane + 32 * k;
-                    sy[k] = ob.sym(bc[k], t);
-                    c1[k] = (t + 1 < Ti) ? scale[(tile * T + t + 1) * 128 + b] : 1.f;
-                    cm[k] = (t > 0) ? scale[(tile * T + t - 1) * 128 + b] : 1.f;
-                }
-                mbar_wait(&bars->prep_empty[buf], ((g >> 1) & 1) ^ 1);
-                Bwd2Prep &P = prep[buf];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int b = lane + 32 * k;
-                    const bool bone = (t == Ti - 1) || (t >= len[k] - 1);
-                    P.srow[b] = (sy[k] * BW_N) | (t < len[k] ? 0 : (int)0x80000000) | (t == len[k] - 1 ? SROW_LAST : 0);
-                    P.mulb[b] = bone ? 0.f : 1.0f / c1[k];
-                    P.rcm1[b] = (t > 0 && t < len[k]) ? 1.0f / cm[k] : 0.f;
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->prep_full[buf]);
-            }
-        }
-    } else if (warp == 11) {
-        // ------------------------------------------------ gather: emission rows b(o_t[b]) -> slabs, 4 table rows per TMA
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (lane == 0) tma_prefetch_desc(&mapB);
-        uint32_t g = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-            for (int t = Ti - 1; t >= 0; t--, g++) {
-                const int buf = g & 1;
-                mbar_wait(&bars->prep_full[buf], (g >> 1) & 1);
-                const Bwd2Prep &P = prep[buf];
-#pragma unroll 1
-                for (int s = 0; s < 4; s++) {
-                    mbar_wait(&bars->s_empty[s], (g & 1) ^ 1);     // the reduction warps have drained the previous step's rows
-                    if (lane == 0) mbar_arrive_expect_tx(&bars->e_full[s], BW_SLAB);
-                    __syncwarp();
-                    if (lane < 8) {
-                        const int b0 = (s & 1) * 64 + (s >> 1) * 32 + 4 * lane;
-                        const int4 r4 = *reinterpret_cast<const int4 *>(P.srow + b0);
-                        tma_gather4(slab + s * BW_SLAB + 4 * lane * 512, &mapB, &bars->e_full[s], 0, (r4.x & SROW_MASK) >> 7,
-                                    (r4.y & SROW_MASK) >> 7, (r4.z & SROW_MASK) >> 7, (r4.w & SROW_MASK) >> 7);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->prep_empty[buf]);
-            }
-    } else if (warp >= 12) {
-        // ------------------------------------------------ reduction warps: gamma_ref rows -> fp32 count table in L2
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        const int r = warp - 12;
-        float *tab0 = out.tab + (size_t)(blockIdx.x % BW_REPL) * (size_t)(M + 2) * BW_N + 4 * lane;
-        float *r_pi = tab0 + (size_t)M * BW_N;
-        float *r_last = tab0 + (size_t)(M + 1) * BW_N;
-        uint32_t g = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-            for (int t = Ti - 1; t >= 0; t--, g++) {
-                const int buf = g & 1;
-                mbar_wait(&bars->prep_full[buf], (g >> 1) & 1);
-                const Bwd2Prep &P = prep[buf];
-#pragma unroll 1
-                for (int s = 0; s < 4; s++) {
-                    mbar_wait(&bars->g_full[s], g & 1);
-                    if (r == 0 && s == 0) BW2_TRACE(16);
-                    const int b0 = (s & 1) * 64 + (s >> 1) * 32 + 8 * r;
-                    const unsigned char *rows = slab + s * BW_SLAB + 8 * r * 512 + 16 * lane;
-                    if (t > 0) {
-#pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            const float4 f = *reinterpret_cast<const float4 *>(rows + k * 512);
-                            const int sy = P.srow[b0 + k];
-                            // unconditional: a dead (row, step) pair holds an all-zero gamma row (zero stash row)
-                            red_add_v4_nc(tab0 + (sy & SROW_MASK), f.x, f.y, f.z, f.w);
-                            if (sy & SROW_LAST) red_add_v4_nc(r_last, f.x, f.y, f.z, f.w);
-                        }
-                    } else {
-                        // t = 0: pi_new = smooth1d(gamma[0]) per sequence (util.py:56-60); the smoothed row counts for pi AND
-                        // for the emission numerators (the reference overwrites gamma[0] in place, discrete_hmm.py:132)
-#pragma unroll 1
-                        for (int k = 0; k < 8; k++) {
-                            const float4 f = *reinterpret_cast<const float4 *>(rows + k * 512);
-                            const int sy = P.srow[b0 + k];
-                            const bool live = sy >= 0;
-                            int cnt = (f.x < 1e-10f) + (f.y < 1e-10f) + (f.z < 1e-10f) + (f.w < 1e-10f);
-                            cnt = __reduce_add_sync(0xffffffffu, cnt);
-                            if (cnt >= BW_N) {
-                                if (live && lane == 0) atomicAdd(out.flags, 1.0);
-                                cnt = BW_N - 1;
-                            }
-                            const float sub = (float)((double)cnt * 1e-10 / (double)(BW_N - cnt));
-                            const float floorv = 1e-10f;
-                            const float x0 = fmaxf(f.x - sub, floorv), x1 = fmaxf(f.y - sub, floorv),
-                                        x2 = fmaxf(f.z - sub, floorv), x3 = fmaxf(f.w - sub, floorv);
-                            const float inv = 1.0f / warp_sum((x0 + x1) + (x2 + x3));
-                            if (live) {
-                                red_add_v4_nc(tab0 + (sy & SROW_MASK), x0 * inv, x1 * inv, x2 * inv, x3 * inv);
-                                red_add_v4_nc(r_pi, x0 * inv, x1 * inv, x2 * inv, x3 * inv);
-                                if (sy & SROW_LAST) red_add_v4_nc(r_last, x0 * inv, x1 * inv, x2 * inv, x3 * inv);
-                            }
-                        }
-                    }
-                    fence_proxy_async();       // the slab is refilled through the async proxy (TMA gather)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->s_empty[s]);
-                    if (r == 0 && s == 3) BW2_TRACE(17);
-                }
-                if (lane == 0) mbar_arrive(&bars->prep_empty[buf]);
-            }
-    } else {
-        // ------------------------------------------------ compute warps: thread = state i, 64 sequences (half h)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
-        const int q = warp & 3, h = warp >> 2;
-        const int i = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        // byte offset of element (b, i) inside a tile:
-        //   K-major SWIZZLE_128B (sVk):        b * 128 + (kbase ^ ((b & 7) << 4))     16-byte chunk (lane / 4) ^ (b & 7)
-        //   MN-major 32-byte atoms (sW):       b * 128 + (mbase ^ ((b & 3) << 5))     32-byte chunk (lane / 8) ^ (b & 3)
-        const uint32_t kbase = q * BW_SUB + ((lane >> 2) << 4) + ((lane & 3) << 2);
-        const uint32_t mbase = q * BW_SUB + ((lane >> 3) << 5) + ((lane & 7) << 2);
-        unsigned char *vk_h = sVk + 64 * h * 128;
-        const unsigned char *w_h = sW + 64 * h * 128;
-        if (h == 0) {
-            // the (tf32-rounded) transition matrix: row i -> TMEM lane i, resident for the whole kernel
-#pragma unroll 1
-            for (int c0 = 0; c0 < BW_N; c0 += 32) {
-                uint32_t a[32];
-#pragma unroll
-                for (int p = 0; p < 8; p++) {
-                    float4 f = ldg4(Ar + (size_t)i * BW_N + c0 + 4 * p);
-                    a[4 * p] = __float_as_uint(f.x); a[4 * p + 1] = __float_as_uint(f.y);
-                    a[4 * p + 2] = __float_as_uint(f.z); a[4 * p + 3] = __float_as_uint(f.w);
-                }
-                tmem_st_32x32(tmem + lane_base + C2_A + c0, a);
-            }
-            tmem_st_wait();
-        }
-        tc_fence_before();
-        uint32_t nd = 0, nm = 0, g = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            for (int t = Ti - 1; t >= 0; t--, g++) {
-                const bool has_mma = (t <= Ti - 2);            // MMA1(t) / MMA2(t) exist
-                const int buf = g & 1;
-                const Bwd2Prep &P = prep[buf];
-                // W_t -> registers (64 values: this state, this half's sequences), then the tile goes back to the TMA producer.
-                // (Waiting for MMA1 first, so that these reads do not share the shared-memory port with its operand fetch,
-                // was measured slower: 9,300 against 8,300 cycles per step.)
-                mbar_wait(&bars->w_full, g & 1);
-                if (warp == 0) BW2_TRACE(8);
-                float gam[64];
-#pragma unroll
-                for (int k = 0; k < 64; k++) gam[k] = *reinterpret_cast<const float *>(w_h + k * 128 + (mbase ^ ((k & 3) << 5)));
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->w_empty);
-                if (!has_mma && threadIdx.x == 0) mbar_arrive(&bars->w_empty);   // t = T-1: in place of MMA2's commit
-                mbar_wait(&bars->prep_full[buf], (g >> 1) & 1);
-                uint32_t d0[32], d1[32];
-                if (has_mma) {
-                    mbar_wait(&bars->d1_full, nd & 1);
-                    nd++;
-                    tc_fence_after();
-                    tmem_ld_32x32(tmem + lane_base + C2_D1 + 64 * h, d0);
-                    tmem_ld_32x32(tmem + lane_base + C2_D1 + 64 * h + 32, d1);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 32; k++) d0[k] = d1[k] = 0u;      // t = T-1: beta = 0 * 0 + 1
-                }
-                if (warp == 0) BW2_TRACE(10);
-                const uint32_t mpar = nm & 1;
-                if (has_mma) nm++;
-                // one chunk = 32 sequences = one slab: emission rows in, gamma_ref rows out; V -> shared memory, V2 -> TMEM
-                auto chunk = [&](auto cc, uint32_t (&d)[32]) {
-                    constexpr int c = decltype(cc)::value;
-                    const int s = 2 * c + h;
-                    const int b0 = 64 * h + 32 * c;
-                    float *srows = reinterpret_cast<float *>(slab + s * BW_SLAB) + i;
-                    mbar_wait(&bars->e_full[s], g & 1);
-                    if (c == 0 && warp == 0) BW2_TRACE(13);
-#pragma unroll
-                    for (int k4 = 0; k4 < 8; k4++) {
-                        const float4 m4 = *reinterpret_cast<const float4 *>(P.mulb + b0 + 4 * k4);
-                        const float4 r4 = *reinterpret_cast<const float4 *>(P.rcm1 + b0 + 4 * k4);
-                        const float mu4[4] = {m4.x, m4.y, m4.z, m4.w};
-                        const float rc4[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            const int k = 4 * k4 + kk;
-                            const float e = srows[k * BW_N];
-                            // beta = D1 / c_{t+1}, or 1 where mulb = 0 (the sequence's last step, its padding)
-                            const float beta = fmaf(__uint_as_float(d[k]), mu4[kk], mu4[kk] == 0.f ? 1.f : 0.f);
-                            srows[k * BW_N] = gam[32 * c + k] * beta;       // gamma_ref: 0 for dead (row, step) pairs
-                            const float v = e * beta;
-                            *reinterpret_cast<uint32_t *>(vk_h + (32 * c + k) * 128 + (kbase ^ ((k & 7) << 4))) = tf32_bits(v);
-                            d[k] = tf32_bits(v * rc4[kk]);
-                        }
-                    }
-                    mbar_arrive(&bars->g_full[s]);                 // the reduction warps may take the slab
-                };
-                if (has_mma) tmem_ld_wait();
-                chunk(std::integral_constant<int, 0>{}, d0);
-                if (warp == 0) BW2_TRACE(11);
-                chunk(std::integral_constant<int, 1>{}, d1);
-                if (t > 0) {
-                    // MMA2(t) reads the V2^T columns until its groups commit (long done by now: it started with this step's
-                    // compute); then this step's V2^T goes in
-                    if (has_mma) {
-                        mbar_wait(&bars->mma2_q[h], mpar);
-                        mbar_wait(&bars->mma2_q[2 + h], mpar);
-                    }
-                    if (warp == 0) BW2_TRACE(15);
-                    tc_fence_after();
-                    tmem_st_32x32(tmem + lane_base + C2_V2T + 64 * h, d0);
-                    tmem_st_32x32(tmem + lane_base + C2_V2T + 64 * h + 32, d1);
-                    tmem_st_wait();
-                    fence_proxy_async();          // V is read by the tensor core through the async proxy
-                    tc_fence_before();
-                    mbar_arrive(&bars->v_ready);
-                    if (warp == 0) BW2_TRACE(12);
-                } else if (Ti > 1) {
-                    mbar_wait(&bars->mma2_q[3], mpar);            // MMA2(0): the tile's Xi is complete
-                    tc_fence_after();
-                    if (h == 0) {
-                        // Xi^T[j][i'] (lane = j = this thread's state) -> float64 counts xi[i'][j]: coalesced over j
-#pragma unroll 1
-                        for (int c0 = 0; c0 < BW_N; c0 += 32) {
-                            uint32_t v[32];
-                            tmem_ld_32x32(tmem + lane_base + C2_XI + c0, v);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int x = 0; x < 32; x++)
-                                atomicAdd(out.xi + (c0 + x) * BW_N + i, (double)__uint_as_float(v[x]));
-                        }
-                        tc_fence_before();
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->prep_empty[buf]);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem, 512);
-}
 
 // ------------------------------------------------- backward, transposed, four quarter-tile pipelines in flight (round 2)
 // Both kernels above run ONE tile per CTA, and a step of a tile is a serial chain -- MMA1 -> thread work -> MMA1 --
@@ -1791,426 +1384,6 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
     if (warp == 17) tmem_dealloc(tmem, 512);
 }
 
-// ------------------------------------------------- forward, transposed, four quarter-tile pipelines (round 2)
-// The forward kernel above has the same weakness as the first backward kernels: one tile per CTA, MMA -> epilogue -> MMA in
-// series (3,700 cycles per step with tf32 operands, 5,000 with bf16 hi/lo pairs, against 2,600 for the stash write at the HBM
-// rate).  This kernel applies the structure of bw_backward_tc3_kernel to the forward recursion: TMEM lane = state, A^T a
-// resident TMEM operand, four quarter-tiles of 32 sequences as independent pipelines, sixteen compute warps,
-// emission values read straight from the table (coalesced, one step ahead).  Per quarter and step t:
-//     MMA_f(t)    D^T[j][b] = sum_i A^T[j][i] W_{t-1}[b][i]        M = 128 states, N = 32 sequences
-//     MMA_S(t-1)  S[.][b]   = sum_i 1 * W_{t-1}[b][i]              the row sum c_{t-1}(b), on EVERY TMEM lane: a thread owns
-//                                                                 one state, so the sum over states is a cross-thread
-//                                                                 reduction -- the tensor core does it with an all-ones A
-//                                                                 operand, and every thread reads c_{t-1} of its 32
-//                                                                 sequences next to D (no shuffles, no shared memory)
-//     threads     W_t[b][j] = D^T[j][b] b_j(o_t(b)) / c_{t-1}(b)   (t = 0: pi_j b_j(o_0)); row sum = c_t as before
-//                 -> operand tile in shared memory (K-major, tf32-rounded or bf16 hi/lo) for MMA_f(t+1) and MMA_S(t)
-//                 -> fp32 stash tile in shared memory (zeros for t >= len) -> TMA tensor store, two buffers per quarter
-// c_{t-1} is the sum of the operand the recursion actually multiplies (rounded), i.e. the exact normaliser of what the
-// tensor core sees.  The scale factors go to HBM from one thread per quarter (16-byte stores); log P is summed from them
-// afterwards by bw_loglik_kernel (mantissa product + exponent sum, no log per step).
-// TMEM: A^T (tf32 128 columns / bf16 hi | lo 2 x 64), ones (128 / 64), D^T 4 x 32, S 4 x 32.
-constexpr uint32_t F3_AT = 0, F3_ONE = 128, F3_D = 256, F3_S = 384;
-struct __align__(8) Fwd3Bars {
-    uint64_t v_ready[4], d_full[4], s_full[4], s_free[4][2], prep_full[2][BW3_PREP], prep_empty[2][BW3_PREP];
-    uint32_t tmem_base;
-};
-struct __align__(16) Fwd3Prep {   // per-sequence scalars of one step of one half
-    uint32_t roff[64];  // 128 * clamped symbol: float offset of the table row o_t(b)
-    float livef[64];    // 1 for t < len (a live (sequence, step) pair), else 0: the stash row is zero there
-    int alllive;        // every sequence of the half is live at this step (the compute warps then skip livef)
-    int pad[3];
-};
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ void bulk_wait_read4() { asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); }
-
-template <int PREC>
-__global__ void __launch_bounds__(BW3_THREADS, 1)
-bw_forward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashQ, const float *__restrict__ ATmat,
-                      const float *__restrict__ pi, const float *__restrict__ Bsm, BwObs ob, int64_t B, int64_t T,
-                      float *__restrict__ scale, long long *trace) {
-    constexpr bool SPLIT = PREC != KHMM_TC_TF32;
-#define F3_TRACE(ev)                                                                                      \
-    do {                                                                                                  \
-        if (trace && blockIdx.x == 0 && tile == blockIdx.x && t >= 8 && t < 16 && (threadIdx.x & 31) == 0) \
-            trace[256 + (t - 8) * 32 + (ev)] = clock64();                                                 \
-    } while (0)
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *sOp = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [half][BW_HTILE] operand tiles
-    unsigned char *sSt = sOp + 2 * BW_HTILE;                                             // [half][buffer][BW_HTILE] stash tiles
-    Fwd3Prep *prep = (Fwd3Prep *)(sSt + 4 * BW_HTILE);                                   // [half][BW3_PREP]
-    Fwd3Bars *bars = (Fwd3Bars *)(prep + 2 * BW3_PREP);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t ntiles = (B + 127) / 128;
-    const int Ti = (int)T;
-    const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    const uint32_t gtotal = (uint32_t)(my_tiles * Ti);     // compute steps of this CTA (all its tiles)
-
-    if (threadIdx.x == 0) {
-        for (int h = 0; h < 2; h++)
-            for (int k = 0; k < BW3_PREP; k++) {
-                mbar_init(&bars->prep_full[h][k], 1);
-                mbar_init(&bars->prep_empty[h][k], 8);
-            }
-        for (int pq = 0; pq < 4; pq++) {
-            mbar_init(&bars->v_ready[pq], 128);
-            mbar_init(&bars->d_full[pq], 1);
-            mbar_init(&bars->s_full[pq], 128);
-            mbar_init(&bars->s_free[pq][0], 1);
-            mbar_init(&bars->s_free[pq][1], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 17) tmem_alloc(&bars->tmem_base, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-    if (warp < 8) {
-        // A^T, row j -> TMEM lane j, resident for the whole kernel: warp (q, hh) stores columns [64hh, 64hh+64)
-        const int q = warp & 3, hh = warp >> 2;
-        const int j = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        if (SPLIT) {
-            uint32_t hi[32], lo[32];
-#pragma unroll
-            for (int p = 0; p < 16; p++) {
-                float4 f = ldg4(ATmat + (size_t)j * BW_N + 64 * hh + 4 * p);
-                split_bf16x2(f.x, f.y, hi[2 * p], lo[2 * p]);
-                split_bf16x2(f.z, f.w, hi[2 * p + 1], lo[2 * p + 1]);
-            }
-            tmem_st_32x32(tmem + lane_base + F3_AT + 32 * hh, hi);
-            tmem_st_32x32(tmem + lane_base + F3_AT + 64 + 32 * hh, lo);
-        } else {
-#pragma unroll 1
-            for (int c0 = 64 * hh; c0 < 64 * hh + 64; c0 += 32) {
-                uint32_t a[32];
-#pragma unroll
-                for (int p = 0; p < 8; p++) {
-                    float4 f = ldg4(ATmat + (size_t)j * BW_N + c0 + 4 * p);
-                    a[4 * p] = __float_as_uint(f.x); a[4 * p + 1] = __float_as_uint(f.y);
-                    a[4 * p + 2] = __float_as_uint(f.z); a[4 * p + 3] = __float_as_uint(f.w);
-                }
-                tmem_st_32x32(tmem + lane_base + F3_AT + c0, a);
-            }
-        }
-        tmem_st_wait();
-    } else if (warp < 12) {
-        // the all-ones operand of the row-sum MMA (tf32: 128 columns of 1.0f; bf16: 64 columns of the pair (1.0, 1.0))
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        uint32_t o[32];
-#pragma unroll
-        for (int p = 0; p < 32; p++) o[p] = SPLIT ? 0x3f803f80u : 0x3f800000u;
-#pragma unroll 1
-        for (int c0 = 0; c0 < (SPLIT ? 64 : 128); c0 += 32) tmem_st_32x32(tmem + lane_base + F3_ONE + c0, o);
-        tmem_st_wait();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    if (warp == 16) {
-        // ------------------------------------------------ stash storer: one thread, the four quarters in turn.  (A compute
-        // thread issuing its quarter's stores held its whole warp -- and with it the quarter -- for 2,500 cycles per step.)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        if (elect_one()) {
-            tma_prefetch_desc(&mapStashQ);
-            uint32_t g = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-                for (int t = 0; t < Ti; t++, g++) {
-                    const int sbuf = g & 1;
-#pragma unroll 1
-                    for (int pq = 0; pq < 4; pq++) {
-                        const int h = pq >> 1, c = pq & 1;
-                        mbar_wait(&bars->s_full[pq], g & 1);
-                        // the quarter's stash tile is complete: four TMA tensor stores (one per 32-column sub-tile)
-                        const unsigned char *src = sSt + (h * 2 + sbuf) * BW_HTILE + 4096 * c;
-                        for (int cc = 0; cc < 4; cc++)
-                            tma_store_3d(&mapStashQ, src + cc * BW_HSUB, cc * 32, 64 * h + 32 * c, (int)(tile * T + t));
-                        bulk_commit();
-                        if (pq == 0) F3_TRACE(13);
-                        if (g >= 1) {
-                            bulk_wait_read4();      // all but the last four groups (one per quarter) have read their buffers:
-                            mbar_arrive(&bars->s_free[pq][sbuf ^ 1]);      // this quarter's store of step g-1 among them
-                        }
-                    }
-                }
-            bulk_wait0();
-        }
-    } else if (warp == 17) {
-        // ------------------------------------------------ MMA issuer: the four quarters in turn
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        if (elect_one()) {
-            const uint32_t idesc = SPLIT ? make_idesc_bf16(128, 32) : make_idesc_tf32(128, 32);
-            const uint64_t dV0 = make_kmajor_sw128_desc(sOp), dV1 = make_kmajor_sw128_desc(sOp + BW_HTILE);
-            uint32_t nv = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-                for (int t = 0; t < Ti; t++, nv++) {
-#pragma unroll
-                    for (int pq = 0; pq < 4; pq++) {
-                        const int h = pq >> 1, c = pq & 1;
-                        mbar_wait(&bars->v_ready[pq], nv & 1);
-                        F3_TRACE(pq == 0 ? 0 : (pq == 2 ? 2 : 31));
-                        tc_fence_after();
-                        uint64_t dvb = desc_advance(h ? dV1 : dV0, 4096 * c);     // rows 32c.. of the half's operand tile
-                        asm volatile("" : "+l"(dvb));      // keeps the per-instruction descriptors out of registers across steps
-                        const uint32_t scol = tmem + F3_S + 32 * pq, dcol = tmem + F3_D + 32 * pq;
-                        // MMA_S(t): c_t = the row sums of W_t
-                        if (SPLIT) {
-#pragma unroll
-                            for (int pass = 0; pass < 2; pass++)
-#pragma unroll
-                                for (int k = 0; k < 8; k++)
-                                    mma_bf16_ts(scol, tmem + F3_ONE + k * 8,
-                                                desc_advance(dvb, (pass ? 2 * BW_HSUB : 0) + (k >> 2) * BW_HSUB + (k & 3) * 32), idesc,
-                                                (pass | k) != 0);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 16; k++)
-                                mma_tf32_ts(scol, tmem + F3_ONE + k * 8, desc_advance(dvb, (k >> 2) * BW_HSUB + (k & 3) * 32), idesc,
-                                            k != 0);
-                        }
-                        // MMA_f(t+1): D^T = A^T . W_t^T
-                        if (t + 1 < Ti) {
-                            if (SPLIT) {
-                                // (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo)
-#pragma unroll
-                                for (int pass = 0; pass < 3; pass++) {
-                                    const uint32_t acol = tmem + F3_AT + (pass == 1 ? 64 : 0);
-#pragma unroll
-                                    for (int k = 0; k < 8; k++)
-                                        mma_bf16_ts(dcol, acol + k * 8,
-                                                    desc_advance(dvb, (pass == 2 ? 2 * BW_HSUB : 0) + (k >> 2) * BW_HSUB + (k & 3) * 32),
-                                                    idesc, (pass | k) != 0);
-                                }
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 16; k++)
-                                    mma_tf32_ts(dcol, tmem + F3_AT + k * 8, desc_advance(dvb, (k >> 2) * BW_HSUB + (k & 3) * 32), idesc,
-                                                k != 0);
-                            }
-                        }
-                        tc_commit(&bars->d_full[pq]);
-                        F3_TRACE(pq == 0 ? 1 : (pq == 2 ? 3 : 31));
-                    }
-                }
-        }
-    } else if (warp >= 18) {
-        // ------------------------------------------------ prep (one warp per half): table row and liveness, up to three steps ahead
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        const int h = warp - 18;
-        int64_t bc[2] = {0, 0};
-        int len[2] = {0, 0};
-        int syn[2] = {0, 0}, lenn[2] = {0, 0};
-        auto issue = [&](uint32_t gg) {      // the symbol loads of step gg
-            const int64_t tile = blockIdx.x + (int64_t)(gg / Ti) * gridDim.x;
-            const int t = (int)(gg % Ti);
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                if (t == 0) {      // first step of a tile: this lane's sequences change
-                    const int64_t gb = tile * 128 + 64 * h + lane + 32 * k;
-                    bc[k] = gb < B ? gb : B - 1;
-                    len[k] = gb < B ? ob.len(gb) : 0;
-                }
-                syn[k] = ob.sym(bc[k], t);
-                lenn[k] = len[k];
-            }
-        };
-        if (gtotal) issue(0);
-        for (uint32_t g = 0; g < gtotal; g++) {
-            const int t = (int)(g % Ti);
-            int sy[2], lenc[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) { sy[k] = syn[k]; lenc[k] = lenn[k]; }
-            if (g + 1 < gtotal) issue(g + 1);
-            const int buf = g % BW3_PREP;
-            mbar_wait(&bars->prep_empty[h][buf], ((g / BW3_PREP) & 1) ^ 1);
-            Fwd3Prep &P = prep[h * BW3_PREP + buf];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int b = lane + 32 * k;
-                P.roff[b] = (uint32_t)(sy[k] * BW_N);
-                P.livef[b] = t < lenc[k] ? 1.f : 0.f;
-            }
-            {
-                const unsigned dead = __ballot_sync(0xffffffffu, (t >= lenc[0]) || (t >= lenc[1]));
-                if (lane == 0) P.alllive = dead == 0u;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->prep_full[h][buf]);
-        }
-    } else {
-        // ------------------------------------------------ compute warps (q, h, c): thread = state j, 32 sequences
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        const int q = warp & 3, h = (warp >> 2) & 1, c = warp >> 3;
-        const int pq = 2 * h + c;
-        const int j = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        // byte offsets inside a half tile as in bw_backward_tc3_kernel (element (b, j), b = 32c + kb)
-        const uint32_t kbase = q * BW_HSUB + ((lane >> 2) << 4) + ((lane & 3) << 2);
-        const uint32_t c16 = 4 * (q & 1) + (lane >> 3);
-        const uint32_t hbase = (q >> 1) * BW_HSUB + 2 * (lane & 6);
-        unsigned char *op_c = sOp + h * BW_HTILE + 32 * c * 128;        // this warp's 32 rows of the operand tile
-        const float *Bj = Bsm + j;
-        const float pij = __ldg(pi + j);
-        const uint32_t t_d = tmem + lane_base + F3_D + 32 * pq, t_s = tmem + lane_base + F3_S + 32 * pq;
-        const bool issuer = (q == 0 && lane == 0);       // this quarter's TMA-store and scale-factor thread
-        float e[32];
-        if (gtotal) {
-            mbar_wait(&bars->prep_full[h][0], 0);
-            const Fwd3Prep &P0 = prep[h * BW3_PREP];
-#pragma unroll
-            for (int k4 = 0; k4 < 8; k4++) {
-                const uint4 s4 = *reinterpret_cast<const uint4 *>(P0.roff + 32 * c + 4 * k4);
-                e[4 * k4] = __ldg(addr_f32(Bj, s4.x));
-                e[4 * k4 + 1] = __ldg(addr_f32(Bj, s4.y));
-                e[4 * k4 + 2] = __ldg(addr_f32(Bj, s4.z));
-                e[4 * k4 + 3] = __ldg(addr_f32(Bj, s4.w));
-            }
-        }
-        uint32_t nd = 0, g = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            for (int t = 0; t <= Ti; t++) {
-                const bool has_prev = t >= 1;           // S(t-1) -- and D(t) for t < T -- are due
-                float *sc_out = scale + (tile * T + (t - 1)) * 128 + 64 * h + 32 * c;
-                if (t == Ti) {
-                    // after the last step: only the scale factors c_{T-1}
-                    mbar_wait(&bars->d_full[pq], nd & 1);
-                    nd++;
-                    tc_fence_after();
-                    if (q == 0) {
-#pragma unroll
-                        for (int k4 = 0; k4 < 8; k4++) {
-                            uint32_t s4[4];
-                            tmem_ld_32x4(t_s + 4 * k4, s4);
-                            tmem_ld_wait();
-                            if (lane == 0)
-                                *reinterpret_cast<uint4 *>(sc_out + 4 * k4) = make_uint4(s4[0], s4[1], s4[2], s4[3]);
-                        }
-                    }
-                    tc_fence_before();
-                    break;
-                }
-                const int pb = g % BW3_PREP, pbn = (g + 1) % BW3_PREP;
-                const Fwd3Prep &P = prep[h * BW3_PREP + pb];
-                const Fwd3Prep &Pn = prep[h * BW3_PREP + pbn];
-                const bool has_next = g + 1 < gtotal;
-                const int sbuf = g & 1;
-                mbar_wait(&bars->prep_full[h][pb], (g / BW3_PREP) & 1);
-                if (warp == 0) F3_TRACE(8);
-                if (has_prev) {
-                    mbar_wait(&bars->d_full[pq], nd & 1);
-                    nd++;
-                    tc_fence_after();
-                }
-                if (warp == 0) F3_TRACE(9);
-                if (warp == 4) F3_TRACE(14);
-                mbar_wait(&bars->s_free[pq][sbuf], ((g >> 1) & 1) ^ 1);     // the store of step g-2 has read this buffer
-                if (warp == 0) F3_TRACE(10);
-                if (has_next) mbar_wait(&bars->prep_full[h][pbn], ((g + 1) / BW3_PREP) & 1);
-                unsigned char *st_c = sSt + (h * 2 + sbuf) * BW_HTILE + 32 * c * 128;   // this warp's 32 rows of the stash tile
-                auto body = [&](auto firstc, auto livec) {
-                    constexpr bool FIRST = decltype(firstc)::value;       // t = 0: W_0 = pi . b(o_0)
-                    constexpr bool ALLLIVE = decltype(livec)::value;
-#pragma unroll
-                    for (int k4 = 0; k4 < 8; k4++) {
-                        const int bq = 32 * c + 4 * k4;
-                        uint32_t d4[4], s4[4];
-                        if (!FIRST) {
-                            tmem_ld_32x4(t_d + 4 * k4, d4);
-                            tmem_ld_32x4(t_s + 4 * k4, s4);
-                        }
-                        float4 l4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                        if (!ALLLIVE) l4 = *reinterpret_cast<const float4 *>(P.livef + bq);
-                        const float lf4[4] = {l4.x, l4.y, l4.z, l4.w};
-                        if (!FIRST) tmem_ld_wait();
-                        float x4[4];
-#pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            const int kb = 4 * k4 + kk;
-                            const float x = FIRST ? pij * e[kb] : (__uint_as_float(d4[kk]) * e[kb]) * rcp_approx(__uint_as_float(s4[kk]));
-                            x4[kk] = x;
-                            const uint32_t off = kb * 128 + (kbase ^ ((kb & 7) << 4));
-                            if (!SPLIT) *reinterpret_cast<uint32_t *>(op_c + off) = tf32_bits(x);
-                            // the stash row of a dead (sequence, step) pair is zero (the recursion itself runs on)
-                            *reinterpret_cast<float *>(st_c + off) = ALLLIVE ? x : x * lf4[kk];
-                        }
-                        if (SPLIT) {
-                            // even lanes take the state pair (j, j+1) of sequence b, odd lanes the pair (j-1, j) of sequence b+1
-#pragma unroll
-                            for (int kk = 0; kk < 4; kk += 2) {
-                                const int kb = 4 * k4 + kk;
-                                const float mine = (lane & 1) ? x4[kk] : x4[kk + 1];
-                                const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                                const float p0 = (lane & 1) ? other : x4[kk];
-                                const float p1 = (lane & 1) ? x4[kk + 1] : other;
-                                uint32_t hi, lo;
-                                split_bf16x2(p0, p1, hi, lo);
-                                const uint32_t offA = kb * 128 + ((c16 ^ (kb & 7)) << 4);
-                                const uint32_t offB = (kb + 1) * 128 + ((c16 ^ ((kb + 1) & 7)) << 4);
-                                unsigned char *dst = op_c + hbase + ((lane & 1) ? offB : offA);
-                                *reinterpret_cast<uint32_t *>(dst) = hi;
-                                *reinterpret_cast<uint32_t *>(dst + 2 * BW_HSUB) = lo;
-                            }
-                        }
-                        if (!FIRST && issuer) *reinterpret_cast<uint4 *>(sc_out + 4 * k4) = make_uint4(s4[0], s4[1], s4[2], s4[3]);
-                        // the emission values of the next step (the next tile's first step after t = T-1), these 4 sequences
-                        if (has_next) {
-                            const uint4 n4 = *reinterpret_cast<const uint4 *>(Pn.roff + bq);
-                            e[4 * k4] = __ldg(addr_f32(Bj, n4.x));
-                            e[4 * k4 + 1] = __ldg(addr_f32(Bj, n4.y));
-                            e[4 * k4 + 2] = __ldg(addr_f32(Bj, n4.z));
-                            e[4 * k4 + 3] = __ldg(addr_f32(Bj, n4.w));
-                        }
-                    }
-                };
-                if (!has_prev) {
-                    if (P.alllive) body(std::true_type{}, std::true_type{});
-                    else body(std::true_type{}, std::false_type{});
-                } else {
-                    if (P.alllive) body(std::false_type{}, std::true_type{});
-                    else body(std::false_type{}, std::false_type{});
-                }
-                if (warp == 0) F3_TRACE(11);
-                fence_proxy_async();          // both tiles are read through the async proxy (tensor core, TMA store)
-                tc_fence_before();
-                mbar_arrive(&bars->v_ready[pq]);
-                mbar_arrive(&bars->s_full[pq]);
-                if (warp == 0) F3_TRACE(12);
-                if (warp == 4) F3_TRACE(15);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->prep_empty[h][pb]);
-                __syncwarp();       // the tcgen05 loads of the next step are warp-collective
-                g++;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 17) tmem_dealloc(tmem, 512);
-}
-
-// log P of every sequence from the stored scale factors (tile-major [tile][t][row]): mantissa product + exponent sum, one
-// log per sequence
-static __global__ void bw_loglik_kernel(const float *__restrict__ scale, BwObs ob, int64_t B, int64_t T, double *__restrict__ loglik) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const float *sc = scale + (b >> 7) * T * 128 + (b & 127);
-    const int len = ob.len(b);
-    float prod = 1.f;
-    int esum = 0;
-    for (int t = 0; t < len; t++) {
-        int ex;
-        prod = frexpf(prod * sc[(int64_t)t * 128], &ex);
-        esum += ex;
-    }
-    loglik[b] = (double)esum * 0.6931471805599453 + log((double)prod);
-}
-
 // Fold the fp32 table replicas into the float64 count buffer:
 //   emis_num[k][i] += sum_r tab[r][k][i];  emis_den[i] += sum_k (that);  pi[i] += row M;
 //   gam[i] += emis_den part - row M+1 (gamma_ref summed over t < T-1);  loglik, nseq.
@@ -2267,13 +1440,12 @@ struct BwWorkspace {
 };
 
 // Which backward kernel: 3 = the transposed kernel with four quarter-tile pipelines (bw_backward_tc3_kernel, the default, both
-// operand precisions); 1 = the round-1 thread-per-sequence kernel (bw_backward_tc_kernel, both precisions); 2 = the first
-// transposed kernel (bw_backward_tc2_kernel, tf32 only).  All three produce the same statistics to rounding; the older ones
-// stay as cross-checks ($KHMM_BW_BACKWARD or khmm_debug_bw_backward_version select them).
-static int bw_backward_version() {
-    const int v = dev_switch(SW_BW_BACKWARD);
-    return (v == 1 || v == 2) ? v : 3;
-}
+// operand precisions); 1 = the round-1 thread-per-sequence kernel (bw_backward_tc_kernel, both precisions), kept as the
+// independent cross-check of the default ($KHMM_BW_BACKWARD or khmm_debug_bw_backward_version select it).  Two further
+// round-2 kernels were measured and removed: a transposed backward kernel with ONE tile per CTA (17.2-17.5 ms at config-4
+// size against 17.0-17.7 ms for kernel 1) and a forward kernel on the quarter-tile structure (slower than the forward
+// kernel above: DESIGN.md 3.5).
+static int bw_backward_version() { return dev_switch(SW_BW_BACKWARD) == 1 ? 1 : 3; }
 
 static BwWorkspace bw_layout(void *ws, int64_t B, int64_t T, int M) {
     auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
@@ -2327,7 +1499,7 @@ int khmm_debug_bw_trace(int64_t *dev_buf) {
 }
 
 int khmm_debug_bw_backward_version(int version) {
-    KHMM_REQUIRE(version >= 0 && version <= 3, "debug_bw_backward_version: 0 (default), 1, 2 or 3");
+    KHMM_REQUIRE(version == 0 || version == 1 || version == 3, "debug_bw_backward_version: 0 (default), 1 or 3");
     return khmm_debug_switch("KHMM_BW_BACKWARD", version == 0 ? -1 : version);
 }
 
@@ -2448,24 +1620,7 @@ int khmm_estep_tc_discrete_ex_f32(int64_t B, int64_t T, int N, int M, const floa
             }
         }
         if (tev) KHMM_CUDA_CHECK(cudaEventRecord(tev[0], st));
-        if (dev_switch(SW_BW_FORWARD) == 3) {
-            KHMM_REQUIRE(M <= (1 << 22), "estep_tc: alphabet size %d exceeds 2^22", M);
-            CUtensorMap mapStashQ;
-            if (make_tmap_stash(&mapStashQ, w.stash, B, T, CU_TENSOR_MAP_SWIZZLE_128B, 32)) {
-                set_error("estep_tc: tensor map creation failed");
-                return KHMM_ERR_CUDA;
-            }
-            size_t smem3 = 6 * (size_t)BW_HTILE + 2 * BW3_PREP * sizeof(Fwd3Prep) + sizeof(Fwd3Bars) + 1024;
-            if (split) {
-                KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc3_kernel<KHMM_TC_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-                bw_forward_tc3_kernel<KHMM_TC_BF16X3><<<grid, BW3_THREADS, smem3, st>>>(mapStashQ, AT, pi, Bsm, ob, B, T, w.scale, g_bw_trace);
-            } else {
-                KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_forward_tc3_kernel<KHMM_TC_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-                bw_forward_tc3_kernel<KHMM_TC_TF32><<<grid, BW3_THREADS, smem3, st>>>(mapStashQ, w.ATr, pi, Bsm, ob, B, T, w.scale, g_bw_trace);
-            }
-            KHMM_LAUNCH_CHECK("bw_forward_tc3_kernel");
-            bw_loglik_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(w.scale, ob, B, T, w.loglik);
-        } else if (operand_precision == KHMM_TC_BF16X3)
+        if (operand_precision == KHMM_TC_BF16X3)
             bw_forward_tc_kernel<KHMM_TC_BF16X3><<<grid, 384, smem, st>>>(mapAT, mapATlo, mapStashSt, pi, Bsm, ob, B, T, w.scale,
                                                                           w.loglik, g_bw_trace);
         else
@@ -2501,39 +1656,9 @@ int khmm_estep_tc_discrete_ex_f32(int64_t B, int64_t T, int N, int M, const floa
         } else if (operand_precision == KHMM_TC_BF16X3) {
             bw_backward_tc_kernel<KHMM_TC_BF16X3><<<grid, 384, smem, st>>>(mapA, mapAlo, mapStash, Bsm, ob, B, T, w.scale, out);
             KHMM_LAUNCH_CHECK("bw_backward_tc_kernel<bf16x3>");
-        } else if (bw_backward_version() == 1) {
+        } else {
             bw_backward_tc_kernel<KHMM_TC_TF32><<<grid, 384, smem, st>>>(mapA, mapAlo, mapStash, Bsm, ob, B, T, w.scale, out);
             KHMM_LAUNCH_CHECK("bw_backward_tc_kernel");
-        } else {
-            KHMM_REQUIRE(M <= (1 << 22), "estep_tc: alphabet size %d exceeds 2^22", M);
-            // emission table rows for the TMA gather: [M][128] fp32, box = one full row (gather4 takes 4 row indices)
-            CUtensorMap mapB;
-            {
-                static PFN_encodeTiled encode = nullptr;
-                if (!encode) {
-                    void *fn = nullptr;
-                    cudaDriverEntryPointQueryResult q;
-                    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
-                        set_error("estep_tc: cuTensorMapEncodeTiled is unavailable");
-                        return KHMM_ERR_CUDA;
-                    }
-                    encode = (PFN_encodeTiled)fn;
-                }
-                cuuint64_t dims[2] = {(cuuint64_t)BW_N, (cuuint64_t)M};
-                cuuint64_t strides[1] = {(cuuint64_t)BW_N * 4};
-                cuuint32_t box[2] = {(cuuint32_t)BW_N, 1};
-                cuuint32_t estr[2] = {1, 1};
-                if (encode(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)Bsm, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-                    set_error("estep_tc: tensor map creation for the emission table failed (is Bsm 16-byte aligned?)");
-                    return KHMM_ERR_CUDA;
-                }
-            }
-            size_t smem2 = 2 * (size_t)BW_TILE + 4 * (size_t)BW_SLAB + 2 * sizeof(Bwd2Prep) + sizeof(Bwd2Bars) + 1024;
-            KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_backward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            bw_backward_tc2_kernel<<<grid, 512, smem2, st>>>(mapStash, mapB, w.Ar, ob, B, T, w.scale, out);
-            KHMM_LAUNCH_CHECK("bw_backward_tc2_kernel");
         }
         if (tev) KHMM_CUDA_CHECK(cudaEventRecord(tev[2], st));
     }

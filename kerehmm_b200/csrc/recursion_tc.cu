@@ -242,7 +242,7 @@ __device__ __forceinline__ void wait_chain(const uint32_t *ctr, uint32_t need) {
 // only depend on the same chain's jobs of the previous step; a job waits for its inputs on a per-chain completion
 // counter in global memory (release by the producing epilogue, acquire by the consuming TMA thread) instead of on a
 // kernel boundary, and only ever for jobs that precede it in every CTA's order, so the globally smallest unfinished
-// job can always run (all CTAs are co-resident).  The clock64 timeline of the first generation (tools/dbg_rc_trace.py)
+// job can always run (all CTAs are co-resident).  The clock64 timeline of the first generation (tools/recursion_tc_timeline.py)
 // showed a job's MMAs taking 8.7k cycles (bf16) while its epilogue took 19k -- 9.5k of exposed L2 latency before the
 // accumulator is even needed (serial row-sum loads, emission constants, a CTA barrier) and 9.4k of TMEM reads,
 // emission evaluation and thread-per-row stores -- with ONE epilogue warpgroup serialising both; and 108 of the 148

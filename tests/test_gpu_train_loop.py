@@ -154,14 +154,14 @@ def test_comm_entry_points_single_rank(K):
     assert L.khmm_comm_destroy(None) == 0
 
 
-# ------------------------------------------------------- the three backward kernels of the fused E-step
+# ------------------------------------------------------- the two backward kernels of the fused E-step
 @pytest.mark.parametrize("M,B,T,ragged", [(16, 128, 1, False), (16, 128, 2, False), (16, 130, 8, False), (48, 300, 33, True),
                                           (1024, 1000, 20, False), (24, 700, 64, True), (64, 148 * 128 + 77, 5, True)])
 def test_backward_kernels_of_the_fused_estep_agree(K, M, B, T, ragged):
     """bw_backward_tc3_kernel (the default: thread = state, four quarter-tile pipelines per CTA, emission values and count
-    reductions straight from registers) and bw_backward_tc2_kernel (thread = state, one tile per CTA) against
-    bw_backward_tc_kernel (thread = sequence) and the float64 oracle: same statistics on equal-length and ragged batches,
-    partial tiles, more tiles than CTAs, T = 1 and T = 2; the default kernel in both operand precisions."""
+    reductions straight from registers) against bw_backward_tc_kernel (thread = sequence) and the float64 oracle: same
+    statistics on equal-length and ragged batches, partial tiles, more tiles than CTAs, T = 1 and T = 2, in both operand
+    precisions."""
     from kerehmm_b200 import _lib, engine
     N = 128
     h, (pi, A, Bm) = random_discrete(K, N, M, seed=N + M + B + T)
@@ -172,8 +172,7 @@ def test_backward_kernels_of_the_fused_estep_agree(K, M, B, T, ragged):
     p = h._params()
     res = {}
     try:
-        for version, prec in ((1, engine.TC_TF32), (2, engine.TC_TF32), (3, engine.TC_TF32), (1, engine.TC_BF16X3),
-                              (3, engine.TC_BF16X3)):
+        for version, prec in ((1, engine.TC_TF32), (3, engine.TC_TF32), (1, engine.TC_BF16X3), (3, engine.TC_BF16X3)):
             _lib.call("khmm_debug_bw_backward_version", version)
             res[(version, prec)] = engine.estep_discrete_tc(p, ob, precision=prec).host()
     finally:

@@ -1,5 +1,7 @@
-"""Development: the half-tile ping-pong backward kernel (v3) against the round-1 kernel (v1) and the float64 oracle on small
-shapes, both operand precisions; then kernel times at config-4 size and a timeline."""
+"""Development: the quarter-tile pipeline backward kernel (v3, the default) against the round-1 kernel (v1) and the float64
+oracle on small shapes, both operand precisions; then kernel times at config-4 size and a clock64 timeline of block 0.
+
+    python tools/estep_backward_check.py [sequences, default 131072]      (QUICK=1: one small shape only)"""
 import ctypes, sys, os, numpy as np, torch
 sys.path.insert(0, '.')
 import kerehmm_b200 as K

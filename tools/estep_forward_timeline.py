@@ -1,4 +1,4 @@
-"""Development: per-role clock64 timeline of the backward tensor-core kernel (block 0, steps 8..15)."""
+"""Development: per-role clock64 timeline of the forward (and round-1 backward) tensor-core kernels (block 0, steps 8..15)."""
 import ctypes, sys, numpy as np, torch
 sys.path.insert(0, '.')
 import kerehmm_b200 as K

@@ -1,4 +1,6 @@
-"""Development: kernel times of the tensor-core E-step at config-4 size for one library variant (KHMM_VARIANT), backward v3."""
+"""Development: forward / backward kernel times of the fused tensor-core E-step at config-4 shape, both operand precisions.
+
+    [KHMM_VARIANT=<name of a tools/build_variant.sh library>] [KHMM_VER=1|3] python tools/estep_kernel_times.py [sequences]"""
 import ctypes, sys, os, numpy as np, torch
 sys.path.insert(0, '.')
 from kerehmm_b200 import _lib
