@@ -170,6 +170,27 @@ def cpu_leg(kind, model, obs, cores):
         sb, st, len(chunks)), len(chunks), dt
 
 
+# bounded samples for the REAL reference (pure Python, one thread): one sequence, a few seconds each
+REAL_REF_T = {"c1": 1000, "c2": 64, "c3": 128, "c4": 32, "c5": 0}
+
+
+def real_reference_live(kind):
+    """The REAL reference timed live on this box's host (one thread, one short sequence) by oracle/time_reference_live.py
+    in a child interpreter, so that its `kerehmm` package never shares a process with the product.  None when there is
+    nothing to run (no converted copy under oracle/_ref and no /root/reference)."""
+    if not REAL_REF_T.get(kind):
+        return None
+    if not (os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "kerehmm")) or os.path.isdir("/root/reference/kerehmm")):
+        return None
+    desc, N, M, _, _ = WORKLOADS[kind]
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "time_reference_live.py"), kind, str(N), str(M),
+                            str(REAL_REF_T[kind]), str(CFG_INDEX[kind])], capture_output=True, text=True, timeout=120, cwd=ROOT)
+        return json.loads(p.stdout.strip().splitlines()[-1])
+    except Exception as e:          # the port stands as the baseline; say why the reference itself did not run
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def real_reference_note(kind):
     """The REAL reference (pure Python 2, converted in memory by oracle/ref_loader.py) cannot travel to the GPU box; it
     was timed in the build container on bounded samples (oracle/time_reference.py): one thread, same N/M."""
@@ -757,7 +778,8 @@ def run_ours(args):
         if ctx.world == 1 and not args.no_cpu:
             cv, sample, cores, dt = cpu_leg(kind, w.model, w.obs_h, args.cpu_cores)
             out["cpu_baseline"] = {"value": cv, "unit": "transitions/s", "cores": cores, "kind": "port",
-                                   "sample": sample, "seconds": dt, "real_reference": real_reference_note(kind)}
+                                   "sample": sample, "seconds": dt, "real_reference": real_reference_note(kind),
+                                   "real_reference_live": real_reference_live(kind)}
     main_model, main_obs = w.model, w.obs_h
     del w
     engine.release_workspace()
@@ -825,7 +847,7 @@ def run_reference(args):
            "config": {"workload": desc, "name": kind, "N": N, "M": M, "B_per_gpu": B, "T": T, "sharding": sharding,
                       "l2": "n/a (CPU arm: each step is a bounded sample of the workload, see cpu_baseline.sample)"},
            "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": used, "kind": "port", "sample": sample,
-                            "real_reference": real_reference_note(kind)},
+                            "real_reference": real_reference_note(kind), "real_reference_live": real_reference_live(kind)},
            "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)

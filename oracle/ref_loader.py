@@ -13,7 +13,12 @@ reference sources are not copied into the repo) and imports it as package
 ``kerehmm``.  No arithmetic line is touched; see SURVEY.md section 8(c).
 
 Only ``oracle/make_golden.py`` (run in the build container, where /root/reference
-exists) and optional CPU tests use this.  Nothing on the GPU box needs it.
+exists), optional CPU tests and the ``cpu_baseline`` leg of ``bench.py`` use this.
+
+``materialize()`` (called by ``__graft_entry__.build()`` where /root/reference exists) writes the converted package to
+``oracle/_ref/`` -- git-ignored like a compiled reference binary would be, so it never enters the history, but part of
+the ``gpurun`` snapshot -- so that ``bench.py`` can time the REAL reference next to the NumPy port on the GPU box's own
+host cores.  ``load_reference()`` falls back to that directory when /root/reference is absent.
 """
 from __future__ import annotations
 
@@ -69,6 +74,28 @@ def py2_to_py3(source: str) -> str:
 
 
 _loaded = None
+MATERIALIZED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _convert_into(pkg_src: str, dst: str):
+    os.makedirs(dst, exist_ok=True)
+    for name in sorted(os.listdir(pkg_src)):
+        if not name.endswith(".py"):
+            continue
+        with open(os.path.join(pkg_src, name)) as f:
+            src = f.read()
+        with open(os.path.join(dst, name), "w") as f:
+            f.write(py2_to_py3(src))
+
+
+def materialize(root: str | None = None, dest_root: str | None = None) -> str | None:
+    """Write the converted reference package to oracle/_ref/kerehmm (build step; no-op without /root/reference)."""
+    pkg_src = os.path.join(root or REFERENCE_ROOT, "kerehmm")
+    if not os.path.isdir(pkg_src):
+        return None
+    dest_root = dest_root or MATERIALIZED
+    _convert_into(pkg_src, os.path.join(dest_root, "kerehmm"))
+    return dest_root
 
 
 def load_reference(root: str | None = None):
@@ -81,18 +108,13 @@ def load_reference(root: str | None = None):
         return _loaded
     root = root or REFERENCE_ROOT
     pkg_src = os.path.join(root, "kerehmm")
-    if not os.path.isdir(pkg_src):
+    if os.path.isdir(pkg_src):
+        dst_root = tempfile.mkdtemp(prefix="khmm_ref_py3_")
+        _convert_into(pkg_src, os.path.join(dst_root, "kerehmm"))
+    elif os.path.isdir(os.path.join(MATERIALIZED, "kerehmm")):
+        dst_root = MATERIALIZED          # the GPU box: the copy that build() wrote before the snapshot was taken
+    else:
         raise FileNotFoundError(pkg_src)
-    dst_root = tempfile.mkdtemp(prefix="khmm_ref_py3_")
-    dst = os.path.join(dst_root, "kerehmm")
-    os.makedirs(dst)
-    for name in sorted(os.listdir(pkg_src)):
-        if not name.endswith(".py"):
-            continue
-        with open(os.path.join(pkg_src, name)) as f:
-            src = f.read()
-        with open(os.path.join(dst, name), "w") as f:
-            f.write(py2_to_py3(src))
     sys.path.insert(0, dst_root)
     for mod in [m for m in sys.modules if m == "kerehmm" or m.startswith("kerehmm.")]:
         del sys.modules[mod]
@@ -104,4 +126,4 @@ def load_reference(root: str | None = None):
 
 
 def reference_available(root: str | None = None) -> bool:
-    return os.path.isdir(os.path.join(root or REFERENCE_ROOT, "kerehmm"))
+    return os.path.isdir(os.path.join(root or REFERENCE_ROOT, "kerehmm")) or os.path.isdir(os.path.join(MATERIALIZED, "kerehmm"))
