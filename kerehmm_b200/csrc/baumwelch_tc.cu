@@ -926,17 +926,32 @@ struct __align__(16) Bwd3Prep {   // per-sequence scalars of one step of one hal
     int anylast;       // some sequence of the half has its last step here (the compute warps then read lastf)
     int pad[3];
 };
-// base + off floats in one IMAD.WIDE (the compiler's LEA / IADD.X pair costs two issue slots per address)
-__device__ __forceinline__ float *addr_f32(const float *base, uint32_t off) {
-    uint64_t a;
-    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(off), "l"(base));
-    return reinterpret_cast<float *>(a);
-}
+// base + off floats with ONE 32-bit add: the host guarantees that neither table straddles a 4 GB boundary, so the high word
+// of the address is a constant of the thread (the compiler's 64-bit LEA / LEA.HI.X pair per address was 4 of the 17.6
+// instructions per (sequence, state) of the loop body)
+struct Base32 {
+    uint32_t lo, hi;
+    __device__ __forceinline__ explicit Base32(const float *p) {
+        const uint64_t a = reinterpret_cast<uint64_t>(p);
+        lo = (uint32_t)a;
+        hi = (uint32_t)(a >> 32);
+    }
+    __device__ __forceinline__ float *at(uint32_t off) const {
+        uint64_t a;
+        const uint32_t l = lo + (off << 2);
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(l), "r"(hi));
+        return reinterpret_cast<float *>(a);
+    }
+};
 __device__ __forceinline__ void red_add_f32_nc(float *p, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a));
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+static bool within_4gb_window(const void *p, size_t bytes) {
+    const uintptr_t a = (uintptr_t)p;
+    return bytes == 0 || (a >> 32) == ((a + bytes - 1) >> 32);
 }
 
 template <int PREC>
@@ -1178,7 +1193,7 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
         unsigned char *vk_c = sV + h * BW_HTILE + 32 * c * 128;       // this warp's 32 sequences of the V tile
         float *tabr = out.tab + (size_t)(blockIdx.x % BW_REPL) * (size_t)(M + 2) * BW_N;
         float *tab0 = tabr + i;
-        const float *Bi = Bsm + i;
+        const Base32 tabB(tab0), emB(Bsm + i);
         float e[32];
         if (gtotal) {
             mbar_wait(&bars->prep_full[h][0], 0);
@@ -1186,10 +1201,10 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
 #pragma unroll
             for (int k4 = 0; k4 < 8; k4++) {
                 const uint4 s4 = *reinterpret_cast<const uint4 *>(P0.roff + 32 * c + 4 * k4);
-                e[4 * k4] = __ldg(addr_f32(Bi, s4.x));
-                e[4 * k4 + 1] = __ldg(addr_f32(Bi, s4.y));
-                e[4 * k4 + 2] = __ldg(addr_f32(Bi, s4.z));
-                e[4 * k4 + 3] = __ldg(addr_f32(Bi, s4.w));
+                e[4 * k4] = __ldg(emB.at(s4.x));
+                e[4 * k4 + 1] = __ldg(emB.at(s4.y));
+                e[4 * k4 + 2] = __ldg(emB.at(s4.z));
+                e[4 * k4 + 3] = __ldg(emB.at(s4.w));
             }
         }
         uint32_t nd = 0, g = 0, ntile = 0;
@@ -1226,6 +1241,7 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
                     constexpr bool T0 = decltype(t0c)::value;
                     constexpr bool MMA = decltype(mmac)::value;
                     constexpr bool LAST = decltype(lastc)::value;     // some sequence of the half ends at this step
+                    float vprev[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int k4 = 0; k4 < 8; k4++) {
                         const int bq = 32 * c + 4 * k4;
@@ -1258,7 +1274,7 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
                             v4[kk] = v;
                             d4[kk] = tf32_bits(v);
                             if (!T0) {
-                                red_add_f32_nc(addr_f32(tab0, sy4[kk]), gm);
+                                red_add_f32_nc(tabB.at(sy4[kk]), gm);
                                 if (LAST) glast = fmaf(gm, lf4[kk], glast);
                                 if (!SPLIT) *reinterpret_cast<uint32_t *>(vk_c + kb * 128 + (kbase ^ ((kb & 7) << 4))) = d4[kk];
                             } else {
@@ -1269,30 +1285,38 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
                         }
                         if (!T0) tmem_st_32x4(t_d1 + 4 * k4, d4);
                         if (SPLIT && !T0) {
-                            // even lanes take the state pair (i, i+1) of sequence b, odd lanes the pair (i-1, i) of sequence b+1
+                            // bf16 pairs: even lanes take the state pair (i, i+1) of sequence b, odd lanes the pair (i-1, i) of
+                            // sequence b+4 -- rows b and b+4 put their 64 bytes into DIFFERENT halves of the 32 banks (rows b and
+                            // b+1 share a half: ncu counted 1.96 wavefronts per store) -- so a group of four waits for its partner
+                            // group: the stores of groups 2m and 2m+1 are issued together
+                            if (k4 & 1) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; kk += 2) {
-                                const int kb = 4 * k4 + kk;
-                                const float mine = (lane & 1) ? v4[kk] : v4[kk + 1];
-                                const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                                const float p0 = (lane & 1) ? other : v4[kk];
-                                const float p1 = (lane & 1) ? v4[kk + 1] : other;
-                                uint32_t hi, lo;
-                                split_bf16x2(p0, p1, hi, lo);
-                                const uint32_t offA = kb * 128 + ((c16 ^ (kb & 7)) << 4);
-                                const uint32_t offB = (kb + 1) * 128 + ((c16 ^ ((kb + 1) & 7)) << 4);
-                                unsigned char *dst = vk_c + hbase + ((lane & 1) ? offB : offA);
-                                *reinterpret_cast<uint32_t *>(dst) = hi;
-                                *reinterpret_cast<uint32_t *>(dst + 2 * BW_HSUB) = lo;
+                                for (int kk = 0; kk < 4; kk++) {
+                                    const int kb = 4 * (k4 - 1) + kk;          // partner: kb + 4
+                                    const float mine = (lane & 1) ? vprev[kk] : v4[kk];
+                                    const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                                    const float p0 = (lane & 1) ? other : vprev[kk];
+                                    const float p1 = (lane & 1) ? v4[kk] : other;
+                                    uint32_t hi, lo;
+                                    split_bf16x2(p0, p1, hi, lo);
+                                    const uint32_t offA = kb * 128 + ((c16 ^ (kb & 7)) << 4);
+                                    const uint32_t offB = (kb + 4) * 128 + ((c16 ^ ((kb + 4) & 7)) << 4);
+                                    unsigned char *dst = vk_c + hbase + ((lane & 1) ? offB : offA);
+                                    *reinterpret_cast<uint32_t *>(dst) = hi;
+                                    *reinterpret_cast<uint32_t *>(dst + 2 * BW_HSUB) = lo;
+                                }
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < 4; kk++) vprev[kk] = v4[kk];
                             }
                         }
                         // the emission values of the next step (the next tile's first step after t = 0), these 4 sequences
                         if (has_next) {
                             const uint4 n4 = *reinterpret_cast<const uint4 *>(Pn.roff + bq);
-                            e[4 * k4] = __ldg(addr_f32(Bi, n4.x));
-                            e[4 * k4 + 1] = __ldg(addr_f32(Bi, n4.y));
-                            e[4 * k4 + 2] = __ldg(addr_f32(Bi, n4.z));
-                            e[4 * k4 + 3] = __ldg(addr_f32(Bi, n4.w));
+                            e[4 * k4] = __ldg(emB.at(n4.x));
+                            e[4 * k4 + 1] = __ldg(emB.at(n4.y));
+                            e[4 * k4 + 2] = __ldg(emB.at(n4.z));
+                            e[4 * k4 + 3] = __ldg(emB.at(n4.w));
                         }
                     }
                 };
@@ -1637,8 +1661,10 @@ int khmm_estep_tc_discrete_ex_f32(int64_t B, int64_t T, int N, int M, const floa
         double *c_xi = counts + BW_N;
         double *c_tail = counts + BW_N + (size_t)BW_N * BW_N + BW_N + (size_t)M * BW_N + BW_N;
         BwdOut out{g_bw_trace, w.tab, c_xi, c_tail + 2};
-        if (bw_backward_version() == 3) {
-            KHMM_REQUIRE(M <= (1 << 22), "estep_tc: alphabet size %d exceeds 2^22", M);
+        // kernel 3 forms table addresses with 32-bit adds: both tables must lie inside one 4 GB window each (else kernel 1)
+        const bool windows_ok = within_4gb_window(Bsm, (size_t)M * BW_N * 4) &&
+                                within_4gb_window(w.tab, (size_t)BW_REPL * (M + 2) * BW_N * 4);
+        if (bw_backward_version() == 3 && windows_ok && M <= (1 << 22)) {
             CUtensorMap mapStashH;
             if (make_tmap_stash(&mapStashH, w.stash, B, T, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 64)) {
                 set_error("estep_tc: tensor map creation failed");
