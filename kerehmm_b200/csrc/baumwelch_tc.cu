@@ -253,7 +253,7 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
             for (int64_t t = 0; t < T; t++) {
                 const int buf = (int)(t & 1);
                 const int s0 = ob.sym(b0, t), s1 = ob.sym(b1, t);
-                mbar_wait(&bars->buf_free[buf], (nuse[buf] & 1) ^ 1);
+                mbar_wait_relaxed(&bars->buf_free[buf], (nuse[buf] & 1) ^ 1);      // a step of slack
                 nuse[buf]++;
                 if (warp == 9) FW_TRACE(4);
                 unsigned char *dstb = ebuf + buf * FW_EBUF;
@@ -279,7 +279,7 @@ bw_forward_tc_kernel(const __grid_constant__ CUtensorMap mapAT, const __grid_con
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
                 for (int64_t t = 0; t < T; t++) {
                     const int buf = (int)(t & 1);
-                    mbar_wait(&bars->w_ready[buf], nuse[buf] & 1);
+                    mbar_wait_relaxed(&bars->w_ready[buf], nuse[buf] & 1);      // off the MMA -> epilogue chain
                     nuse[buf]++;
                     FW_TRACE(8);
                     for (int c = 0; c < 4; c++)
@@ -1042,7 +1042,7 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
                     const int buf = g & 1;
                     const uint32_t par = ((g >> 1) & 1) ^ 1;
                     for (int h = 0; h < 2; h++) {
-                        mbar_wait(&bars->w_empty[h][buf], par);
+                        mbar_wait_relaxed(&bars->w_empty[h][buf], par);      // a step of slack
                         if (h == 0) BW2_TRACE(0);
                         mbar_arrive_expect_tx(&bars->w_full[h][buf], BW_HTILE);
                         unsigned char *dst = sW + (h * 2 + buf) * BW_HTILE;
@@ -1156,7 +1156,7 @@ bw_backward_tc3_kernel(const __grid_constant__ CUtensorMap mapStashH, const floa
             for (int k = 0; k < 2; k++) { sy[k] = syn[k]; c1[k] = c1n[k]; c0[k] = c0n[k]; cm[k] = cmn[k]; lenc[k] = lenn[k]; }
             if (g + 1 < gtotal) issue(g + 1);
             const int buf = g % BW3_PREP;
-            mbar_wait(&bars->prep_empty[h][buf], ((g / BW3_PREP) & 1) ^ 1);
+            mbar_wait_relaxed(&bars->prep_empty[h][buf], ((g / BW3_PREP) & 1) ^ 1);     // three steps of slack
             Bwd3Prep &P = prep[h * BW3_PREP + buf];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
