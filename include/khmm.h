@@ -172,6 +172,26 @@ int khmm_emissions_discrete_f64(int64_t B, int64_t T, int N, int M, const double
                                 int obs_dtype, double *E, khmm_stream_t stream);
 int khmm_emissions_gauss_f64(int64_t B, int64_t T, int N, const double *mean, const double *sd, const void *obs,
                              int obs_dtype, double *E, khmm_stream_t stream);
+/* Forward / backward with FUSED full-covariance Gaussian emissions, D <= KHMM_GAUSS_FULL_DMAX features
+ * (GaussianDistribution with a covariance matrix, distribution.py:153; AbstractHMM.forward / backward,
+ * abstract_hmm.py:250-285, 327-351): no [B][T][N] emission matrix is materialised.  means[N][D], Linv[N][D][D],
+ * lognorm[N] as for khmm_emissions_gauss_full_f64 below (float64 whatever the recursion's type: the density is
+ * evaluated in float64 with that function's operation order, then cast); obs[B][T][D] (f32/f64). */
+#define KHMM_GAUSS_FULL_DMAX 8
+int khmm_forward_gaussfull_f32(int64_t B, int64_t T, int N, int D, const float *pi, const float *A, const double *means,
+                               const double *Linv, const double *lognorm, const void *obs, int obs_dtype,
+                               const int32_t *lengths, float *alpha, float *scale, double *loglik, khmm_stream_t stream);
+int khmm_forward_gaussfull_f64(int64_t B, int64_t T, int N, int D, const double *pi, const double *A, const double *means,
+                               const double *Linv, const double *lognorm, const void *obs, int obs_dtype,
+                               const int32_t *lengths, double *alpha, double *scale, double *loglik, khmm_stream_t stream);
+int khmm_backward_gaussfull_f32(int64_t B, int64_t T, int N, int D, const float *AT, const double *means, const double *Linv,
+                                const double *lognorm, const void *obs, int obs_dtype, const int32_t *lengths,
+                                const float *scale, const float *alpha, float *beta, float *gamma, int gamma_kind,
+                                khmm_stream_t stream);
+int khmm_backward_gaussfull_f64(int64_t B, int64_t T, int N, int D, const double *AT, const double *means, const double *Linv,
+                                const double *lognorm, const void *obs, int obs_dtype, const int32_t *lengths,
+                                const double *scale, const double *alpha, double *beta, double *gamma, int gamma_kind,
+                                khmm_stream_t stream);
 /* Full-covariance Gaussians (distribution.py:153): means[N][D], Linv[N][D][D] = inverse of the lower
  * Cholesky factor of each covariance (row-major, lower triangular), lognorm[N] =
  * -0.5*(D*log(2*pi) + log det cov); obs[B][T][D] (f32/f64).  E = exp(lognorm - 0.5*|Linv (x-mean)|^2). */

@@ -95,6 +95,42 @@ struct GaussEmis {
     }
 };
 
+// Full-covariance Gaussian, D <= KHMM_GAUSS_FULL_DMAX features (distribution.py:153: scipy multivariate_normal(mean, cov).pdf):
+// b_j(x) = exp(lognorm_j - 0.5 |Linv_j (x - mean_j)|^2), Linv_j = inverse of the lower Cholesky factor of cov_j, lognorm_j =
+// -0.5 (D log 2 pi + log det cov_j).  Evaluated in float64 whatever R, operation for operation like
+// khmm_emissions_gauss_full_f64 (so the fused path and the dense-matrix path give the same emission values), then cast.
+template <typename R>
+struct GaussFullEmis {
+    const double *means, *Linv, *lognorm;   // [N][D], [N][D][D] (row-major, lower triangular), [N]
+    const void *obs;                        // [B][T][D]
+    int obs_dtype;
+    int N, D;
+    int64_t T;
+    struct Obs { double x[KHMM_GAUSS_FULL_DMAX]; };
+    __device__ __forceinline__ Obs load(int64_t b, int64_t t) const {
+        Obs o;
+#pragma unroll
+        for (int a = 0; a < KHMM_GAUSS_FULL_DMAX; a++) o.x[a] = a < D ? load_real<double>(obs, obs_dtype, (b * T + t) * D + a) : 0.0;
+        return o;
+    }
+    __device__ __forceinline__ R eval(const Obs &o, int j) const {
+        const double *mu = means + (int64_t)j * D;
+        const double *L = Linv + (int64_t)j * D * D;
+        double maha = 0.0;
+#pragma unroll
+        for (int a = 0; a < KHMM_GAUSS_FULL_DMAX; a++) {
+            if (a < D) {
+                double y = 0.0;
+#pragma unroll
+                for (int c = 0; c < KHMM_GAUSS_FULL_DMAX; c++)
+                    if (c <= a) y += __ldg(L + a * D + c) * (o.x[c] - __ldg(mu + c));
+                maha += y * y;
+            }
+        }
+        return (R)exp(__ldg(lognorm + j) - 0.5 * maha);
+    }
+};
+
 template <typename R>
 struct DenseEmis {
     const R *E;  // [B][T][N]

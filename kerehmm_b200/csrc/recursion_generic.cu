@@ -463,6 +463,16 @@ static int check_reals(int64_t B, int obs_dtype, const void *obs, const void *me
     return KHMM_OK;
 }
 
+static int check_gaussfull(int64_t B, int D, int obs_dtype, const void *obs, const void *means, const void *Linv,
+                           const void *lognorm) {
+    KHMM_REQUIRE(D >= 1 && D <= KHMM_GAUSS_FULL_DMAX, "gaussfull: D = %d features, supported 1 .. %d (use the dense-emission "
+                 "entry points beyond that)", D, KHMM_GAUSS_FULL_DMAX);
+    if (B == 0) return KHMM_OK;
+    KHMM_REQUIRE(obs && means && Linv && lognorm, "gaussfull: obs/means/Linv/lognorm must not be NULL");
+    KHMM_REQUIRE(obs_dtype == KHMM_F32 || obs_dtype == KHMM_F64, "gaussfull: obs dtype code %d is not f32/f64", obs_dtype);
+    return KHMM_OK;
+}
+
 }  // namespace khmm
 
 using namespace khmm;
@@ -482,6 +492,25 @@ using namespace khmm;
         if (rc) return rc;                                                                                            \
         GaussEmis<R> em{mean, sd, obs, obs_dtype, N, T};                                                              \
         return launch_forward<R>(B, T, N, pi, A, em, lengths, alpha, scale, loglik, stream);                          \
+    }
+#define FWD_GAUSSFULL(R, name)                                                                                        \
+    int name(int64_t B, int64_t T, int N, int D, const R *pi, const R *A, const double *means, const double *Linv,    \
+             const double *lognorm, const void *obs, int obs_dtype, const int32_t *lengths, R *alpha, R *scale,       \
+             double *loglik, khmm_stream_t stream) {                                                                  \
+        int rc = check_gaussfull(B, D, obs_dtype, obs, means, Linv, lognorm);                                         \
+        if (rc) return rc;                                                                                            \
+        GaussFullEmis<R> em{means, Linv, lognorm, obs, obs_dtype, N, D, T};                                           \
+        return launch_forward<R>(B, T, N, pi, A, em, lengths, alpha, scale, loglik, stream);                          \
+    }
+#define BWD_GAUSSFULL(R, name)                                                                                        \
+    int name(int64_t B, int64_t T, int N, int D, const R *AT, const double *means, const double *Linv,                \
+             const double *lognorm, const void *obs, int obs_dtype, const int32_t *lengths, const R *scale,           \
+             const R *alpha, R *beta, R *gamma, int gamma_kind, khmm_stream_t stream) {                               \
+        int rc = check_gaussfull(B, D, obs_dtype, obs, means, Linv, lognorm);                                         \
+        if (rc) return rc;                                                                                            \
+        GaussFullEmis<R> em{means, Linv, lognorm, obs, obs_dtype, N, D, T};                                           \
+        return launch_backward<R, GaussFullEmis<R>, false>(B, T, N, AT, em, lengths, scale, alpha, beta, gamma,       \
+                                                           gamma_kind, nullptr, EstepOut{nullptr, 0}, stream);        \
     }
 #define FWD_DENSE(R, name)                                                                                            \
     int name(int64_t B, int64_t T, int N, const R *pi, const R *A, const R *E, const int32_t *lengths, R *alpha,      \
@@ -533,6 +562,10 @@ FWD_DISCRETE(float, khmm_forward_discrete_f32)
 FWD_DISCRETE(double, khmm_forward_discrete_f64)
 FWD_GAUSS(float, khmm_forward_gauss_f32)
 FWD_GAUSS(double, khmm_forward_gauss_f64)
+FWD_GAUSSFULL(float, khmm_forward_gaussfull_f32)
+FWD_GAUSSFULL(double, khmm_forward_gaussfull_f64)
+BWD_GAUSSFULL(float, khmm_backward_gaussfull_f32)
+BWD_GAUSSFULL(double, khmm_backward_gaussfull_f64)
 FWD_DENSE(float, khmm_forward_dense_f32)
 FWD_DENSE(double, khmm_forward_dense_f64)
 BWD_DISCRETE(float, khmm_backward_discrete_f32)

@@ -242,6 +242,20 @@ def _emission_args(dm: DeviceModel):
     raise ValueError(k)
 
 
+GAUSS_FULL_DMAX = 8     # KHMM_GAUSS_FULL_DMAX: feature count up to which full-covariance emissions are fused into the recursions
+
+
+def _gauss_full_operands(p: ModelParams):
+    """Device float64 (means[N][D], Linv[N][D][D], lognorm[N]) of a full-covariance model: the inverse lower Cholesky
+    factor and the log normaliser of each state's density (distribution.py:153)."""
+    t = torch()
+    D = p.mean.shape[1]
+    Ls = np.linalg.cholesky(p.cov)
+    Linv = np.stack([np.linalg.inv(L) for L in Ls])
+    lognorm = -0.5 * (D * np.log(2.0 * np.pi) + 2.0 * np.log(np.diagonal(Ls, axis1=1, axis2=2)).sum(axis=1))
+    return D, _dev(p.mean, t.float64), _dev(Linv, t.float64), _dev(lognorm, t.float64)
+
+
 def dense_emissions(p: ModelParams, ob: Obs):
     """E[B][T][N] float64 on the device (abstract_hmm.py:362-366 batched)."""
     t = require_cuda()
@@ -256,11 +270,7 @@ def dense_emissions(p: ModelParams, ob: Obs):
         _lib.call("khmm_emissions_gauss_f64", ob.B, ob.T, N, ptr(mean), ptr(sd), ptr(ob.tensor), ob.code, ptr(E),
                   stream_ptr())
     else:
-        D = p.mean.shape[1]
-        Ls = np.linalg.cholesky(p.cov)
-        Linv = np.stack([np.linalg.inv(L) for L in Ls])
-        lognorm = -0.5 * (D * np.log(2.0 * np.pi) + 2.0 * np.log(np.diagonal(Ls, axis1=1, axis2=2)).sum(axis=1))
-        dm_, dl, dn = _dev(p.mean, t.float64), _dev(Linv, t.float64), _dev(lognorm, t.float64)
+        D, dm_, dl, dn = _gauss_full_operands(p)
         _lib.call("khmm_emissions_gauss_full_f64", ob.B, ob.T, N, D, ptr(dm_), ptr(dl), ptr(dn), ptr(ob.tensor),
                   ob.code, ptr(E), stream_ptr())
     return E
@@ -274,6 +284,12 @@ def forward(p: ModelParams, ob: Obs, real, want_alpha=True, want_scale=True, wan
     alpha = t.empty((ob.B, ob.T, N), dtype=real, device=dev) if want_alpha else None
     scale = t.empty((ob.B, ob.T), dtype=real, device=dev) if want_scale else None
     loglik = t.empty((ob.B,), dtype=t.float64, device=dev) if want_loglik else None
+    if p.kind == "gauss_full" and p.mean.shape[1] <= GAUSS_FULL_DMAX:
+        # fused emissions (round 2): no [B][T][N] emission matrix
+        D, dmean, dlinv, dnorm = _gauss_full_operands(p)
+        _lib.call("khmm_forward_gaussfull_" + dm.suffix, ob.B, ob.T, N, D, ptr(dm.pi), ptr(dm.A), ptr(dmean), ptr(dlinv),
+                  ptr(dnorm), ptr(ob.tensor), ob.code, ptr(ob.lengths), ptr(alpha), ptr(scale), ptr(loglik), stream_ptr())
+        return alpha, scale, loglik
     if p.kind == "gauss_full":
         E = dense_emissions(p, ob).to(real)
         _lib.call("khmm_forward_dense_" + dm.suffix, ob.B, ob.T, N, ptr(dm.pi), ptr(dm.A), ptr(E), ptr(ob.lengths),
@@ -297,6 +313,12 @@ def backward(p: ModelParams, ob: Obs, real, scale, alpha=None, want_beta=True, w
     N, dev = p.N, device()
     beta = t.empty((ob.B, ob.T, N), dtype=real, device=dev) if want_beta else None
     gamma = t.empty((ob.B, ob.T, N), dtype=real, device=dev) if want_gamma else None
+    if p.kind == "gauss_full" and p.mean.shape[1] <= GAUSS_FULL_DMAX:
+        D, dmean, dlinv, dnorm = _gauss_full_operands(p)
+        _lib.call("khmm_backward_gaussfull_" + dm.suffix, ob.B, ob.T, N, D, ptr(dm.AT), ptr(dmean), ptr(dlinv), ptr(dnorm),
+                  ptr(ob.tensor), ob.code, ptr(ob.lengths), ptr(scale), ptr(alpha), ptr(beta), ptr(gamma), gamma_kind,
+                  stream_ptr())
+        return beta, gamma
     if p.kind == "gauss_full":
         E = dense_emissions(p, ob).to(real)
         _lib.call("khmm_backward_dense_" + dm.suffix, ob.B, ob.T, N, ptr(dm.AT), ptr(E), ptr(ob.lengths), ptr(scale),
@@ -464,6 +486,9 @@ def fwdbwd_loglik_tc(p: ModelParams, ob: Obs, both=True, precision=TC_TF32):
         run(precision)
     except _lib.KhmmError as e:
         if precision == TC_BF16 and e.code == _lib.ERR_UNSUPPORTED:
+            import warnings
+            warnings.warn("fwdbwd_loglik_tc: bf16 operands are not available for this shape / device (%s); running with tf32 "
+                          "operands (more precise, about half the tensor rate)" % e, RuntimeWarning, stacklevel=2)
             run(TC_TF32)
         else:
             raise

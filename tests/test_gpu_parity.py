@@ -912,3 +912,39 @@ def test_tensor_core_loglik_small_batches(K, N, B, T, mode):
     tol = 2e-4 if mode == "bf16" else 5e-5
     np.testing.assert_allclose(ll.cpu().numpy(), ref, rtol=tol)
     np.testing.assert_allclose(llb.cpu().numpy(), ref, rtol=tol)
+
+
+# ----------------------------------------------- full-covariance Gaussian emissions fused into the recursions (round 2)
+@pytest.mark.parametrize("D,dtype,tol", [(2, "float64", 1e-10), (3, "float32", 3e-5),
+                                          (8, "float64", 1e-10), (9, "float64", 1e-10)])
+def test_full_covariance_emissions_fused_in_the_recursions(K, D, dtype, tol):
+    """GaussianDistribution with a covariance matrix (distribution.py:153) on a ragged batch: forward / backward with the
+    density evaluated inside the recursion kernels (D <= 8; D = 9 takes the dense emission matrix) against the oracle's
+    per-sequence forward / backward on SciPy-checked densities (abstract_hmm.py:250-285, 327-351)."""
+    N, B, T = 5, 23, 40
+    rng = np.random.default_rng(100 + D)
+    np.random.seed(D)
+    h = K.GaussianHMM(N, D, random_transitions=True)
+    means = rng.normal(scale=3.0, size=(N, D))
+    covs = np.empty((N, D, D))
+    for j in range(N):
+        Q = rng.normal(size=(D, D))
+        covs[j] = Q @ Q.T / D + 0.5 * np.eye(D)
+    h.emissionDistributions = [K.GaussianDistribution(D, mean=means[j], variance=covs[j]) for j in range(N)]
+    x = means[rng.integers(0, N, size=(B, T))] + rng.normal(size=(B, T, D))
+    lengths = rng.integers(1, T + 1, size=B)
+    lengths[0] = T
+    alpha, scale, ll = h.forward_batch(x, lengths=lengths, dtype=dtype)
+    beta = h.backward_batch(x, scale, lengths=lengths, dtype=dtype)
+    gam, ll2 = h.posterior_batch(x, lengths=lengths, dtype=dtype)
+    pi, A = h.initialProbabilities, h.transitionMatrix
+    for b in range(B):
+        L = int(lengths[b])
+        E = O.emissions_gaussian_full(means, covs, x[b, :L])
+        ra, rc = O.forward(pi, A, E)
+        rb = O.backward(A, E, rc)
+        np.testing.assert_allclose(alpha[b, :L], ra, rtol=tol, atol=1e-30)
+        np.testing.assert_allclose(scale[b, :L], rc, rtol=tol)
+        np.testing.assert_allclose(beta[b, :L], rb, rtol=tol * 10, atol=1e-30)
+        np.testing.assert_allclose(gam[b, :L], ra * rb, rtol=tol * 10, atol=1e-12)
+        assert np.isclose(ll[b], np.log(rc).sum(), rtol=max(tol, 1e-12)) and np.isclose(ll2[b], ll[b], rtol=1e-12)
