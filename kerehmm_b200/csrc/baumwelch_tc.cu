@@ -1671,6 +1671,19 @@ int khmm_estep_tc_discrete_ex_f32(int64_t B, int64_t T, int N, int M, const floa
                 return KHMM_ERR_CUDA;
             }
             size_t smem3 = 6 * (size_t)BW_HTILE + 2 * BW3_PREP * sizeof(Bwd3Prep) + sizeof(Bwd3Bars) + 1024;
+            {
+                // the kernel re-splits its register file with setmaxnreg (16 compute warps x 104, 4 helper warps x 64): the
+                // CTA's pool is what the launch allocates (registers per thread x 640), and a pool that is too small would
+                // make setmaxnreg.inc wait forever -- refuse to launch instead
+                cudaFuncAttributes fa;
+                KHMM_CUDA_CHECK(split ? cudaFuncGetAttributes(&fa, bw_backward_tc3_kernel<KHMM_TC_BF16X3>)
+                                      : cudaFuncGetAttributes(&fa, bw_backward_tc3_kernel<KHMM_TC_TF32>));
+                if (fa.numRegs * BW3_THREADS < 512 * 104 + 128 * 64) {
+                    set_error("estep_tc: bw_backward_tc3_kernel was compiled with %d registers per thread; its setmaxnreg split "
+                              "needs 96", fa.numRegs);
+                    return KHMM_ERR_UNSUPPORTED;
+                }
+            }
             if (split) {
                 KHMM_CUDA_CHECK(cudaFuncSetAttribute(bw_backward_tc3_kernel<KHMM_TC_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
                 bw_backward_tc3_kernel<KHMM_TC_BF16X3><<<grid, BW3_THREADS, smem3, st>>>(mapStashH, A, Bsm, ob, B, T, w.scale, out);
