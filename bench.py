@@ -346,7 +346,7 @@ def setup_c4(ctx, args):
         ach = bwd_bytes / (bwd_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of one backward launch (ncu --set full at B=18944, scaled to
         # this batch; profiles/): traffic ~ algorithmic bytes
-        traffic = (5.037033e9 + 0.004398e9) * (B * T) / (18944.0 * 512.0)
+        traffic = (5.030011e9 + 0.005003e9) * (B * T) / (18944.0 * 512.0)      # profiles/r2_ncu_c4_bw_backward_tc3_bf16x3_summary.csv
         other, other_ms = w.secondary_result
         return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "traffic": traffic, "kernel": w.dominant, "peak_source": pk["hbm_source"],
