@@ -72,6 +72,7 @@ def peaks():
     pipes = _json("profiles/r1_microbench_pipes.json") or {}
     out["ffma2_tflops"] = float(pipes.get("fp32_ffma2_packed_tflops", 67.7))
     out["dadd_gops"] = float(pipes.get("fp64_dadd_gops", 18396.0))
+    out["mufu_gops"] = float(pipes.get("mufu_ex2_gops", 4626.7))
     tf = _json("profiles/r2_microbench_tf32.json")
     if tf and tf.get("tf32_tflops"):
         out["tf32_tflops"] = float(tf["tf32_tflops"])
@@ -424,7 +425,7 @@ def setup_c2(ctx, args):
     w.step, w.e2e_step = step, e2e_step
     w.launches_per_step = 1
     w.h2d, w.d2h = B * T * 4, 2 * B * 8
-    w.dominant = "fwdbwd_small_kernel<8, gauss>"
+    w.dominant = "fwdbwd_mma8_kernel<gauss, f32>"
     w.l2_note = "two alternating 134 MB observation sets (268 MB > 126 MB L2)"
     w.dtype = "f32"
     w.sharding = "sequences sharded across ranks, no data-path collective"
@@ -440,8 +441,14 @@ def setup_c2(ctx, args):
                 "peak_source": "measured packed-FFMA2 rate (tools/microbench.cu, profiles/r1_microbench_pipes.json)",
                 "hbm": {"achieved_gbs": ach_gb, "peak_gbs": pk["hbm_gbs"], "frac": ach_gb / pk["hbm_gbs"],
                         "algorithmic_bytes_per_launch": algo_bytes},
-                "note": "binding roof = FP32 issue (SURVEY 8(d): max of the HBM floor and the FP32 floor): achieved counts "
-                        "only the 4 N^2 flop per (sequence, step) of the two matrix-vector products"}
+                "mufu": {"floor_ms": 16.0 * B * T / (pk["mufu_gops"] * 1e9) * 1e3,
+                         "frac": 16.0 * B * T / (pk["mufu_gops"] * 1e9) * 1e3 / ms_per_step},
+                "note": "roof = FP32 floor of SURVEY 8(d) (max of the HBM floor and the FP32 floor): achieved counts only "
+                        "the 4 N^2 flop per (sequence, step) of the two matrix-vector products.  Since round 2 those "
+                        "products run as warp-level mma.sync tiles (split tf32 operands); no pipe is saturated, the "
+                        "instruction classes serialise on the scheduler (profiles/r2_c2_mma8_ablation.txt); `mufu` is the "
+                        "floor set by the 16 ex2 per (sequence, step) at the measured MUFU rate; `traffic` is the ncu "
+                        "figure of the scalar-load instantiation"}
 
     w.roofline = roofline
     return w
@@ -607,7 +614,7 @@ def setup_c1(ctx, args):
 SETUP = {"c1": setup_c1, "c2": setup_c2, "c3": setup_c3, "c4": setup_c4, "c5": setup_c5}
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, ncu --set full at full size (profiles/)
-NCU_TRAFFIC = {"c2": 180.484352e6 + 4.261632e6, "c3": 0.309431808e9 + 17.133593e9, "c5": 43.3344e6}
+NCU_TRAFFIC = {"c2": 193.742336e6 + 4.065536e6, "c3": 0.309431808e9 + 17.133593e9, "c5": 43.3344e6}
 
 
 class Ctx:

@@ -201,8 +201,10 @@ int khmm_emissions_gauss_full_f64(int64_t B, int64_t T, int N, int D, const doub
 
 /* ---------------------------------------------------------------------------------------
  * Fused forward-backward log-likelihood (no alpha/beta in HBM) for small state spaces
- * (N <= KHMM_SMALL_N_MAX): one thread per sequence, A and the alpha/beta rows in registers,
- * emission evaluation fused.  loglik[B] = sum_t log c_t (forward); loglik_bwd[B] (may be
+ * (N <= KHMM_SMALL_N_MAX), emission evaluation fused, everything but the observations in
+ * registers: one thread per (sequence, direction) in packed FP32, or -- N = 5..8 -- one warp per
+ * 16 sequences with the matrix-vector products as mma.sync tiles on split tf32 operands (same
+ * fp32-class accuracy).  loglik[B] = sum_t log c_t (forward); loglik_bwd[B] (may be
  * NULL: forward only) = the same likelihood recovered from the backward recursion, which runs
  * concurrently with its own scaling s_t: log(sum_i pi_i b_i(o_0) beta_0(i)) = sum_t log s_t +
  * log(pi . w_0)  -- equal to loglik up to rounding.
@@ -350,7 +352,8 @@ int khmm_estep_tc_timing(int enable);
 int khmm_estep_tc_kernel_ms(int calls_back, float *forward_ms_host, float *backward_ms_host);
 int khmm_estep_tc_last_kernel_ms(float *forward_ms_host, float *backward_ms_host);
 
-/* Development switches: name = "KHMM_RC_MODE" | "KHMM_RC_BN" | "KHMM_VIT_SCREEN" | "KHMM_BW_BACKWARD" (DESIGN.md 4a), value -1
+/* Development switches: name = "KHMM_RC_MODE" | "KHMM_RC_BN" | "KHMM_VIT_SCREEN" | "KHMM_BW_BACKWARD" |
+ * "KHMM_SMALL_MMA" (DESIGN.md 4a), value -1
  * restores the library's default.  The environment variable of the same name sets the initial value and is read once per
  * process; no production call reads the environment. */
 int khmm_debug_switch(const char *name, int value);

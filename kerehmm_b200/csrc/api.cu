@@ -33,7 +33,8 @@ int sm_count() {
     return cached;
 }
 
-static const char *kSwitchNames[SW_COUNT] = {"KHMM_RC_MODE", "KHMM_RC_BN", "KHMM_VIT_SCREEN", "KHMM_BW_BACKWARD"};
+static const char *kSwitchNames[SW_COUNT] = {"KHMM_RC_MODE", "KHMM_RC_BN", "KHMM_VIT_SCREEN", "KHMM_BW_BACKWARD",
+                                             "KHMM_SMALL_MMA"};
 static int g_switch[SW_COUNT];
 static bool g_switch_init = false;
 

@@ -37,7 +37,7 @@ int sm_count();  // cached SM count of the current device (148 on B200)
 
 // Development switches (khmm_debug_switch; the environment variable of the same name gives the initial value, read
 // ONCE per process): which kernel variant a call takes.  None is needed in production.
-enum DevSwitch { SW_RC_MODE = 0, SW_RC_BN = 1, SW_VIT_SCREEN = 2, SW_BW_BACKWARD = 3, SW_COUNT = 4 };
+enum DevSwitch { SW_RC_MODE = 0, SW_RC_BN = 1, SW_VIT_SCREEN = 2, SW_BW_BACKWARD = 3, SW_SMALL_MMA = 4, SW_COUNT = 5 };
 int dev_switch(DevSwitch which);   // -1 = unset (the library's default applies)
 
 // ---------------------------------------------------------------- observation loads

@@ -12,6 +12,9 @@
 // (w_t = b_t . beta_t up to scaling).  Both are "row vector times matrix, times emission,
 // normalise" -- with A^T and reversed time for the backward pass -- so one code path serves both.
 //
+// (N = 5..8 takes fwdbwd_mma8_kernel further down, which runs the matrix-vector products on the tensor cores; the
+// thread-per-sequence kernel described here serves the other N and stays selectable as its cross-check.)
+//
 // Blackwell specifics: all FP32 work is issued as packed FFMA2/FMUL2/FADD2 (fma.rn.f32x2, two
 // states per instruction) -- the kernel is bound by FP32 issue, not by HBM; the
 // matrix-vector product keeps one accumulation chain per pair of OUTPUT states (broadcast input
@@ -62,20 +65,36 @@ struct SmallStep {
         }
     }
 
-    // w M: input states in ONE accumulation chain per output pair (the four / eight chains of a step are independent,
-    // which is all the instruction-level parallelism a warp needs with packed FFMA2 issuing every other cycle; the
-    // round-1 version split even and odd inputs into two chains and paid a packed add per output pair to merge them)
+    // w M: input states in ONE accumulation chain per output pair (the round-1 version split even and odd inputs into two
+    // chains and paid a packed add per output pair to merge them), written input-state-major so that the H chains
+    // advance together and consecutive instructions are independent (the compiler kept output-pair-major source order
+    // and interleaved only two chains: 0.355 against 0.340 ms at config-2 size)
     __device__ __forceinline__ void matvec(const float2 (&w)[H], float2 (&out)[H]) const {
+        if constexpr (MX_SMEM) {        // N = 9..16: eight chains at once would only add to the register pressure
 #pragma unroll
-        for (int k = 0; k < H; k++) {
-            float2 c = __fmul2_rn(make_float2(w[0].x, w[0].x), mat(0, k));
-            c = __ffma2_rn(make_float2(w[0].y, w[0].y), mat(1, k), c);
+            for (int k = 0; k < H; k++) {
+                float2 c = __fmul2_rn(make_float2(w[0].x, w[0].x), mat(0, k));
+                c = __ffma2_rn(make_float2(w[0].y, w[0].y), mat(1, k), c);
+#pragma unroll
+                for (int y2 = 1; y2 < H; y2++) {
+                    c = __ffma2_rn(make_float2(w[y2].x, w[y2].x), mat(2 * y2, k), c);
+                    c = __ffma2_rn(make_float2(w[y2].y, w[y2].y), mat(2 * y2 + 1, k), c);
+                }
+                out[k] = c;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < H; k++) out[k] = __fmul2_rn(make_float2(w[0].x, w[0].x), mat(0, k));
+#pragma unroll
+            for (int k = 0; k < H; k++) out[k] = __ffma2_rn(make_float2(w[0].y, w[0].y), mat(1, k), out[k]);
 #pragma unroll
             for (int y2 = 1; y2 < H; y2++) {
-                c = __ffma2_rn(make_float2(w[y2].x, w[y2].x), mat(2 * y2, k), c);
-                c = __ffma2_rn(make_float2(w[y2].y, w[y2].y), mat(2 * y2 + 1, k), c);
+#pragma unroll
+                for (int k = 0; k < H; k++) out[k] = __ffma2_rn(make_float2(w[y2].x, w[y2].x), mat(2 * y2, k), out[k]);
+#pragma unroll
+                for (int k = 0; k < H; k++)
+                    out[k] = __ffma2_rn(make_float2(w[y2].y, w[y2].y), mat(2 * y2 + 1, k), out[k]);
             }
-            out[k] = c;
         }
     }
 
@@ -277,6 +296,356 @@ fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// N in 5..8 (round 2): the matrix-vector products of 16 sequences as ONE warp-level tensor-core tile.
+//
+// The kernel above is bound by the FP32 pipe, and only 62 % of what it issues there is the matrix-vector product (the rest
+// is the emission density, the scaling and the row sum).  Here a warp owns 16 sequences of one direction and the product
+// (16 x 8) . (8 x 8) is one mma.sync.m16n8k8 (tf32 operands, fp32 accumulate), issued three times with split operands
+//     w M  ~  w_hi M_hi + w_hi M_lo + w_lo M_hi        (w_hi = the upper 19 bits of w, w_lo = w - w_hi exactly)
+// which keeps fp32-class accuracy (the dropped w_lo M_lo term is below 2^-21 of the product).  The fragment layouts make
+// the recursion shuffle-free: lane (g = lane / 4, c = lane % 4) receives D[g][2c], D[g][2c+1], D[g+8][2c], D[g+8][2c+1]
+// and has to supply A[g][c], A[g+8][c], A[g][c+4], A[g+8][c+4] -- so the K index is permuted (k = c -> state 2c,
+// k = c + 4 -> state 2c + 1, the rows of the matrix operand permuted to match) and a lane's outputs ARE its next inputs.
+// A lane therefore owns the state pair (2c, 2c+1) of sequences g and g + 8: two packed emission evaluations per step, two
+// packed multiplies, and a fourth mma against a matrix of ones that returns the row sums (only their exponent is used:
+// the scale factors stay exact powers of two, taken every other step as above).  What is left on the FP32 pipe is a
+// quarter of the kernel above per sequence; the step is bound by the eight MUFU.EX2 per sequence instead.
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t b0, uint32_t b1, const float (&c)[4]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+__device__ __forceinline__ uint32_t tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
+// one observation as the float the emission evaluation takes: the value (Gaussian) or the bits of the clamped symbol
+template <int DT>
+__device__ __forceinline__ float obs_elem(const void *obs, int64_t idx, int M) {
+    if (DT == KHMM_F32) return __ldg((const float *)obs + idx);
+    if (DT == KHMM_F64) return (float)__ldg((const double *)obs + idx);
+    int sym;
+    if (DT == KHMM_U8) sym = (int)__ldg((const uint8_t *)obs + idx);
+    else if (DT == KHMM_U16) sym = (int)__ldg((const uint16_t *)obs + idx);
+    else if (DT == KHMM_I32) sym = __ldg((const int32_t *)obs + idx);
+    else sym = (int)__ldg((const long long *)obs + idx);
+    return __int_as_float(min(max(sym, 0), M - 1));
+}
+
+// DIR (0 forward, 1 backward) and the observation type are compile-time: the observation loads of the unrolled path are
+// then plain loads at immediate offsets from one running pointer per sequence (the first version computed a 64-bit
+// address, a type dispatch and a length predicate per element: half of the instructions it issued).
+#ifndef KHMM_MMA8_BLK
+#define KHMM_MMA8_BLK 8
+#endif
+constexpr int kBlkM = KHMM_MMA8_BLK;  // steps per observation prefetch block of the warp-tile kernel
+
+// VEC: every sequence has the full length T, T is a multiple of 8 and the rows are 16-byte aligned (the host checks) --
+// the observations of a block are then two 16-byte loads per sequence, a quarter of the L1 data-pipe wavefronts of eight
+// 4-byte loads (one wavefront per 128-byte line and instruction; that pipe was 77 % busy and set the pace), the blocks
+// are aligned to multiples of 8 steps and there is no ragged tail.
+template <bool GAUSS, int DT, int DIR, bool VEC>
+__device__ __forceinline__ void mma8_body(int64_t B, int64_t T, int N, int M, const float *__restrict__ pi,
+                                          const float *__restrict__ A, const float *__restrict__ p0,
+                                          const float *__restrict__ p1, const void *__restrict__ obs,
+                                          const int32_t *__restrict__ lengths, double *__restrict__ out, int64_t tile) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const int j0 = 2 * c, j1 = 2 * c + 1;                   // the state pair of this lane
+
+    // matrix operand: B[k][n] with n = g the output state; k = c -> input state 2c, k = c + 4 -> input state 2c + 1
+    auto m_elem = [&](int y, int x) -> float {              // M[y][x], M = A forward, A^T backward, zero padded
+        if (y >= N || x >= N) return 0.f;
+        return DIR ? __ldg(A + x * N + y) : __ldg(A + y * N + x);
+    };
+    const float m0 = m_elem(j0, g), m1 = m_elem(j1, g);
+    const uint32_t bh0 = tf32_rna(m0), bh1 = tf32_rna(m1);
+    const uint32_t bl0 = tf32_rna(m0 - __uint_as_float(bh0)), bl1 = tf32_rna(m1 - __uint_as_float(bh1));
+    const uint32_t kOne = 0x3f800000u;
+    const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+
+    const float2 pv = make_float2(j0 < N ? __ldg(pi + j0) : 0.f, j1 < N ? __ldg(pi + j1) : 0.f);
+    const float2 live = make_float2(j0 < N ? 1.f : 0.f, j1 < N ? 1.f : 0.f);
+    float2 nm = make_float2(0.f, 0.f), kk = nm, lc = nm;
+    if (GAUSS) {
+        float mm[2], kq[2], l[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int j = 2 * c + q;
+            const float sd = j < N ? __ldg(p1 + j) : 1.f;
+            mm[q] = j < N ? -__ldg(p0 + j) : 0.f;
+            kq[q] = j < N ? -0.5f * 1.4426950408889634f / (sd * sd) : 0.f;
+            l[q] = j < N ? -log2f(sd * 2.5066282746310002f) : -INFINITY;   // padded states emit 0
+        }
+        nm = make_float2(mm[0], mm[1]);
+        kk = make_float2(kq[0], kq[1]);
+        lc = make_float2(l[0], l[1]);
+    }
+    auto emis = [&](float x) -> float2 {                    // the two emission values of this lane for one observation
+        if (GAUSS) {
+            const float2 d = __fadd2_rn(make_float2(x, x), nm);
+            const float2 a = __ffma2_rn(__fmul2_rn(d, d), kk, lc);
+            return make_float2(ex2_approx(a.x), ex2_approx(a.y));
+        }
+        const float *row = p0 + (int64_t)__float_as_int(x) * N;
+        return make_float2(j0 < N ? __ldg(row + j0) : 0.f, j1 < N ? __ldg(row + j1) : 0.f);
+    };
+
+    int len[2];
+    int64_t first[2];                                       // element index of recursion step 0
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int64_t b = tile * 16 + g + 8 * q;
+        len[q] = b < B ? (lengths ? lengths[b] : (int)T) : 0;
+        first[q] = (b < B ? b : tile * 16) * T + (DIR ? len[q] - 1 : 0);
+    }
+    int lmax = max(len[0], len[1]);
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    // observation of recursion step s (time runs backwards for the backward pass); 0 past the end of the sequence
+    auto load_x = [&](int q, int s) -> float {
+        return s < len[q] ? obs_elem<DT>(obs, first[q] + (DIR ? -s : s), M) : 0.f;
+    };
+
+    // the vector in fragment order: w[0] = w(g, 2c), w[1] = w(g+8, 2c), w[2] = w(g, 2c+1), w[3] = w(g+8, 2c+1)
+    // (scalars, not packed pairs: the accumulator pairs states of one sequence, the A fragment pairs sequences of one
+    // state, and packed results would have to be moved between register pairs at every step)
+    float w[4];
+    float sc[2];
+    int esum[2] = {0, 0};
+    uint32_t h[4], l[4];                                     // operands: upper 19 bits and the exact remainder
+    auto split = [&]() {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            h[i] = __float_as_uint(w[i]) & 0xffffe000u;
+            l[i] = __float_as_uint(w[i] - __uint_as_float(h[i]));
+        }
+    };
+    auto product = [&](float (&d)[4]) {                      // d = (w M) of both sequences, from h / l
+        mma_m16n8k8_tf32(d, h[0], h[1], h[2], h[3], bh0, bh1, zero4);
+        mma_m16n8k8_tf32(d, h[0], h[1], h[2], h[3], bl0, bl1, d);
+        mma_m16n8k8_tf32(d, l[0], l[1], l[2], l[3], bh0, bh1, d);
+    };
+    auto times = [&](const float (&d)[4], float2 b0, float2 b1, bool a0, bool a1) {   // w = d . b where live
+        if (a0) { w[0] = d[0] * b0.x; w[2] = d[1] * b0.y; }
+        if (a1) { w[1] = d[2] * b1.x; w[3] = d[3] * b1.y; }
+    };
+    auto rescale = [&](bool a0, bool a1) {                   // row sums of h -> pending power-of-two factors
+        float s[4];
+        mma_m16n8k8_tf32(s, h[0], h[1], h[2], h[3], kOne, kOne, zero4);
+        const int e0 = (int)((__float_as_uint(s[0]) >> 23) & 0xffu) - 127;
+        const int e1 = (int)((__float_as_uint(s[2]) >> 23) & 0xffu) - 127;
+        if (a0) { esum[0] += e0; sc[0] = __uint_as_float((uint32_t)(127 - e0) << 23); }
+        if (a1) { esum[1] += e1; sc[1] = __uint_as_float((uint32_t)(127 - e1) << 23); }
+    };
+
+    if constexpr (VEC) {
+        static_assert(DT == KHMM_F32 && kBlkM == 8, "vector path: float observations, 8-step blocks");
+        // block k = recursion steps 8k .. 8k+7 = elements 8k .. 8k+7 forward, T-8-8k .. T-1-8k (reversed) backward
+        const float *row[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int64_t b = tile * 16 + g + 8 * q;
+            row[q] = (const float *)obs + (b < B ? b : tile * 16) * T;
+        }
+        auto load_vec = [&](float (&x)[2][kBlkM], int s0) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const float4 *p = (const float4 *)(row[q] + (DIR ? (int)T - 8 - s0 : s0));
+                const float4 lo = __ldg(p), hi = __ldg(p + 1);
+                const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                for (int i = 0; i < kBlkM; i++) x[q][i] = DIR ? v[7 - i] : v[i];
+            }
+        };
+        float xs[2][kBlkM], xn[2][kBlkM];
+        load_vec(xs, 0);
+        load_vec(xn, 8);
+        {   // step 0: start vector (pi forward, ones backward) times the first emission; steps 1..7 rescale at every step
+            const float2 st = DIR ? live : pv;
+            const float d0[4] = {st.x, st.y, st.x, st.y};
+            times(d0, emis(xs[0][0]), emis(xs[1][0]), true, true);
+            sc[0] = sc[1] = 1.f;
+            split();
+            rescale(true, true);
+#pragma unroll
+            for (int i = 1; i < kBlkM; i++) {
+                float d[4];
+                const float2 b0 = __fmul2_rn(emis(xs[0][i]), make_float2(sc[0], sc[0]));
+                const float2 b1 = __fmul2_rn(emis(xs[1][i]), make_float2(sc[1], sc[1]));
+                product(d);
+                times(d, b0, b1, true, true);
+                split();
+                rescale(true, true);
+            }
+        }
+        for (int s0 = 8; s0 < (int)T; s0 += kBlkM) {
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+#pragma unroll
+                for (int i = 0; i < kBlkM; i++) xs[q][i] = xn[q][i];
+            if (s0 + kBlkM < (int)T) load_vec(xn, s0 + kBlkM);   // the block after this one, in flight meanwhile
+#pragma unroll
+            for (int i = 0; i < kBlkM; i += 2) {
+                float d[4];
+                // scaled step (takes the pending factors), then a plain step whose row sums give the next factors
+                const float2 b0 = __fmul2_rn(emis(xs[0][i]), make_float2(sc[0], sc[0]));
+                const float2 b1 = __fmul2_rn(emis(xs[1][i]), make_float2(sc[1], sc[1]));
+                product(d);
+                times(d, b0, b1, true, true);
+                split();
+                const float2 c0 = emis(xs[0][i + 1]), c1 = emis(xs[1][i + 1]);
+                product(d);
+                times(d, c0, c1, true, true);
+                split();
+                rescale(true, true);
+            }
+        }
+    } else {
+    {   // step 0: start vector (pi forward, ones backward) times the first emission
+        const float2 st = DIR ? live : pv;
+        const float d0[4] = {st.x, st.y, st.x, st.y};
+        times(d0, emis(load_x(0, 0)), emis(load_x(1, 0)), true, true);
+        sc[0] = sc[1] = 1.f;
+        split();
+        rescale(true, true);
+    }
+    // Measured and dropped (config-2 size, 0.316 ms as below): alternating two observation buffers over a loop unrolled
+    // twice to save the register copies between blocks (0.330 ms: the loop no longer sits well in the instruction
+    // cache); one lane of a quad loading each observation and a quad shuffle handing it out, for a quarter of the L1 tag
+    // look-ups (0.330 ms: the shuffle latency lands on the step); evaluating the emission values one step ahead by hand
+    // (0.32 - 0.36 ms); 16-step or 4-step blocks (0.46 / 0.345 ms).
+    float xs[2][kBlkM], xn[2][kBlkM];
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int i = 0; i < kBlkM; i++) xs[q][i] = load_x(q, 1 + i);
+    for (int s0 = 1; s0 < lmax; s0 += kBlkM) {
+        // the block after this one, in flight while this one is computed
+        if (__all_sync(0xffffffffu, s0 + 2 * kBlkM <= len[0] && s0 + 2 * kBlkM <= len[1])) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int64_t at = first[q] + (DIR ? -(s0 + kBlkM) : (s0 + kBlkM));
+#pragma unroll
+                for (int i = 0; i < kBlkM; i++) xn[q][i] = obs_elem<DT>(obs, at + (DIR ? -i : i), M);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+#pragma unroll
+                for (int i = 0; i < kBlkM; i++) xn[q][i] = load_x(q, s0 + kBlkM + i);
+        }
+        if (__all_sync(0xffffffffu, s0 + kBlkM <= len[0] && s0 + kBlkM <= len[1])) {
+#pragma unroll
+            for (int i = 0; i < kBlkM; i += 2) {
+                float d[4];
+                // scaled step (takes the pending factors), then a plain step whose row sums give the next factors
+                const float2 b0 = __fmul2_rn(emis(xs[0][i]), make_float2(sc[0], sc[0]));
+                const float2 b1 = __fmul2_rn(emis(xs[1][i]), make_float2(sc[1], sc[1]));
+                product(d);
+                times(d, b0, b1, true, true);
+                split();
+                const float2 c0 = emis(xs[0][i + 1]), c1 = emis(xs[1][i + 1]);
+                product(d);
+                times(d, c0, c1, true, true);
+                split();
+                rescale(true, true);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kBlkM; i++) {                 // the ragged tail rescales at every step
+                const bool a0 = s0 + i < len[0], a1 = s0 + i < len[1];
+                float d[4];
+                const float2 b0 = __fmul2_rn(emis(xs[0][i]), make_float2(sc[0], sc[0]));
+                const float2 b1 = __fmul2_rn(emis(xs[1][i]), make_float2(sc[1], sc[1]));
+                product(d);
+                times(d, b0, b1, a0, a1);
+                split();
+                rescale(a0, a1);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int i = 0; i < kBlkM; i++) xs[q][i] = xn[q][i];
+    }
+    }   // !VEC
+    // closing dot product: forward sum(w), backward pi . w_0 -- of the vector as it stands (the pending factor was
+    // counted in esum but not applied yet, so it is applied here)
+    const float2 wf = DIR ? pv : live;
+    float f[2] = {w[0] * wf.x + w[2] * wf.y, w[1] * wf.x + w[3] * wf.y};
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        f[q] += __shfl_xor_sync(0xffffffffu, f[q], 1);
+        f[q] += __shfl_xor_sync(0xffffffffu, f[q], 2);
+        const int64_t b = tile * 16 + g + 8 * q;
+        if (c != 0 || b >= B) continue;
+        const float fin = f[q] * sc[q];
+        double ll = (double)esum[q] * 0.6931471805599453 + log((double)fin);
+        if (!(fin > 0.f) || !(fin < INFINITY)) ll = __longlong_as_double(0x7ff8000000000000ll);  // underflow -> NaN (Q15)
+        out[b] = ll;
+    }
+}
+
+template <bool GAUSS, int DT, bool VEC>
+__global__ void __launch_bounds__(64)
+fwdbwd_mma8_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict__ pi, const float *__restrict__ A,
+                   const float *__restrict__ p0, const float *__restrict__ p1, const void *__restrict__ obs,
+                   const int32_t *__restrict__ lengths, double *__restrict__ loglik, double *__restrict__ loglik_bwd) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool two = loglik_bwd != nullptr;
+    const int64_t tile = two ? (warp >> 1) : warp;          // 16 sequences; even warps forward, odd warps backward
+    if (tile * 16 >= B) return;
+    if (two && (warp & 1))
+        mma8_body<GAUSS, DT, 1, VEC>(B, T, N, M, pi, A, p0, p1, obs, lengths, loglik_bwd, tile);
+    else
+        mma8_body<GAUSS, DT, 0, VEC>(B, T, N, M, pi, A, p0, p1, obs, lengths, loglik, tile);
+}
+
+template <bool GAUSS, int DT>
+static int launch_mma8_typed(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *p0,
+                             const float *p1, const void *obs, const int32_t *lengths, double *loglik,
+                             double *loglik_bwd, cudaStream_t st) {
+    const int64_t tiles = (B + 15) / 16;
+    const int64_t warps = tiles * (loglik_bwd ? 2 : 1);
+    // whole sequences, blocks of 8 steps, 16-byte aligned rows -> the vector-load instantiation
+    const bool vec = GAUSS && DT == KHMM_F32 && !lengths && T >= 16 && T % 8 == 0 && ((uintptr_t)obs & 15) == 0 &&
+                     dev_switch(SW_SMALL_MMA) != 2;
+    if constexpr (GAUSS && DT == KHMM_F32) {
+        if (vec) {
+            fwdbwd_mma8_kernel<GAUSS, DT, true><<<(unsigned)((warps + 1) / 2), 64, 0, st>>>(
+                B, T, N, M, pi, A, p0, p1, obs, lengths, loglik, loglik_bwd);
+            KHMM_LAUNCH_CHECK("fwdbwd_mma8_kernel");
+            return KHMM_OK;
+        }
+    }
+    fwdbwd_mma8_kernel<GAUSS, DT, false><<<(unsigned)((warps + 1) / 2), 64, 0, st>>>(B, T, N, M, pi, A, p0, p1, obs, lengths,
+                                                                                   loglik, loglik_bwd);
+    KHMM_LAUNCH_CHECK("fwdbwd_mma8_kernel");
+    return KHMM_OK;
+}
+
+template <bool GAUSS>
+static int launch_mma8(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *p0,
+                       const float *p1, const void *obs, int obs_dtype, const int32_t *lengths, double *loglik,
+                       double *loglik_bwd, cudaStream_t st) {
+#define KHMM_MMA8(DT) launch_mma8_typed<GAUSS, DT>(B, T, N, M, pi, A, p0, p1, obs, lengths, loglik, loglik_bwd, st)
+    if constexpr (GAUSS) {
+        return obs_dtype == KHMM_F32 ? KHMM_MMA8(KHMM_F32) : KHMM_MMA8(KHMM_F64);
+    } else {
+        switch (obs_dtype) {
+            case KHMM_U8: return KHMM_MMA8(KHMM_U8);
+            case KHMM_U16: return KHMM_MMA8(KHMM_U16);
+            case KHMM_I32: return KHMM_MMA8(KHMM_I32);
+            default: return KHMM_MMA8(KHMM_I64);
+        }
+    }
+#undef KHMM_MMA8
+}
+
 template <int NP, bool GAUSS, bool MX_SMEM>
 static int launch_small(int64_t B, int64_t T, int N, int M, const float *pi, const float *A, const float *p0,
                         const float *p1, const void *obs, int obs_dtype, const int32_t *lengths, double *loglik,
@@ -313,6 +682,8 @@ static int dispatch_small(int64_t B, int64_t T, int N, int M, const float *pi, c
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 2) return launch_small<2, GAUSS, false>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
     if (N <= 4) return launch_small<4, GAUSS, false>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
+    if (N > 4 && N <= 8 && dev_switch(SW_SMALL_MMA) != 0)
+        return launch_mma8<GAUSS>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
     if (N <= 8) return launch_small<8, GAUSS, false>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
     return launch_small<16, GAUSS, true>(B, T, N, M, pi, A, p0, p1, obs, obs_dtype, lengths, loglik, loglik_bwd, st);
 }

@@ -361,6 +361,57 @@ def test_fused_loglik_small_discrete(K):
     np.testing.assert_allclose(llb, ref, rtol=F32_RTOL)
 
 
+@pytest.mark.parametrize("N", [5, 6, 7, 8])
+def test_fused_loglik_warp_tile_kernel(K, N):
+    """N in 5..8 takes the kernel that runs the matrix-vector products of 16 sequences as one warp-level tensor-core tile
+    (split tf32 operands): float64 oracle within the fp32 bound, Gaussian and discrete, ragged batches whose size is not
+    a multiple of the tile, lengths from 1 up; and agreement with the thread-per-sequence kernel it replaces."""
+    from kerehmm_b200 import _lib
+    B, T, M = 117, 203, 11
+    np.random.seed(300 + N)
+    pi, A, mean, sd = O.random_gaussian_model(N)
+    sd = sd * np.random.uniform(0.5, 2.0, size=N)
+    hg = gaussian_model(K, pi, A, mean, sd)
+    hd, (pid, Ad, Bm) = random_discrete(K, N, M, seed=310 + N)
+    rng = np.random.default_rng(320 + N)
+    x = (mean[rng.integers(0, N, size=(B, T))] + rng.standard_normal((B, T))).astype(np.float32)
+    sym = rng.integers(0, M, size=(B, T)).astype(np.uint8)
+    lengths = rng.integers(1, T + 1, size=B)
+    lengths[:20] = T                   # whole tiles on the unrolled path
+    lengths[40] = 1
+    ref_g = np.array([np.log(O.forward(pi, A, O.emissions_gaussian_1d(mean, sd, x[b, :lengths[b]].astype(np.float64)))[1]).sum()
+                      for b in range(B)])
+    ref_d = np.array([np.log(O.forward(pid, Ad, O.emissions_discrete(Bm, sym[b, :lengths[b]]))[1]).sum() for b in range(B)])
+    got = {}
+    try:
+        for sw in (1, 0):
+            _lib.call("khmm_debug_switch", b"KHMM_SMALL_MMA", sw)
+            got[sw] = (hg.log_likelihood_batch(x, lengths=lengths), hd.log_likelihood_batch(sym, lengths=lengths))
+    finally:
+        _lib.call("khmm_debug_switch", b"KHMM_SMALL_MMA", -1)
+    for sw in (1, 0):
+        (ll, llb), (dl, dlb) = got[sw]
+        for r in (ll, llb):
+            np.testing.assert_allclose(r, ref_g, rtol=F32_RTOL, atol=1e-4)
+        for r in (dl, dlb):
+            np.testing.assert_allclose(r, ref_d, rtol=F32_RTOL, atol=1e-4)
+    np.testing.assert_allclose(got[1][0][0], got[0][0][0], rtol=2e-6, atol=2e-5)
+    np.testing.assert_allclose(got[1][1][0], got[0][1][0], rtol=2e-6, atol=2e-5)
+    # whole sequences of a multiple of 8 steps take the vector-load instantiation (switch value 2: scalar loads)
+    xw = np.ascontiguousarray(x[:, :200])
+    ref_w = np.array([np.log(O.forward(pi, A, O.emissions_gaussian_1d(mean, sd, xw[b].astype(np.float64)))[1]).sum()
+                      for b in range(B)])
+    try:
+        vec = hg.log_likelihood_batch(xw)
+        _lib.call("khmm_debug_switch", b"KHMM_SMALL_MMA", 2)
+        scalar = hg.log_likelihood_batch(xw)
+    finally:
+        _lib.call("khmm_debug_switch", b"KHMM_SMALL_MMA", -1)
+    for r in vec + scalar:
+        np.testing.assert_allclose(r, ref_w, rtol=F32_RTOL, atol=1e-4)
+    np.testing.assert_allclose(vec[0], scalar[0], rtol=2e-6, atol=2e-5)
+
+
 @pytest.mark.parametrize("N,B,T", [(128, 200, 40), (256, 129, 25), (1024, 64, 12)])
 def test_tensor_core_loglik_gaussian(K, N, B, T):
     """tcgen05 (tf32) recursion: forward and backward log-likelihoods against the float64 oracle.
