@@ -55,7 +55,7 @@ class AbstractHMM(object):
         """Table size the symbols index (discrete models), else None."""
         return None
 
-    def _prep(self, observations, lengths=None, single=False):
+    def _prep(self, observations, lengths=None, single=False, overlap=False):
         obs = observations
         if single:
             import torch
@@ -64,7 +64,7 @@ class AbstractHMM(object):
             else:
                 obs = np.asarray(obs)[None]
         return engine.prepare_obs(obs, symbols=self._symbols(), lengths=lengths, feature_dims=self._feature_dims(),
-                                  alphabet=self._alphabet())
+                                  alphabet=self._alphabet(), overlap=overlap)
 
     # ---------------------------------------------------------------- state alignment
     def compute_initprob_mapping_score(self, to_hmm, mapping):

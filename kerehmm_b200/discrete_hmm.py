@@ -127,8 +127,10 @@ class DiscreteHMM(AbstractHMM):
         once, after the last iteration, the way do_pass installs them (discrete_hmm.py:168-173).  If an iteration
         hits one of the reference's exceptional cases (ZeroDivisionError / ValueError of smooth_probabilities, a
         failed sanity_check) the parameters of the last good iteration are installed and that exception is raised."""
-        ob = self._prep(observations, lengths)
+        # parameter uploads first: behind the batch they would wait for the whole of it on the copy engine, and the
+        # first E-step is meant to start while the batch is still arriving (overlapped upload, engine.prepare_obs)
         trainer = engine.DiscreteTrainer(self._params(), self._real(dtype), max_iterations=iterations)
+        ob = self._prep(observations, lengths, overlap=True)
         for it in range(iterations):
             trainer.step(ob, chunk=chunk, tensor_cores=tensor_cores, group=group)
             if tol is not None and it > 0:

@@ -109,6 +109,32 @@ class Obs:
     on_host: bool       # the caller passed host memory -> results go back to the host
     lengths: object = None
     h2d_bytes: int = 0
+    # overlapped upload (prepare_obs(..., overlap=True)): row blocks still in flight on a side stream --
+    # [(first row, end row, event, page-locked (min, max) of the block's symbols or None)] -- and the alphabet they are
+    # checked against
+    ready: object = None
+    alphabet: int = None
+
+    def wait_block(self, k):
+        """Make the current stream wait for row block k of an overlapped upload and run its deferred symbol check
+        (raises the reference's IndexError).  -> (first row, end row)."""
+        t = torch()
+        b0, b1, ev, cell = self.ready[k]
+        t.cuda.current_stream().wait_event(ev)
+        if cell is not None:
+            ev.synchronize()                        # the copy, the range kernel and its read-back of THIS block only
+            lo, hi = (int(v) for v in cell.numpy())
+            if lo <= hi and (hi >= self.alphabet or lo < 0):
+                raise IndexError("index %d is out of bounds for axis 0 with size %d" % (hi if hi >= self.alphabet else lo,
+                                                                                       self.alphabet))
+        return b0, b1
+
+    def wait_all(self):
+        """Consumers that do not work block by block: wait for the whole upload."""
+        if self.ready is not None:
+            for k in range(len(self.ready)):
+                self.wait_block(k)
+            self.ready = None
 
 
 def _as_tensor(x):
@@ -151,11 +177,58 @@ def check_symbols(x, code: int, B: int, T: int, lengths, alphabet: int):
     return x
 
 
+OVERLAP_MIN_BYTES = 32 << 20      # below this an overlapped upload is not worth its extra launches
+_side_streams = {}                # device index -> the upload stream of the overlapped path
+
+
+def _upload_overlapped(x, code: int, alphabet):
+    """Page-locked host batch of unsigned symbols -> Obs whose row blocks arrive on a side stream while the consumer
+    already works on the first ones.  Blocks: one tile of 128 sequences per SM, two per SM, the rest -- so that a
+    block-wise E-step runs the same number of tile rounds as one call over the whole batch."""
+    t = torch()
+    dev = device()
+    B, T = int(x.shape[0]), int(x.shape[1])
+    per_round = 128 * t.cuda.get_device_properties(dev).multi_processor_count
+    bounds = [0, per_round, 3 * per_round, B]
+    main = t.cuda.current_stream()
+    # ONE side stream per device, kept: a new stream per call has an empty allocator pool, and the cudaMalloc that
+    # fills it (1 - 7 ms, measured) would sit in front of the first kernel launch.  High priority: its small range
+    # kernels go in front of queued E-step CTAs.
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = t.cuda.Stream(device=dev, priority=-1)
+    xd = t.empty((B, T), dtype=x.dtype, device=dev)
+    check = alphabet is not None and not (code in _UNSIGNED_LIMIT and alphabet >= _UNSIGNED_LIMIT[code])
+    mm = t.empty((3, 2), dtype=t.int64, device=dev) if check else None          # allocated from the main stream's pool
+    cells = t.empty((3, 2), dtype=t.int64, pin_memory=True) if check else None
+    side.wait_stream(main)
+    ready = []
+    with t.cuda.stream(side):
+        for k in range(3):
+            b0, b1 = bounds[k], bounds[k + 1]
+            xd[b0:b1].copy_(x[b0:b1], non_blocking=True)
+            cell = None
+            if check:
+                _lib.call("khmm_symbol_range", b1 - b0, T, ptr(xd[b0:b1]), code, None, ptr(mm[k]), side.cuda_stream)
+                cell = cells[k]
+                cell.copy_(mm[k], non_blocking=True)   # read back on the side stream, before the block's event
+            ev = t.cuda.Event()
+            ev.record(side)
+            ready.append((b0, b1, ev, cell))
+    xd.record_stream(side)
+    if check:
+        mm.record_stream(side)
+    return Obs(tensor=xd, code=code, B=B, T=T, on_host=True, lengths=None, h2d_bytes=x.numel() * x.element_size(),
+               ready=ready, alphabet=None if alphabet is None else int(alphabet))
+
+
 def prepare_obs(obs, symbols: bool, lengths=None, feature_dims: int = 0, u16_bits: bool = False,
-                alphabet: int = None) -> Obs:
+                alphabet: int = None, overlap: bool = False) -> Obs:
     """Move a batch of observations to the device.  symbols=True: integer symbols (B, T);
     else real observations (B, T) or (B, T, D).  `alphabet` (discrete models): the table size M the live symbols are
-    checked against, with the reference's IndexError / negative-index behaviour."""
+    checked against, with the reference's IndexError / negative-index behaviour.  `overlap`: the caller consumes the
+    batch block by block (`Obs.ready`, the training loop): a large page-locked batch of unsigned symbols is then copied
+    on a side stream while the first blocks are already being worked on, its symbol check deferred to each block."""
     t = require_cuda()
     was_u16 = (not isinstance(obs, t.Tensor)) and np.asarray(obs).dtype == np.uint16
     x = _as_tensor(obs)
@@ -183,6 +256,10 @@ def prepare_obs(obs, symbols: bool, lengths=None, feature_dims: int = 0, u16_bit
             x = x.to(t.float32)
         code = _lib.F32 if x.dtype == t.float32 else _lib.F64
     h2d = 0
+    if (overlap and on_host and symbols and lengths is None and code in _UNSIGNED_LIMIT and x.dim() == 2 and x.is_contiguous()
+            and x.numel() * x.element_size() >= OVERLAP_MIN_BYTES and x.is_pinned() and int(x.shape[1]) >= 1
+            and int(x.shape[0]) > 4 * 128 * t.cuda.get_device_properties(device()).multi_processor_count):
+        return _upload_overlapped(x, code, alphabet)
     if on_host:
         h2d = x.numel() * x.element_size()
         x = x.to(device(), non_blocking=True)
@@ -691,12 +768,24 @@ def estep_discrete_tc(p: ModelParams, ob: Obs, counts: "Counts" = None, chunk=No
     if stash_out:
         W = t.zeros(((nb0 + 127) // 128, ob.T, 128, N), dtype=t.float32, device=dev)   # tile-major stash
         sc = t.zeros(((nb0 + 127) // 128, ob.T, 128), dtype=t.float32, device=dev)           # tile-major c
-    for b0 in range(0, ob.B, chunk):
-        nb = min(chunk, ob.B - b0)
-        obs_c = ob.tensor[b0:b0 + nb]
-        len_c = ob.lengths[b0:b0 + nb] if ob.lengths is not None else None
-        _lib.call("khmm_estep_tc_discrete_ex_f32", nb, ob.T, N, M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.Bsm),
-                  ptr(obs_c), ob.code, ptr(len_c), wsp, nbytes, ptr(counts.buf), ptr(W), ptr(sc), int(precision), stream_ptr())
+    # an overlapped upload is consumed block by block (each block waits for its own copy only); afterwards -- and for
+    # every other batch -- the blocks are the chunks the scratch buffer allows
+    blocks = [(0, ob.B)]
+    if ob.ready is not None:
+        if stash_out:
+            ob.wait_all()
+        else:
+            blocks = [None] * len(ob.ready)
+    for k, blk in enumerate(blocks):
+        lo, hi = ob.wait_block(k) if blk is None else blk
+        for b0 in range(lo, hi, chunk):
+            nb = min(chunk, hi - b0)
+            obs_c = ob.tensor[b0:b0 + nb]
+            len_c = ob.lengths[b0:b0 + nb] if ob.lengths is not None else None
+            _lib.call("khmm_estep_tc_discrete_ex_f32", nb, ob.T, N, M, ptr(dm.pi), ptr(dm.A), ptr(dm.AT), ptr(dm.Bsm),
+                      ptr(obs_c), ob.code, ptr(len_c), wsp, nbytes, ptr(counts.buf), ptr(W), ptr(sc), int(precision),
+                      stream_ptr())
+    ob.ready = None
     if stash_out:
         W = W.permute(0, 2, 1, 3).reshape(-1, ob.T, N)[:nb0]     # -> [b][t][:]
         sc = sc.permute(0, 2, 1).reshape(-1, ob.T)[:nb0]
@@ -722,6 +811,7 @@ def estep_discrete(p: ModelParams, ob: Obs, real, counts: Counts = None, chunk=N
     if estep_uses_tc(p, ob, real, tensor_cores):
         return estep_discrete_tc(p, ob, counts=counts, chunk=chunk, operands=operands,
                                  precision=estep_precision(tensor_cores)[1])
+    ob.wait_all()
     dm = operands if operands is not None else DeviceModel(p, real)
     N, M, dev = p.N, p.M, device()
     counts = counts or Counts(N, M)

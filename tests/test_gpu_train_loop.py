@@ -253,3 +253,39 @@ def test_config4_reestimated_parameters_against_the_oracle(K):
     st5 = O.batch_stats_discrete(pi, A, Bm, obs[:512])
     _, rA5, _ = O.mstep_discrete(st5)
     assert rel(h2.transitionMatrix, rA5) < rel(h3.transitionMatrix, rA5) and rel(h2.transitionMatrix, rA5) <= 2e-5
+
+
+def test_overlapped_upload_of_a_pinned_batch(K):
+    """`train_batch` on a large page-locked batch of unsigned symbols copies it on a side stream in three row blocks and
+    runs the E-step block by block (each block waits for its own copy only; the symbol check is deferred to each
+    block): same parameters as the device-resident batch, and an out-of-range symbol in the LAST block still raises
+    the reference's IndexError and leaves the model untouched."""
+    import torch
+    from kerehmm_b200 import engine
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    N, M, T = 128, 300, 224
+    B = 4 * 128 * sms + 3000
+    rng = np.random.default_rng(171)
+    host = torch.from_numpy(rng.integers(0, M, size=(B, T)).astype(np.uint16).view(np.int16)).pin_memory()
+    assert host.numel() * 2 >= engine.OVERLAP_MIN_BYTES
+    ob = engine.prepare_obs(host.numpy().view(np.uint16), symbols=True, alphabet=M, overlap=True)
+    assert ob.ready is not None and [b1 - b0 for b0, b1, _, _ in ob.ready] == [128 * sms, 256 * sms, B - 384 * sms]
+    ob.wait_all()
+    assert torch.equal(ob.tensor.cpu(), host)
+    h1, _ = random_discrete(K, N, M, seed=172)
+    h2, _ = random_discrete(K, N, M, seed=172)
+    hist1 = h1.train_batch(host.numpy().view(np.uint16), iterations=2)          # overlapped upload
+    hist2 = h2.train_batch(host.numpy().view(np.uint16).copy(), iterations=2)   # pageable copy: plain upload
+    np.testing.assert_allclose(hist1, hist2, rtol=1e-9)
+    np.testing.assert_allclose(h1.initialProbabilities, h2.initialProbabilities, rtol=2e-5, atol=1e-12)
+    np.testing.assert_allclose(h1.transitionMatrix, h2.transitionMatrix, rtol=2e-5, atol=1e-12)
+    np.testing.assert_allclose(h1.emission_matrix(), h2.emission_matrix(), rtol=2e-5, atol=1e-12)
+    bad = host.clone().pin_memory()
+    bad[B - 7, 11] = M + 5
+    h3, _ = random_discrete(K, N, M, seed=172)
+    before = (h3.initialProbabilities.copy(), h3.transitionMatrix.copy(), h3.emission_matrix().copy())
+    with pytest.raises(IndexError, match="index %d is out of bounds for axis 0 with size %d" % (M + 5, M)):
+        h3.train_batch(bad.numpy().view(np.uint16), iterations=1)
+    torch.cuda.synchronize()
+    assert np.array_equal(h3.initialProbabilities, before[0]) and np.array_equal(h3.transitionMatrix, before[1])
+    assert np.array_equal(h3.emission_matrix(), before[2])
