@@ -55,7 +55,7 @@ class AbstractHMM(object):
         """Table size the symbols index (discrete models), else None."""
         return None
 
-    def _prep(self, observations, lengths=None, single=False, overlap=False):
+    def _prep(self, observations, lengths=None, single=False, overlap=None):
         obs = observations
         if single:
             import torch
@@ -441,7 +441,9 @@ class AbstractHMM(object):
         observations with log b_j(x) = (-0.5 z) z - log(sd_j) - log sqrt(2 pi) (the reference's own viterbi_path
         fails on float observations); bit-exact against oracle.viterbi_gaussian_1d."""
         t = engine.require_cuda()
-        ob = self._prep(observations, lengths)
+        # a large page-locked batch is decoded block by block while it is still arriving, and its paths travel back
+        # while the next block is decoded (engine.decoding_blocks)
+        ob = self._prep(observations, lengths, overlap=engine.decoding_blocks)
         if path_dtype is not None and not isinstance(path_dtype, t.dtype):
             path_dtype = {"uint8": t.uint8, "int16": t.int16, "int32": t.int32, "int64": t.int64}[
                 np.dtype(path_dtype).name]

@@ -130,7 +130,7 @@ class DiscreteHMM(AbstractHMM):
         # parameter uploads first: behind the batch they would wait for the whole of it on the copy engine, and the
         # first E-step is meant to start while the batch is still arriving (overlapped upload, engine.prepare_obs)
         trainer = engine.DiscreteTrainer(self._params(), self._real(dtype), max_iterations=iterations)
-        ob = self._prep(observations, lengths, overlap=True)
+        ob = self._prep(observations, lengths, overlap=engine.training_blocks)
         for it in range(iterations):
             trainer.step(ob, chunk=chunk, tensor_cores=tensor_cores, group=group)
             if tol is not None and it > 0:

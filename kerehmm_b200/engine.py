@@ -114,11 +114,16 @@ class Obs:
     # checked against
     ready: object = None
     alphabet: int = None
+    starter: object = None      # queues the copies; called by the first wait_block, i.e. AFTER the consumer's own (small)
+                                # parameter uploads -- behind the batch they would wait for all of it on the copy engine
 
     def wait_block(self, k):
         """Make the current stream wait for row block k of an overlapped upload and run its deferred symbol check
         (raises the reference's IndexError).  -> (first row, end row)."""
         t = torch()
+        if self.starter is not None:
+            self.starter(self)
+            self.starter = None
         b0, b1, ev, cell = self.ready[k]
         t.cuda.current_stream().wait_event(ev)
         if cell is not None:
@@ -181,16 +186,28 @@ OVERLAP_MIN_BYTES = 32 << 20      # below this an overlapped upload is not worth
 _side_streams = {}                # device index -> the upload stream of the overlapped path
 
 
-def _upload_overlapped(x, code: int, alphabet):
-    """Page-locked host batch of unsigned symbols -> Obs whose row blocks arrive on a side stream while the consumer
-    already works on the first ones.  Blocks: one tile of 128 sequences per SM, two per SM, the rest -- so that a
-    block-wise E-step runs the same number of tile rounds as one call over the whole batch."""
+def training_blocks(B: int):
+    """Row blocks of an overlapped upload for the tensor-core E-step: one tile of 128 sequences per SM, two per SM, the
+    rest -- so that the block-wise E-step runs the same number of tile rounds as one call over the whole batch."""
+    r = 128 * torch().cuda.get_device_properties(device()).multi_processor_count
+    return [r, 3 * r, B] if B > 4 * r else None
+
+
+def decoding_blocks(B: int):
+    """Row blocks for Viterbi (a warp per sequence, eight warps per CTA): a small first block so that decoding starts
+    early, and a small last one so that only its paths are still to be copied back when the kernels end."""
+    r = 2 * 8 * torch().cuda.get_device_properties(device()).multi_processor_count
+    return [r, B - r, B] if B > 8 * r else None
+
+
+def _upload_overlapped(x, code: int, alphabet, ends):
+    """Page-locked host batch of unsigned symbols -> Obs whose row blocks (ending at `ends`) arrive on a side stream while
+    the consumer already works on the first ones."""
     t = torch()
     dev = device()
     B, T = int(x.shape[0]), int(x.shape[1])
-    per_round = 128 * t.cuda.get_device_properties(dev).multi_processor_count
-    bounds = [0, per_round, 3 * per_round, B]
-    main = t.cuda.current_stream()
+    bounds = [0] + list(ends)
+    nblk = len(ends)
     # ONE side stream per device, kept: a new stream per call has an empty allocator pool, and the cudaMalloc that
     # fills it (1 - 7 ms, measured) would sit in front of the first kernel launch.  High priority: its small range
     # kernels go in front of queued E-step CTAs.
@@ -199,36 +216,44 @@ def _upload_overlapped(x, code: int, alphabet):
         side = _side_streams[dev.index] = t.cuda.Stream(device=dev, priority=-1)
     xd = t.empty((B, T), dtype=x.dtype, device=dev)
     check = alphabet is not None and not (code in _UNSIGNED_LIMIT and alphabet >= _UNSIGNED_LIMIT[code])
-    mm = t.empty((3, 2), dtype=t.int64, device=dev) if check else None          # allocated from the main stream's pool
-    cells = t.empty((3, 2), dtype=t.int64, pin_memory=True) if check else None
-    side.wait_stream(main)
-    ready = []
-    with t.cuda.stream(side):
-        for k in range(3):
-            b0, b1 = bounds[k], bounds[k + 1]
-            xd[b0:b1].copy_(x[b0:b1], non_blocking=True)
-            cell = None
-            if check:
-                _lib.call("khmm_symbol_range", b1 - b0, T, ptr(xd[b0:b1]), code, None, ptr(mm[k]), side.cuda_stream)
-                cell = cells[k]
-                cell.copy_(mm[k], non_blocking=True)   # read back on the side stream, before the block's event
-            ev = t.cuda.Event()
-            ev.record(side)
-            ready.append((b0, b1, ev, cell))
-    xd.record_stream(side)
-    if check:
-        mm.record_stream(side)
-    return Obs(tensor=xd, code=code, B=B, T=T, on_host=True, lengths=None, h2d_bytes=x.numel() * x.element_size(),
-               ready=ready, alphabet=None if alphabet is None else int(alphabet))
+    mm = t.empty((nblk, 2), dtype=t.int64, device=dev) if check else None       # allocated from the main stream's pool
+    cells = t.empty((nblk, 2), dtype=t.int64, pin_memory=True) if check else None
+    ob = Obs(tensor=xd, code=code, B=B, T=T, on_host=True, lengths=None, h2d_bytes=x.numel() * x.element_size(),
+             ready=[(bounds[k], bounds[k + 1], None, None) for k in range(nblk)],
+             alphabet=None if alphabet is None else int(alphabet))
+
+    def start(ob):
+        side.wait_stream(t.cuda.current_stream())
+        ready = []
+        with t.cuda.stream(side):
+            for k in range(nblk):
+                b0, b1 = bounds[k], bounds[k + 1]
+                xd[b0:b1].copy_(x[b0:b1], non_blocking=True)
+                cell = None
+                if check:
+                    _lib.call("khmm_symbol_range", b1 - b0, T, ptr(xd[b0:b1]), code, None, ptr(mm[k]), side.cuda_stream)
+                    cell = cells[k]
+                    cell.copy_(mm[k], non_blocking=True)   # read back on the side stream, before the block's event
+                ev = t.cuda.Event()
+                ev.record(side)
+                ready.append((b0, b1, ev, cell))
+        xd.record_stream(side)
+        if check:
+            mm.record_stream(side)
+        ob.ready = ready
+
+    ob.starter = start
+    return ob
 
 
 def prepare_obs(obs, symbols: bool, lengths=None, feature_dims: int = 0, u16_bits: bool = False,
-                alphabet: int = None, overlap: bool = False) -> Obs:
+                alphabet: int = None, overlap=None) -> Obs:
     """Move a batch of observations to the device.  symbols=True: integer symbols (B, T);
     else real observations (B, T) or (B, T, D).  `alphabet` (discrete models): the table size M the live symbols are
-    checked against, with the reference's IndexError / negative-index behaviour.  `overlap`: the caller consumes the
-    batch block by block (`Obs.ready`, the training loop): a large page-locked batch of unsigned symbols is then copied
-    on a side stream while the first blocks are already being worked on, its symbol check deferred to each block."""
+    checked against, with the reference's IndexError / negative-index behaviour.  `overlap` (`training_blocks` /
+    `decoding_blocks`): the caller consumes the batch block by block (`Obs.ready`): a large page-locked batch of unsigned
+    symbols is then copied on a side stream while the first blocks are already being worked on, its symbol check
+    deferred to each block."""
     t = require_cuda()
     was_u16 = (not isinstance(obs, t.Tensor)) and np.asarray(obs).dtype == np.uint16
     x = _as_tensor(obs)
@@ -256,10 +281,12 @@ def prepare_obs(obs, symbols: bool, lengths=None, feature_dims: int = 0, u16_bit
             x = x.to(t.float32)
         code = _lib.F32 if x.dtype == t.float32 else _lib.F64
     h2d = 0
-    if (overlap and on_host and symbols and lengths is None and code in _UNSIGNED_LIMIT and x.dim() == 2 and x.is_contiguous()
-            and x.numel() * x.element_size() >= OVERLAP_MIN_BYTES and x.is_pinned() and int(x.shape[1]) >= 1
-            and int(x.shape[0]) > 4 * 128 * t.cuda.get_device_properties(device()).multi_processor_count):
-        return _upload_overlapped(x, code, alphabet)
+    if (overlap is not None and on_host and symbols and lengths is None and code in _UNSIGNED_LIMIT and x.dim() == 2
+            and x.is_contiguous() and x.numel() * x.element_size() >= OVERLAP_MIN_BYTES and x.is_pinned()
+            and int(x.shape[1]) >= 1):
+        ends = overlap(int(x.shape[0]))
+        if ends is not None:
+            return _upload_overlapped(x, code, alphabet, ends)
     if on_host:
         h2d = x.numel() * x.element_size()
         x = x.to(device(), non_blocking=True)
@@ -303,7 +330,7 @@ def _to_host(x):
 def finish(ob: Obs, *tensors):
     """Return results on the side the observations came from."""
     if ob.on_host:
-        out = tuple(None if x is None else _to_host(x) for x in tensors)
+        out = tuple(None if x is None else (x.array if isinstance(x, HostResult) else _to_host(x)) for x in tensors)
     else:
         out = tensors
     return out if len(out) != 1 else out[0]
@@ -595,7 +622,11 @@ def viterbi(p: ModelParams, ob: Obs, path_dtype=None):
         raise ValueError("path_dtype %s cannot hold the states of a %d-state model" % (pname, N))
     path = t.zeros((ob.B, ob.T), dtype=path_dtype, device=dev)
     logp = t.empty((ob.B,), dtype=t.float64, device=dev)
-    ws_bytes = _lib.lib().khmm_viterbi_workspace_bytes(ob.B, ob.T, N)
+    # an overlapped upload (prepare_obs(..., overlap=decoding_blocks)) is decoded block by block, and the paths of a
+    # block travel back on a second side stream while the next block is decoded
+    blocks = [(0, ob.B)] if ob.ready is None else [None] * len(ob.ready)
+    bmax = ob.B if ob.ready is None else max(b1 - b0 for b0, b1, _, _ in ob.ready)
+    ws_bytes = _lib.lib().khmm_viterbi_workspace_bytes(bmax, ob.T, N)
     ws, wsp = workspace(ws_bytes, 256)      # cached: the backpointer workspace is 17 GB at config 3
     if p.kind == "gauss":
         # EXTENSION (include/khmm.h): log-density constants on the host, exactly as oracle.log_gaussian_pdf_1d forms them
@@ -603,16 +634,50 @@ def viterbi(p: ModelParams, ob: Obs, path_dtype=None):
         with np.errstate(divide="ignore"):
             logc = -np.log(sd) - np.log(np.sqrt(2.0 * np.pi))
         d_tab = _dev(np.stack([mean, sd, logc]), t.float64)
-        _lib.call("khmm_viterbi_gauss_f64", ob.B, ob.T, N, ptr(d_logpi), ptr(d_logA), ptr(d_tab), ptr(ob.tensor), ob.code,
-                  ptr(ob.lengths), wsp, ws_bytes, ptr(path), _PATH_CODES[pname], ptr(logp), stream_ptr())
-        return path, logp
-    with np.errstate(divide="ignore"):
-        logBsm = np.log(p.B.T)
-    d_logBsm = _dev(logBsm, t.float64)
-    _lib.call("khmm_viterbi_discrete_f64", ob.B, ob.T, N, p.M, ptr(d_logpi), ptr(d_logA), ptr(d_logBsm),
-              ptr(ob.tensor), ob.code, ptr(ob.lengths), wsp, ws_bytes, ptr(path), _PATH_CODES[pname],
-              ptr(logp), stream_ptr())
+    else:
+        with np.errstate(divide="ignore"):
+            logBsm = np.log(p.B.T)
+        d_logBsm = _dev(logBsm, t.float64)
+    host_path = back = None
+    if ob.ready is not None:
+        try:
+            host_path = t.empty((ob.B, ob.T), dtype=path_dtype, pin_memory=True)
+            back = _side_streams.get(("d2h", dev.index))
+            if back is None:
+                back = _side_streams[("d2h", dev.index)] = t.cuda.Stream(device=dev)
+        except RuntimeError:                # page-locked memory exhausted: results come back after the last block
+            host_path = back = None
+    main = t.cuda.current_stream()
+    for k, blk in enumerate(blocks):
+        b0, b1 = ob.wait_block(k) if blk is None else blk
+        len_c = None if ob.lengths is None else ob.lengths[b0:b1]
+        if p.kind == "gauss":
+            _lib.call("khmm_viterbi_gauss_f64", b1 - b0, ob.T, N, ptr(d_logpi), ptr(d_logA), ptr(d_tab),
+                      ptr(ob.tensor[b0:b1]), ob.code, ptr(len_c), wsp, ws_bytes, ptr(path[b0:b1]), _PATH_CODES[pname],
+                      ptr(logp[b0:b1]), stream_ptr())
+        else:
+            _lib.call("khmm_viterbi_discrete_f64", b1 - b0, ob.T, N, p.M, ptr(d_logpi), ptr(d_logA), ptr(d_logBsm),
+                      ptr(ob.tensor[b0:b1]), ob.code, ptr(len_c), wsp, ws_bytes, ptr(path[b0:b1]), _PATH_CODES[pname],
+                      ptr(logp[b0:b1]), stream_ptr())
+        if host_path is not None:
+            back.wait_stream(main)
+            with t.cuda.stream(back):
+                host_path[b0:b1].copy_(path[b0:b1], non_blocking=True)
+    if ob.ready is not None:
+        ob.ready = None
+        if host_path is not None:
+            path.record_stream(back)
+            host_logp = logp.cpu().numpy()          # synchronises the main stream
+            back.synchronize()
+            return HostResult(host_path.numpy()), HostResult(host_logp)
     return path, logp
+
+
+class HostResult:
+    """A result that is already on the host (block-wise paths of an overlapped Viterbi call); `finish` passes it on."""
+
+    def __init__(self, array):
+        self.array = array
 
 
 def gamma(alpha, beta, scale, kind=_lib.GAMMA_REFERENCE):

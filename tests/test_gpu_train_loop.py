@@ -268,7 +268,7 @@ def test_overlapped_upload_of_a_pinned_batch(K):
     rng = np.random.default_rng(171)
     host = torch.from_numpy(rng.integers(0, M, size=(B, T)).astype(np.uint16).view(np.int16)).pin_memory()
     assert host.numel() * 2 >= engine.OVERLAP_MIN_BYTES
-    ob = engine.prepare_obs(host.numpy().view(np.uint16), symbols=True, alphabet=M, overlap=True)
+    ob = engine.prepare_obs(host.numpy().view(np.uint16), symbols=True, alphabet=M, overlap=engine.training_blocks)
     assert ob.ready is not None and [b1 - b0 for b0, b1, _, _ in ob.ready] == [128 * sms, 256 * sms, B - 384 * sms]
     ob.wait_all()
     assert torch.equal(ob.tensor.cpu(), host)
@@ -289,3 +289,28 @@ def test_overlapped_upload_of_a_pinned_batch(K):
     torch.cuda.synchronize()
     assert np.array_equal(h3.initialProbabilities, before[0]) and np.array_equal(h3.transitionMatrix, before[1])
     assert np.array_equal(h3.emission_matrix(), before[2])
+
+
+def test_overlapped_upload_and_read_back_of_viterbi(K):
+    """`viterbi_batch` on a large page-locked batch decodes it block by block while it is still arriving and sends the
+    paths of a block back while the next one is decoded: bit-identical to the plain call, IndexError kept."""
+    import torch
+    from kerehmm_b200 import engine
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    N, M, T = 8, 16, 1500
+    B = 8 * 16 * sms + 5000
+    rng = np.random.default_rng(181)
+    host = torch.from_numpy(rng.integers(0, M, size=(B, T)).astype(np.uint8)).pin_memory()
+    assert host.numel() >= engine.OVERLAP_MIN_BYTES
+    ob = engine.prepare_obs(host, symbols=True, alphabet=M, overlap=engine.decoding_blocks)
+    assert ob.ready is not None and [b1 - b0 for b0, b1, _, _ in ob.ready] == [16 * sms, B - 32 * sms, 16 * sms]
+    h, _ = random_discrete(K, N, M, seed=182)
+    path1, logp1 = h.viterbi_batch(host, path_dtype="uint8")                     # overlapped
+    path2, logp2 = h.viterbi_batch(host.numpy().copy(), path_dtype="uint8")      # pageable copy: plain upload
+    assert isinstance(path1, np.ndarray) and path1.dtype == np.uint8 and path1.shape == (B, T)
+    assert np.array_equal(path1, path2) and np.array_equal(logp1, logp2)
+    bad = host.clone().pin_memory()
+    bad[B - 3, 7] = M
+    with pytest.raises(IndexError, match="index %d is out of bounds for axis 0 with size %d" % (M, M)):
+        h.viterbi_batch(bad, path_dtype="uint8")
+    torch.cuda.synchronize()
