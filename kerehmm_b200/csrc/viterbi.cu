@@ -608,6 +608,54 @@ __global__ void viterbi_backtrace_kernel(int64_t B, int64_t T, int N, const int3
     }
 }
 
+// Small batches: a WARP per sequence stages the backpointer rows of 32 steps in shared memory (they are contiguous:
+// psi[b][t][:]) with coalesced loads and one lane chases through the staged rows -- one DRAM latency per 32 steps
+// instead of one per step.  The thread-per-sequence kernel above is bound by that latency whatever the batch size
+// (T x ~0.55 us: 2.2 ms at T = 4096, a fifth of a lone T = 1000 sequence's three calls); it stays the kernel of large
+// batches, where reading every row (N bytes per step instead of one 32-byte sector) would cost more than the latency.
+constexpr int kBtChunk = 32, kBtWarps = 4;
+template <typename OUT>
+__global__ void __launch_bounds__(32 * kBtWarps)
+viterbi_backtrace_staged_kernel(int64_t B, int64_t T, int N, const int32_t *__restrict__ lengths,
+                                const uint8_t *__restrict__ psi, const int32_t *__restrict__ last_state,
+                                OUT *__restrict__ path) {
+    extern __shared__ __align__(16) unsigned char bt_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * kBtWarps + warp;
+    if (b >= B) return;
+    const int rows_bytes = (kBtChunk * N + 15) & ~15;
+    unsigned char *rows = bt_smem + (size_t)warp * (rows_bytes + kBtChunk * sizeof(int));
+    int *out = reinterpret_cast<int *>(rows + rows_bytes);
+    const int len = lengths ? lengths[b] : (int)T;
+    int st = last_state[b];
+    OUT *row = path + b * T;
+    const uint8_t *prow = psi + b * T * N;
+    if (lane == 0) row[len - 1] = (OUT)st;
+    const bool vec = (N % 16 == 0) && ((reinterpret_cast<uintptr_t>(psi) & 15) == 0);
+    for (int t_hi = len - 2; t_hi >= 0; t_hi -= kBtChunk) {
+        const int t_lo = max(t_hi - kBtChunk + 1, 0), n = t_hi - t_lo + 1;
+        const uint8_t *src = prow + (int64_t)(t_lo + 1) * N;          // rows t_lo+1 .. t_hi+1, contiguous
+        const int nbytes = n * N;
+        if (vec) {
+            for (int i = lane * 16; i < nbytes; i += 32 * 16)
+                *reinterpret_cast<uint4 *>(rows + i) = *reinterpret_cast<const uint4 *>(src + i);
+        } else {
+            for (int i = lane; i < nbytes; i += 32) rows[i] = src[i];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int j = n - 1; j >= 0; j--) {                        // step t = t_lo + j reads row t + 1 = staged row j
+                st = (int)rows[j * N + st];
+                out[j] = st;
+            }
+        }
+        st = __shfl_sync(0xffffffffu, st, 0);
+        __syncwarp();
+        if (lane < n) row[t_lo + lane] = (OUT)out[lane];
+        __syncwarp();
+    }
+}
+
 template <typename PSI>
 static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, const double *logA,
                        const double *logBsm, const void *obs, int obs_dtype, const int32_t *lengths, void *backptr,
@@ -657,6 +705,20 @@ static int run_viterbi(int64_t B, int64_t T, int N, int M, const double *logpi, 
             KHMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NT, smem, st>>>(B, T, N, M, logpi, logA, logBsm, obs, obs_dtype, lengths, psi, last, logp);
         KHMM_LAUNCH_CHECK("viterbi_generic_kernel");
+    }
+    if (sizeof(PSI) == 1 && B * (int64_t)N <= (1 << 21)) {
+        // small batch: staged warp-per-sequence backtrace (one memory latency per 32 steps)
+        const size_t sm = (size_t)kBtWarps * (((size_t)kBtChunk * N + 15) / 16 * 16 + kBtChunk * sizeof(int));
+        const unsigned g = (unsigned)((B + kBtWarps - 1) / kBtWarps);
+        const uint8_t *p8 = reinterpret_cast<const uint8_t *>(psi);
+        switch (path_dtype) {
+            case KHMM_U8: viterbi_backtrace_staged_kernel<uint8_t><<<g, 32 * kBtWarps, sm, st>>>(B, T, N, lengths, p8, last, (uint8_t *)path); break;
+            case KHMM_U16: viterbi_backtrace_staged_kernel<uint16_t><<<g, 32 * kBtWarps, sm, st>>>(B, T, N, lengths, p8, last, (uint16_t *)path); break;
+            case KHMM_I32: viterbi_backtrace_staged_kernel<int32_t><<<g, 32 * kBtWarps, sm, st>>>(B, T, N, lengths, p8, last, (int32_t *)path); break;
+            default: viterbi_backtrace_staged_kernel<int64_t><<<g, 32 * kBtWarps, sm, st>>>(B, T, N, lengths, p8, last, (int64_t *)path); break;
+        }
+        KHMM_LAUNCH_CHECK("viterbi_backtrace_staged_kernel");
+        return KHMM_OK;
     }
     int bt = 128;
     int bg = (int)((B + bt - 1) / bt);
