@@ -26,12 +26,31 @@ class DiscreteHMM(AbstractHMM):
     def sanity_check(self):
         """Takes no arguments, like the reference's override (discrete_hmm.py:24-27)."""
         super(DiscreteHMM, self).sanity_check()
-        sums = np.array([dist.probabilities.sum() for dist in self.emissionDistributions])
+        rows = self._shared_rows()
+        if rows is not None:
+            sums = rows.sum(axis=1)     # one vectorised sum instead of N Python-level ones (0.25 ms at 128 states)
+        else:
+            sums = np.array([dist.probabilities.sum() for dist in self.emissionDistributions])
         assert np.isclose(sums, 1.).all()
+
+    def _shared_rows(self):
+        """The (N, M) matrix whose rows the distribution objects view (installed by `_assign`), or None once any
+        distribution has been given another table."""
+        rows = getattr(self, "_emission_rows", None)
+        dists = self.emissionDistributions
+        if rows is None or len(dists) != rows.shape[0]:
+            return None
+        for d in dists:
+            if getattr(d.probabilities, "base", None) is not rows:
+                return None
+        return rows
 
     # -------------------------------------------------------------------------- packing
     def emission_matrix(self):
         """State-major (N, M) table assembled from the per-state distribution objects."""
+        rows = self._shared_rows()
+        if rows is not None:
+            return rows.copy()
         return np.stack([np.asarray(d.probabilities, dtype=np.float64) for d in self.emissionDistributions])
 
     def _params(self):
@@ -49,10 +68,12 @@ class DiscreteHMM(AbstractHMM):
         new arrays for pi/A, new distribution objects, a sanity_check after each."""
         self.initialProbabilities = pi
         self.sanity_check()
-        dists = []
+        rows = np.array(Bm, dtype=np.float64)          # one matrix of our own; distribution i views row i
+        dists = np.empty(self.nStates, dtype=object)
         for i in range(self.nStates):
-            dists.append(DiscreteDistribution.from_probabilities(Bm[i]))
-        self.emissionDistributions = np.array(dists)
+            dists[i] = DiscreteDistribution.from_row(rows[i])
+        self._emission_rows = rows
+        self.emissionDistributions = dists
         self.sanity_check()
         self.transitionMatrix = A
         self.sanity_check()

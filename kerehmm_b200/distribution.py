@@ -39,6 +39,15 @@ class DiscreteDistribution(Distribution):
         d.n = len(d.probabilities)
         return d
 
+    @classmethod
+    def from_row(cls, row):
+        """A distribution whose table IS `row` (a float64 row view of a matrix the caller owns; no copy) -- the N
+        distributions installed after a batched Baum-Welch pass share one (N, M) matrix this way."""
+        d = cls.__new__(cls)
+        d.probabilities = row
+        d.n = len(row)
+        return d
+
     def get_probability(self, observation, *args, **kwargs):
         return self.probabilities[observation]
 
