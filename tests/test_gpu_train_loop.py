@@ -280,6 +280,19 @@ def test_overlapped_upload_of_a_pinned_batch(K):
     np.testing.assert_allclose(h1.initialProbabilities, h2.initialProbabilities, rtol=2e-5, atol=1e-12)
     np.testing.assert_allclose(h1.transitionMatrix, h2.transitionMatrix, rtol=2e-5, atol=1e-12)
     np.testing.assert_allclose(h1.emission_matrix(), h2.emission_matrix(), rtol=2e-5, atol=1e-12)
+    # a consumer that does not work block by block (the SIMT E-step) waits for the whole upload
+    sub = host[:128 * sms * 4 + 300, :40].contiguous().pin_memory()
+    big_enough = engine.OVERLAP_MIN_BYTES
+    engine.OVERLAP_MIN_BYTES = 1 << 20
+    try:
+        h4, _ = random_discrete(K, N, M, seed=172)
+        h5, _ = random_discrete(K, N, M, seed=172)
+        h4.train_batch(sub.numpy().view(np.uint16), iterations=1, tensor_cores=False)
+        h5.train_batch(sub.numpy().view(np.uint16).copy(), iterations=1, tensor_cores=False)
+    finally:
+        engine.OVERLAP_MIN_BYTES = big_enough
+    np.testing.assert_allclose(h4.transitionMatrix, h5.transitionMatrix, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(h4.emission_matrix(), h5.emission_matrix(), rtol=1e-6, atol=1e-12)
     bad = host.clone().pin_memory()
     bad[B - 7, 11] = M + 5
     h3, _ = random_discrete(K, N, M, seed=172)

@@ -4,7 +4,7 @@ sys.path.insert(0, '.')
 import kerehmm_b200 as K
 from kerehmm_b200 import engine, _lib
 from oracle import hmm_oracle as O
-N, B, T = 1024, 4096, 64
+N, B, T = 1024, int(sys.argv[2]) if len(sys.argv) > 2 else 4096, 64
 mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 np.random.seed(5)
 pi, A, mean, sd = O.random_gaussian_model(N)
