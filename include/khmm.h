@@ -203,7 +203,7 @@ int khmm_emissions_gauss_full_f64(int64_t B, int64_t T, int N, int D, const doub
  * Fused forward-backward log-likelihood (no alpha/beta in HBM) for small state spaces
  * (N <= KHMM_SMALL_N_MAX), emission evaluation fused, everything but the observations in
  * registers: one thread per (sequence, direction) in packed FP32, or -- N = 5..8 -- one warp per
- * 16 sequences with the matrix-vector products as mma.sync tiles on split tf32 operands (same
+ * 16 sequences with the matrix-vector products as mma.sync tiles on split operands (same
  * fp32-class accuracy).  loglik[B] = sum_t log c_t (forward); loglik_bwd[B] (may be
  * NULL: forward only) = the same likelihood recovered from the backward recursion, which runs
  * concurrently with its own scaling s_t: log(sum_i pi_i b_i(o_0) beta_0(i)) = sum_t log s_t +

@@ -301,22 +301,40 @@ fwdbwd_small_kernel(int64_t B, int64_t T, int N, int M, const float *__restrict_
 //
 // The kernel above is bound by the FP32 pipe, and only 62 % of what it issues there is the matrix-vector product (the rest
 // is the emission density, the scaling and the row sum).  Here a warp owns 16 sequences of one direction and the product
-// (16 x 8) . (8 x 8) is one mma.sync.m16n8k8 (tf32 operands, fp32 accumulate), issued three times with split operands
-//     w M  ~  w_hi M_hi + w_hi M_lo + w_lo M_hi        (w_hi = the upper 19 bits of w, w_lo = w - w_hi exactly)
-// which keeps fp32-class accuracy (the dropped w_lo M_lo term is below 2^-21 of the product).  The fragment layouts make
+// (16 x 8) . (8 x 8) is one mma.sync.m16n8k8 (tf32 operands, fp32 accumulate) on split operands
+//     w M  ~  w_hi M_hi + (w_lo M_hi + w_hi M_lo)      (w_hi = the upper 19 bits of w, w_lo = w - w_hi exactly)
+// with the two correction terms -- 2^-11 of the product, so bf16 operands leave 2^-19 of it -- as ONE bf16 m16n8k16
+// whose K index runs over (w_lo, w_hi) against (M_hi; M_lo): two tensor-core instructions per step and fp32-class
+// accuracy (3e-8 relative on log P against float64 at config-2 size).  The fragment layouts make
 // the recursion shuffle-free: lane (g = lane / 4, c = lane % 4) receives D[g][2c], D[g][2c+1], D[g+8][2c], D[g+8][2c+1]
 // and has to supply A[g][c], A[g+8][c], A[g][c+4], A[g+8][c+4] -- so the K index is permuted (k = c -> state 2c,
 // k = c + 4 -> state 2c + 1, the rows of the matrix operand permuted to match) and a lane's outputs ARE its next inputs.
 // A lane therefore owns the state pair (2c, 2c+1) of sequences g and g + 8: two packed emission evaluations per step, two
-// packed multiplies, and a fourth mma against a matrix of ones that returns the row sums (only their exponent is used:
-// the scale factors stay exact powers of two, taken every other step as above).  What is left on the FP32 pipe is a
-// quarter of the kernel above per sequence; the step is bound by the eight MUFU.EX2 per sequence instead.
+// packed multiplies, and every other step a third mma against a matrix of ones that returns the row sums (only their
+// exponent is used: the scale factors stay exact powers of two, as above).  What is left on the FP32 pipe is a quarter of
+// the kernel above per sequence; the step costs the SUM of what its instruction classes cost the scheduler
+// (profiles/r2_c2_mma8_ablation.txt): an mma.sync holds it for ~8 cycles, a packed FP32 instruction ~2.2.
 __device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                  uint32_t b0, uint32_t b1, const float (&c)[4]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
                  : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
 }
+__device__ __forceinline__ void mma_m16n8k16_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                  uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// two floats -> packed bf16 pair, `lo` in the lower half (the lower k index of a fragment register)
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+#ifndef KHMM_MMA8_BF16CORR
+#define KHMM_MMA8_BF16CORR 1     /* 0: the two correction terms as two more tf32 mma (0.295 against 0.288 ms at config 2) */
+#endif
 __device__ __forceinline__ uint32_t tf32_rna(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -364,6 +382,10 @@ __device__ __forceinline__ void mma8_body(int64_t B, int64_t T, int N, int M, co
     const float m0 = m_elem(j0, g), m1 = m_elem(j1, g);
     const uint32_t bh0 = tf32_rna(m0), bh1 = tf32_rna(m1);
     const uint32_t bl0 = tf32_rna(m0 - __uint_as_float(bh0)), bl1 = tf32_rna(m1 - __uint_as_float(bh1));
+    // the two correction terms w_lo M_hi + w_hi M_lo as ONE bf16 m16n8k16 (k < 8: w_lo against M_hi, k >= 8: w_hi against
+    // M_lo; natural state order): they are 2^-11 of the product, so bf16's 2^-9 leaves 2^-19 of it
+    const uint32_t bc0 = pack_bf16(__uint_as_float(bh0), __uint_as_float(bh1));
+    const uint32_t bc1 = pack_bf16(m0 - __uint_as_float(bh0), m1 - __uint_as_float(bh1));
     const uint32_t kOne = 0x3f800000u;
     const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -426,8 +448,15 @@ __device__ __forceinline__ void mma8_body(int64_t B, int64_t T, int N, int M, co
     };
     auto product = [&](float (&d)[4]) {                      // d = (w M) of both sequences, from h / l
         mma_m16n8k8_tf32(d, h[0], h[1], h[2], h[3], bh0, bh1, zero4);
+#if KHMM_MMA8_BF16CORR
+        // fragment order of w / h / l: [0] = (g, 2c), [1] = (g+8, 2c), [2] = (g, 2c+1), [3] = (g+8, 2c+1)
+        mma_m16n8k16_bf16(d, pack_bf16(__uint_as_float(l[0]), __uint_as_float(l[2])),
+                          pack_bf16(__uint_as_float(l[1]), __uint_as_float(l[3])), pack_bf16(w[0], w[2]),
+                          pack_bf16(w[1], w[3]), bc0, bc1);
+#else
         mma_m16n8k8_tf32(d, h[0], h[1], h[2], h[3], bl0, bl1, d);
         mma_m16n8k8_tf32(d, l[0], l[1], l[2], l[3], bh0, bh1, d);
+#endif
     };
     auto times = [&](const float (&d)[4], float2 b0, float2 b1, bool a0, bool a1) {   // w = d . b where live
         if (a0) { w[0] = d[0] * b0.x; w[2] = d[1] * b0.y; }
