@@ -194,10 +194,12 @@ def training_blocks(B: int):
 
 
 def decoding_blocks(B: int):
-    """Row blocks for Viterbi (a warp per sequence, eight warps per CTA): a small first block so that decoding starts
-    early, and a small last one so that only its paths are still to be copied back when the kernels end."""
+    """Row blocks for Viterbi (a warp per sequence, eight warps per CTA; r = two CTA rounds): a small first block so that
+    decoding starts early and a small last one so that only its paths are still to be copied back when the kernels end,
+    each with a three times larger neighbour -- with eight ranks copying at once the bulk of the batch takes longer to
+    arrive (and its paths longer to leave) than the small block alone takes to decode."""
     r = 2 * 8 * torch().cuda.get_device_properties(device()).multi_processor_count
-    return [r, B - r, B] if B > 8 * r else None
+    return [r, 4 * r, B - 4 * r, B - r, B] if B > 16 * r else None
 
 
 def _upload_overlapped(x, code: int, alphabet, ends):

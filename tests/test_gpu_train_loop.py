@@ -310,13 +310,13 @@ def test_overlapped_upload_and_read_back_of_viterbi(K):
     import torch
     from kerehmm_b200 import engine
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    N, M, T = 8, 16, 1500
-    B = 8 * 16 * sms + 5000
+    N, M, T = 8, 16, 900
+    B = 16 * 16 * sms + 5000
     rng = np.random.default_rng(181)
     host = torch.from_numpy(rng.integers(0, M, size=(B, T)).astype(np.uint8)).pin_memory()
     assert host.numel() >= engine.OVERLAP_MIN_BYTES
     ob = engine.prepare_obs(host, symbols=True, alphabet=M, overlap=engine.decoding_blocks)
-    assert ob.ready is not None and [b1 - b0 for b0, b1, _, _ in ob.ready] == [16 * sms, B - 32 * sms, 16 * sms]
+    assert ob.ready is not None and [b1 - b0 for b0, b1, _, _ in ob.ready] == [16 * sms, 48 * sms, B - 128 * sms, 48 * sms, 16 * sms]
     h, _ = random_discrete(K, N, M, seed=182)
     path1, logp1 = h.viterbi_batch(host, path_dtype="uint8")                     # overlapped
     path2, logp2 = h.viterbi_batch(host.numpy().copy(), path_dtype="uint8")      # pageable copy: plain upload
